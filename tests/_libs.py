@@ -81,3 +81,100 @@ def golden_raw(name):
         for line in f:
             out += line.rstrip(b"\n").split(b"\t")[0]
     return bytes(out)
+
+
+# ---------------------------------------------------------------- BGZF helpers
+import struct, zlib
+
+BGZF_EOF = bytes.fromhex("1f8b08040000000000ff0600424302001b0003000000000000000000")
+
+
+def bgzf_block(payload, level=6, raw_deflate=None):
+    """One BGZF block the way bgzf_compress's zlib arm writes it (bgzf.c:624-683):
+    deflateInit2(level, Z_DEFLATED, -15, 8, Z_DEFAULT_STRATEGY) + header + CRC32 + ISIZE."""
+    if raw_deflate is None:
+        if level == 0:   # bgzf.c:573-580 stored block
+            raw_deflate = b"\x01" + struct.pack("<HH", len(payload), len(payload) ^ 0xffff) + payload
+        else:
+            c = zlib.compressobj(level, zlib.DEFLATED, -15, 8)
+            raw_deflate = c.compress(payload) + c.flush()
+    bsize = 18 + len(raw_deflate) + 8
+    assert bsize <= 65536
+    hdr = b"\x1f\x8b\x08\x04\0\0\0\0\0\xff\x06\0BC\x02\0" + struct.pack("<H", bsize - 1)
+    return hdr + raw_deflate + struct.pack("<II", zlib.crc32(payload) & 0xffffffff, len(payload))
+
+
+def bgzf_file(data, level=6, block=0xff00, eof=True):
+    out = bytearray()
+    for i in range(0, len(data), block):
+        out += bgzf_block(data[i:i + block], level)
+    if eof:
+        out += BGZF_EOF
+    return bytes(out)
+
+
+def orc_inflate_raw(src, cap=65536):
+    o = orc()
+    out = (C.c_uint8 * max(1, cap))()
+    dl = C.c_uint64(0); used = C.c_uint64(0)
+    rc = o.orc_inflate_raw(buf(src), C.c_uint64(len(src)), out, C.c_uint64(cap), C.byref(dl), C.byref(used))
+    if rc:
+        return None, 0
+    return bytes(out[: dl.value]), used.value
+
+
+def orc_bgzf_inflate_block(block):
+    o = orc()
+    out = (C.c_uint8 * 65536)()
+    rc = o.orc_bgzf_inflate_block(buf(block), C.c_uint32(len(block)), out)
+    return rc, (bytes(out[:rc]) if rc >= 0 else b"")
+
+
+def orc_bgzf_scan(data):
+    o = orc()
+    o.orc_bgzf_scan.restype = C.c_long
+    cap = len(data) // 26 + 2
+    off = (C.c_uint64 * cap)(); ln = (C.c_uint32 * cap)()
+    n = o.orc_bgzf_scan(buf(data), C.c_uint64(len(data)), off, ln, C.c_long(cap))
+    if n < 0:
+        return n, []
+    return n, [(off[i], ln[i]) for i in range(n)]
+
+
+def ref_bgzf_read_all(data, threads=0):
+    """Decompress a whole BGZF file image with the compiled reference: hopen("mem:") ->
+    bgzf_hopen -> [bgzf_mt] -> bgzf_read loop.  Returns (bytes, errcode)."""
+    r = ref()
+    r.hopen.restype = C.c_void_p
+    r.hopen.argtypes = [C.c_char_p, C.c_char_p, C.c_void_p, C.c_size_t]
+    r.bgzf_hopen.restype = C.c_void_p
+    r.bgzf_hopen.argtypes = [C.c_void_p, C.c_char_p]
+    r.bgzf_read.restype = C.c_ssize_t
+    r.bgzf_read.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t]
+    r.bgzf_close.argtypes = [C.c_void_p]
+    r.bgzf_mt.argtypes = [C.c_void_p, C.c_int, C.c_int]
+    # the mem: backend takes ownership of a malloc'ed buffer and frees it at close (hfile.c:837)
+    libc = C.CDLL(None)
+    libc.malloc.restype = C.c_void_p
+    libc.malloc.argtypes = [C.c_size_t]
+    mem = libc.malloc(max(1, len(data)))
+    C.memmove(mem, bytes(data), len(data))
+    hf = r.hopen(b"mem:", b"r:", mem, len(data))
+    assert hf
+    fp = r.bgzf_hopen(hf, b"r")
+    assert fp
+    if threads:
+        r.bgzf_mt(fp, threads, 256)
+    out = bytearray()
+    chunk = (C.c_uint8 * (1 << 20))()
+    err = 0
+    while True:
+        n = r.bgzf_read(fp, chunk, len(chunk))
+        if n < 0:
+            err = 1
+            break
+        if n == 0:
+            break
+        out += bytes(chunk[:n])
+    r.bgzf_close(fp)
+    return bytes(out), err
