@@ -1,0 +1,134 @@
+"""htslib_b200 — Python face of libhtsgpu.so (hand-written sm_100a CUDA behind a C ABI).
+
+The library is the product; this module only loads it with ctypes and passes raw pointers
+(torch is used by callers for device memory and streams, never for compute).  There is no CPU
+fallback: if the shared library is missing, importing `htslib_b200.lib()` raises.
+"""
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libhtsgpu.so")
+HEADER_PATH = os.path.join(os.path.dirname(_HERE), "include", "htsgpu.h")
+
+HGPU_OK = 0
+BGZF_ERR_ZLIB, BGZF_ERR_CRC, BGZF_ERR_HEADER, BGZF_ERR_SPACE = -1, -2, -3, -4
+RANS_ERR = -1
+
+_lib = None
+u8p = C.POINTER(C.c_uint8)
+
+
+class HgpuError(RuntimeError):
+    pass
+
+
+def lib():
+    """Load libhtsgpu.so (built in-tree by __graft_entry__.build() / htslib_b200/build.py)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise HgpuError("libhtsgpu.so is not built (%s); run `python -c 'import __graft_entry__ as g; g.build()'`. "
+                        "There is no CPU fallback." % LIB_PATH)
+    L = C.CDLL(LIB_PATH)
+    vp, u32, u64, i32 = C.c_void_p, C.c_uint32, C.c_uint64, C.c_int32
+    L.hgpu_create.restype = vp
+    L.hgpu_create.argtypes = [C.c_int]
+    L.hgpu_destroy.argtypes = [vp]
+    L.hgpu_last_error.restype = C.c_char_p
+    L.hgpu_version.restype = C.c_char_p
+    L.hgpu_launch_count.restype = u64
+    L.hgpu_bgzf_inflate_batch_dev.argtypes = [vp, vp, vp, vp, u32, vp, vp, vp, vp, vp, vp]
+    L.hgpu_bgzf_scan.restype = C.c_long
+    L.hgpu_bgzf_scan.argtypes = [vp, u64, vp, vp, vp, C.c_long]
+    L.hgpu_bgzf_inflate_file_host.argtypes = [vp, vp, u64, vp, u64, C.POINTER(u64), C.POINTER(C.c_long)]
+    L.hgpu_crc32.restype = u32
+    L.hgpu_crc32.argtypes = [vp, u32, vp, C.c_size_t]
+    L.hgpu_rans_nx16_decode_batch_dev.argtypes = [vp, vp, vp, vp, u32, vp, vp, vp, vp, vp, u32, vp]
+    L.hgpu_rans_nx16_decode_batch_host.argtypes = [vp, vp, vp, vp, u32, vp, vp, vp, vp, vp]
+    L.rans_uncompress_to_4x16.restype = vp
+    L.rans_uncompress_to_4x16.argtypes = [vp, C.c_uint, vp, C.POINTER(C.c_uint)]
+    L.rans_uncompress_4x16.restype = vp
+    L.rans_uncompress_4x16.argtypes = [vp, C.c_uint, C.POINTER(C.c_uint)]
+    L.hts_crc32.restype = u32
+    L.hts_crc32.argtypes = [u32, vp, C.c_size_t]
+    _lib = L
+    return L
+
+
+def last_error():
+    return lib().hgpu_last_error().decode()
+
+
+def check(rc, what=""):
+    if rc != HGPU_OK:
+        raise HgpuError("%s failed: rc=%d (%s)" % (what, rc, last_error()))
+
+
+class Context:
+    """hgpu_ctx wrapper: one device, its streams and scratch."""
+
+    def __init__(self, device=-1):
+        self.h = lib().hgpu_create(device)
+        if not self.h:
+            raise HgpuError("hgpu_create failed: %s" % last_error())
+
+    def close(self):
+        if self.h:
+            lib().hgpu_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ---- device-pointer entry points; tensors are torch CUDA tensors ----
+    def bgzf_inflate_dev(self, d_in, d_in_off, d_in_len, d_out, d_out_off, d_out_cap, d_out_len, d_status, stream=0):
+        n = d_in_len.numel()
+        check(lib().hgpu_bgzf_inflate_batch_dev(self.h, d_in.data_ptr(), d_in_off.data_ptr(), d_in_len.data_ptr(), n,
+                                                d_out.data_ptr(), d_out_off.data_ptr(), d_out_cap.data_ptr(),
+                                                d_out_len.data_ptr(), d_status.data_ptr(), stream), "bgzf_inflate_batch_dev")
+
+    def rans_nx16_decode_dev(self, d_in, d_in_off, d_in_len, d_out, d_out_off, d_out_len, d_got, d_status, max_out_len, stream=0):
+        n = d_in_len.numel()
+        check(lib().hgpu_rans_nx16_decode_batch_dev(self.h, d_in.data_ptr(), d_in_off.data_ptr(), d_in_len.data_ptr(), n,
+                                                    d_out.data_ptr(), d_out_off.data_ptr(), d_out_len.data_ptr(),
+                                                    d_got.data_ptr(), d_status.data_ptr(), int(max_out_len), stream),
+              "rans_nx16_decode_batch_dev")
+
+    # ---- host-pointer entry points; buffers are numpy uint8 arrays (or pinned torch tensors' .numpy()) ----
+    def bgzf_inflate_file_host(self, file_np, out_np):
+        out_len = C.c_uint64(0)
+        bad = C.c_long(-1)
+        rc = lib().hgpu_bgzf_inflate_file_host(self.h, file_np.ctypes.data, file_np.size, out_np.ctypes.data, out_np.size,
+                                               C.byref(out_len), C.byref(bad))
+        return rc, out_len.value, bad.value
+
+    def rans_nx16_decode_host(self, in_np, in_off, in_len, out_np, out_off, out_len):
+        import numpy as np
+        n = len(in_len)
+        got = np.zeros(n, dtype=np.uint32)
+        st = np.zeros(n, dtype=np.int32)
+        check(lib().hgpu_rans_nx16_decode_batch_host(self.h, in_np.ctypes.data, in_off.ctypes.data, in_len.ctypes.data, n,
+                                                     out_np.ctypes.data, out_off.ctypes.data, out_len.ctypes.data,
+                                                     got.ctypes.data, st.ctypes.data), "rans_nx16_decode_batch_host")
+        return got, st
+
+    def crc32(self, data, crc=0):
+        import numpy as np
+        a = np.frombuffer(data, dtype=np.uint8)
+        return lib().hgpu_crc32(self.h, crc, a.ctypes.data if a.size else None, a.size)
+
+
+def bgzf_scan(file_np):
+    """BSIZE-chain walk: returns (off u64[n], len u32[n], isize u32[n]) or raises on a bad block."""
+    import numpy as np
+    n = lib().hgpu_bgzf_scan(file_np.ctypes.data, file_np.size, None, None, None, 0)
+    if n < 0:
+        raise HgpuError("bad BGZF block %d" % (-1 - n))
+    off = np.zeros(n, dtype=np.uint64); ln = np.zeros(n, dtype=np.uint32); isz = np.zeros(n, dtype=np.uint32)
+    lib().hgpu_bgzf_scan(file_np.ctypes.data, file_np.size, off.ctypes.data, ln.ctypes.data, isz.ctypes.data, n)
+    return off, ln, isz

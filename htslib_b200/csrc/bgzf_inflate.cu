@@ -1,0 +1,526 @@
+// BGZF block inflate for sm_100a: one warp per <=64 KiB BGZF block.
+//
+// Replaces, for a batch of blocks, what one htslib worker does per job in bgzf_decode_func
+// (bgzf.c:1373-1384): check_header (:896-903), inflate_block (:808-824) -> bgzf_uncompress
+// (:762-804, raw inflate with a 32 KiB window) and the CRC32 comparison against the footer.
+// DEFLATE itself (RFC 1951) and CRC-32 live in zlib/libdeflate for the reference; here they are
+// written from the RFC for the GPU.
+//
+// Kernel structure (v1 — "uniform decode"): all 32 lanes of the warp walk the Huffman stream in
+// lock step (same bit buffer, table lookups broadcast from shared memory), so every lane knows
+// every token without shuffles; literal bytes are stored by lane 0 and LZ77 matches are copied
+// by the whole warp (lane i moves byte i, i+32, ...).  Decode tables are built by the warp in
+// parallel (canonical code assignment by __match_any_sync ranks) into shared memory:
+//   litlen: 10-bit root + sub-tables, dist: 8-bit root + sub-tables, 32-bit entries
+//     [31:16] value (literal / length base / distance base / sub-table offset)
+//     [15:8]  extra-bit count (or sub-table index bits)
+//     [7:4]   kind   [3:0] code bits consumed
+// The CRC-32 of the output is computed by the same warp: 32 equal chunks, slice-by-4 per lane,
+// then a log-step combine with carry-less multiplications mod the CRC polynomial.
+#include "hgpu_internal.h"
+
+namespace {
+
+constexpr int LIT_ROOT = 10, DST_ROOT = 8;
+constexpr int LIT_TABLE = (1 << LIT_ROOT) + 1334;   // zlib "enough 286 10 15" = 1332 sub-table slots
+constexpr int DST_TABLE = (1 << DST_ROOT) + 600;    // generous for 30 symbols / 8 root bits
+constexpr int CL_TABLE = 128;
+
+enum : uint32_t { K_LIT = 0, K_LEN = 1, K_EOB = 2, K_SUB = 3, K_BAD = 4, K_DIST = 5 };
+#define ENTRY(value, xb, kind, nbits) (((uint32_t)(value) << 16) | ((uint32_t)(xb) << 8) | ((uint32_t)(kind) << 4) | (uint32_t)(nbits))
+constexpr uint32_t BAD_ENTRY = ENTRY(0, 0, K_BAD, 0);
+
+struct InflateSmem {
+    uint32_t lit[LIT_TABLE];
+    uint32_t dst[DST_TABLE];
+    uint32_t cl[CL_TABLE];
+    uint16_t code[320];      // canonical code per symbol
+    uint8_t  lens[320];
+    uint32_t count[16];
+    uint32_t next[16];
+    uint32_t sub_alloc;
+};
+
+__constant__ uint16_t c_len_base[29] = {3,4,5,6,7,8,9,10,11,13,15,17,19,23,27,31,35,43,51,59,67,83,99,115,131,163,195,227,258};
+__constant__ uint8_t  c_len_xtra[29] = {0,0,0,0,0,0,0,0,1,1,1,1,2,2,2,2,3,3,3,3,4,4,4,4,5,5,5,5,0};
+__constant__ uint16_t c_dst_base[30] = {1,2,3,4,5,7,9,13,17,25,33,49,65,97,129,193,257,385,513,769,1025,1537,2049,3073,4097,6145,8193,12289,16385,24577};
+__constant__ uint8_t  c_dst_xtra[30] = {0,0,0,0,1,1,2,2,3,3,4,4,5,5,6,6,7,7,8,8,9,9,10,10,11,11,12,12,13,13};
+__constant__ uint8_t  c_cl_order[19] = {16,17,18,0,8,7,9,6,10,5,11,4,12,3,13,2,14,1,15};
+
+__device__ uint32_t g_crc_tab[4][256];      // slice-by-4 tables, filled once by crc_init_kernel
+
+__global__ void crc_init_kernel()
+{
+    uint32_t i = threadIdx.x;
+    uint32_t c = i;
+    for (int k = 0; k < 8; k++) c = (c >> 1) ^ (0xEDB88320u & (0u - (c & 1)));
+    g_crc_tab[0][i] = c;
+    __syncthreads();
+    uint32_t c1 = g_crc_tab[0][c & 0xff] ^ (c >> 8);
+    g_crc_tab[1][i] = c1;
+    uint32_t c2 = g_crc_tab[0][c1 & 0xff] ^ (c1 >> 8);
+    g_crc_tab[2][i] = c2;
+    uint32_t c3 = g_crc_tab[0][c2 & 0xff] ^ (c2 >> 8);
+    g_crc_tab[3][i] = c3;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Bit reader: warp-uniform, 64-bit buffer refilled with aligned 32-bit words.
+// ---------------------------------------------------------------------------------------------
+struct Bits {
+    const uint32_t *w;     // next aligned word to load
+    const uint32_t *wend;  // first word entirely past the input
+    uint64_t buf;
+    int cnt;               // valid bits in buf
+    int64_t avail;         // bits of real input not yet moved into buf (may go negative = overrun)
+};
+
+__device__ __forceinline__ void bits_init(Bits &b, const uint8_t *p, uint32_t nbytes)
+{
+    uintptr_t a = reinterpret_cast<uintptr_t>(p);
+    uint32_t mis = (uint32_t)(a & 3);
+    b.w = reinterpret_cast<const uint32_t *>(a - mis);
+    b.wend = reinterpret_cast<const uint32_t *>((a + nbytes + 3) & ~(uintptr_t)3);
+    b.buf = 0; b.cnt = 0;
+    b.avail = (int64_t)nbytes * 8;
+    if (mis) {
+        uint32_t v = b.w < b.wend ? *b.w : 0;
+        b.w++;
+        b.buf = v >> (8 * mis);
+        b.cnt = 32 - 8 * (int)mis;
+        b.avail -= b.cnt;
+    }
+}
+
+// guarantee >= 32 valid bits (zero-padded past the end; overrun is detected via avail)
+__device__ __forceinline__ void bits_fill(Bits &b)
+{
+    if (b.cnt <= 32) {
+        uint32_t v = b.w < b.wend ? __ldg(b.w) : 0;
+        b.w++;
+        b.buf |= (uint64_t)v << b.cnt;
+        b.cnt += 32;
+        b.avail -= 32;
+    }
+}
+__device__ __forceinline__ uint32_t bits_peek(const Bits &b, int n) { return (uint32_t)b.buf & ((1u << n) - 1u); }
+__device__ __forceinline__ void bits_drop(Bits &b, int n) { b.buf >>= n; b.cnt -= n; }
+__device__ __forceinline__ uint32_t bits_get(Bits &b, int n) { uint32_t v = bits_peek(b, n); bits_drop(b, n); return v; }
+// true once more bits were consumed than the input holds
+__device__ __forceinline__ bool bits_overrun(const Bits &b) { return b.avail + b.cnt < 0; }
+
+// ---------------------------------------------------------------------------------------------
+// Huffman table construction (warp-parallel).  lens[0..n) in shared memory.
+// Returns 0 ok, -1 invalid (over-subscribed, or incomplete where zlib refuses it).
+// kind_of(sym) supplies the entry payload.
+// ---------------------------------------------------------------------------------------------
+template <int ROOT, int CAP, typename MakeEntry>
+__device__ int build_table(InflateSmem &s, uint32_t *table, int n, bool allow_single, MakeEntry make)
+{
+    const uint32_t lane = hgpu_lane();
+    __syncwarp();
+    if (lane < 16) s.count[lane] = 0;
+    for (int i = lane; i < CAP; i += 32) table[i] = BAD_ENTRY;
+    if (lane == 0) s.sub_alloc = 1u << ROOT;
+    __syncwarp();
+    for (int i = lane; i < n; i += 32) atomicAdd(&s.count[s.lens[i]], 1u);
+    __syncwarp();
+    // canonical first codes + Kraft check (zlib inftrees.c: over-subscribed -> error; incomplete
+    // only tolerated when the longest code is 1 bit)
+    int maxlen = 0;
+    int64_t left = 1;
+    uint32_t code = 0;
+    bool over = false;
+    for (int l = 1; l <= 15; l++) {
+        uint32_t c = s.count[l];
+        left = (left << 1) - (int64_t)c;
+        if (left < 0) over = true;
+        if (c) maxlen = l;
+        code = (code + (l > 1 ? s.count[l - 1] : 0)) << 1;
+        if (l == 1) code = 0;
+        if (lane == 0) s.next[l] = code;
+    }
+    if (over) return -1;
+    if (maxlen == 0) return allow_single ? 0 : -1;       // no codes at all: every lookup is invalid
+    if (left > 0 && !(allow_single && maxlen == 1)) return -1;
+    __syncwarp();
+    // per-symbol canonical codes, in symbol order: rank within its length class
+    for (int base = 0; base < n; base += 32) {
+        int i = base + lane;
+        uint32_t l = i < n ? s.lens[i] : 0;
+        uint32_t peers = __match_any_sync(0xffffffffu, l);
+        uint32_t rank = __popc(peers & hgpu_lanemask_lt());
+        if (l) s.code[i] = (uint16_t)(s.next[l] + rank);
+        __syncwarp();
+        if (l && rank + 1 == (uint32_t)__popc(peers)) s.next[l] += __popc(peers);   // last peer bumps the class
+        __syncwarp();
+    }
+    // root entries for short codes; longest length per root prefix for long ones
+    for (int i = lane; i < n; i += 32) {
+        uint32_t l = s.lens[i];
+        if (!l) continue;
+        uint32_t rev = __brev((uint32_t)s.code[i]) >> (32 - l);
+        if (l <= ROOT) {
+            uint32_t e = make(i, l);
+            for (uint32_t k = rev; k < (1u << ROOT); k += 1u << l) table[k] = e;
+        } else {
+            // temporarily keep the max length of the group in the root slot (kind K_SUB, value 0)
+            atomicMax(&table[rev & ((1u << ROOT) - 1)], ENTRY(0, l - ROOT, K_SUB, ROOT) | 0x80000000u);
+        }
+    }
+    __syncwarp();
+    // allocate sub-tables
+    for (uint32_t k = lane; k < (1u << ROOT); k += 32) {
+        uint32_t e = table[k];
+        if (e & 0x80000000u) {
+            uint32_t sub_bits = (e >> 8) & 0xff;
+            uint32_t off = atomicAdd(&s.sub_alloc, 1u << sub_bits);
+            table[k] = off + (1u << sub_bits) <= (uint32_t)CAP ? ENTRY(off, sub_bits, K_SUB, ROOT) : BAD_ENTRY;
+        }
+    }
+    __syncwarp();
+    if (s.sub_alloc > (uint32_t)CAP) return -1;      // cannot happen for a valid code set
+    for (int i = lane; i < n; i += 32) {
+        uint32_t l = s.lens[i];
+        if (l <= ROOT) continue;
+        uint32_t rev = __brev((uint32_t)s.code[i]) >> (32 - l);
+        uint32_t root = table[rev & ((1u << ROOT) - 1)];
+        uint32_t off = root >> 16, sub_bits = (root >> 8) & 0xff;
+        uint32_t e = make(i, l - ROOT);
+        for (uint32_t k = rev >> ROOT; k < (1u << sub_bits); k += 1u << (l - ROOT)) table[off + k] = e;
+    }
+    __syncwarp();
+    return 0;
+}
+
+__device__ __forceinline__ uint32_t lit_entry(int sym, uint32_t nbits)
+{
+    if (sym < 256) return ENTRY(sym, 0, K_LIT, nbits);
+    if (sym == 256) return ENTRY(0, 0, K_EOB, nbits);
+    if (sym > 285) return ENTRY(0, 0, K_BAD, nbits);
+    return ENTRY(c_len_base[sym - 257], c_len_xtra[sym - 257], K_LEN, nbits);
+}
+__device__ __forceinline__ uint32_t dst_entry(int sym, uint32_t nbits)
+{
+    if (sym > 29) return ENTRY(0, 0, K_BAD, nbits);
+    return ENTRY(c_dst_base[sym], c_dst_xtra[sym], K_DIST, nbits);
+}
+__device__ __forceinline__ uint32_t cl_entry(int sym, uint32_t nbits) { return ENTRY(sym, 0, K_LIT, nbits); }
+
+template <int ROOT>
+__device__ __forceinline__ uint32_t lookup(const uint32_t *table, Bits &b)
+{
+    uint32_t e = table[bits_peek(b, ROOT)];
+    if (((e >> 4) & 15) == K_SUB) {
+        bits_drop(b, ROOT);
+        e = table[(e >> 16) + bits_peek(b, (e >> 8) & 0xff)];
+    }
+    bits_drop(b, e & 15);
+    return e;
+}
+
+// ---------------------------------------------------------------------------------------------
+// CRC-32
+// ---------------------------------------------------------------------------------------------
+__device__ uint32_t multmodp(uint32_t a, uint32_t b)       // a*b mod P, reflected (zlib crc32.c)
+{
+    uint32_t p = 0;
+    for (uint32_t m = 1u << 31; m; m >>= 1) {
+        if (a & m) p ^= b;
+        b = (b & 1) ? (b >> 1) ^ 0xEDB88320u : b >> 1;
+    }
+    return p;
+}
+
+// x^(8*nbytes) mod P
+__device__ uint32_t xpow_bytes(uint32_t nbytes)
+{
+    uint32_t p = 1u << 31;            // x^0
+    uint32_t sq = 1u << 23;           // x^8  (one byte)
+    while (nbytes) {
+        if (nbytes & 1) p = multmodp(sq, p);
+        sq = multmodp(sq, sq);
+        nbytes >>= 1;
+    }
+    return p;
+}
+
+// CRC-32 of out[0..n) by the whole warp.  Caller must have made the bytes visible.
+__device__ uint32_t warp_crc32(const uint8_t *out, uint32_t n)
+{
+    const uint32_t lane = hgpu_lane();
+    uint32_t c = n / 32, r = n % 32;
+    // lane 0 takes c + r bytes, every other lane c bytes
+    uint32_t beg = lane == 0 ? 0 : r + lane * c;
+    uint32_t len = lane == 0 ? c + r : c;
+    uint32_t crc = 0xffffffffu;
+    const uint8_t *p = out + beg, *e = p + len;
+    while (p < e && (reinterpret_cast<uintptr_t>(p) & 3)) crc = g_crc_tab[0][(crc ^ *p++) & 0xff] ^ (crc >> 8);
+    while (e - p >= 4) {
+        crc ^= *reinterpret_cast<const uint32_t *>(p);
+        crc = g_crc_tab[3][crc & 0xff] ^ g_crc_tab[2][(crc >> 8) & 0xff] ^ g_crc_tab[1][(crc >> 16) & 0xff] ^ g_crc_tab[0][crc >> 24];
+        p += 4;
+    }
+    while (p < e) crc = g_crc_tab[0][(crc ^ *p++) & 0xff] ^ (crc >> 8);
+    crc = ~crc;
+    if (c == 0) return __shfl_sync(0xffffffffu, crc, 0);
+    // combine: crc(A||B) = crc(A) * x^(8|B|) ^ crc(B)   (crc32_combine).  Level d merges blocks
+    // of d lanes; the right-hand block is always d*c bytes long.
+    uint32_t xp = xpow_bytes(c);
+    for (int d = 1; d < 32; d <<= 1) {
+        uint32_t right = __shfl_down_sync(0xffffffffu, crc, d);
+        if ((lane & (2 * d - 1)) == 0) crc = multmodp(xp, crc) ^ right;
+        xp = multmodp(xp, xp);
+    }
+    return __shfl_sync(0xffffffffu, crc, 0);
+}
+
+// ---------------------------------------------------------------------------------------------
+// One BGZF block.
+// ---------------------------------------------------------------------------------------------
+__device__ int inflate_member(InflateSmem &s, const uint8_t *src, uint32_t slen, uint8_t *out, uint32_t cap,
+                              uint32_t &olen)
+{
+    const uint32_t lane = hgpu_lane();
+    Bits b;
+    bits_init(b, src, slen);
+    uint32_t o = 0;
+    for (;;) {
+        bits_fill(b);
+        uint32_t final = bits_get(b, 1), type = bits_get(b, 2);
+        if (type == 0) {                                       // stored
+            bits_drop(b, b.cnt & 7);
+            bits_fill(b);
+            uint32_t len = bits_get(b, 16);
+            bits_fill(b);
+            uint32_t nlen = bits_get(b, 16);
+            if (bits_overrun(b)) return HGPU_BGZF_ERR_ZLIB;
+            if ((len ^ 0xffffu) != nlen) return HGPU_BGZF_ERR_ZLIB;
+            // byte position of the payload inside src
+            int64_t consumed_bits = (int64_t)slen * 8 - (b.avail + b.cnt);
+            uint32_t pos = (uint32_t)(consumed_bits >> 3);
+            if ((uint64_t)pos + len > slen) return HGPU_BGZF_ERR_ZLIB;
+            if (o + len > cap) return HGPU_BGZF_ERR_SPACE;
+            for (uint32_t i = lane; i < len; i += 32) out[o + i] = src[pos + i];
+            o += len;
+            bits_init(b, src + pos + len, slen - pos - len);
+        } else if (type == 1 || type == 2) {
+            int rc;
+            if (type == 1) {
+                __syncwarp();
+                for (int i = lane; i < 288; i += 32) s.lens[i] = i < 144 ? 8 : i < 256 ? 9 : i < 280 ? 7 : 8;
+                __syncwarp();
+                rc = build_table<LIT_ROOT, LIT_TABLE>(s, s.lit, 288, false, lit_entry);
+                if (rc) return HGPU_BGZF_ERR_ZLIB;
+                __syncwarp();
+                for (int i = lane; i < 32; i += 32) s.lens[i] = 5;
+                __syncwarp();
+                rc = build_table<DST_ROOT, DST_TABLE>(s, s.dst, 32, false, dst_entry);
+                if (rc) return HGPU_BGZF_ERR_ZLIB;
+            } else {
+                bits_fill(b);
+                uint32_t hlit = bits_get(b, 5) + 257, hdist = bits_get(b, 5) + 1, hclen = bits_get(b, 4) + 4;
+                if (hlit > 286 || hdist > 30) return HGPU_BGZF_ERR_ZLIB;
+                __syncwarp();
+                if (lane < 19) s.lens[lane] = 0;
+                __syncwarp();
+                for (uint32_t i = 0; i < hclen; i++) {
+                    bits_fill(b);
+                    uint32_t v = bits_get(b, 3);
+                    if (lane == 0) s.lens[c_cl_order[i]] = (uint8_t)v;
+                }
+                if (bits_overrun(b)) return HGPU_BGZF_ERR_ZLIB;
+                __syncwarp();
+                rc = build_table<7, CL_TABLE>(s, s.cl, 19, false, cl_entry);
+                if (rc) return HGPU_BGZF_ERR_ZLIB;
+                // code lengths: serial by nature (run-length coded); uniform across lanes
+                uint32_t nsym = hlit + hdist, i = 0, prev = 0;
+                // lens[] is reused for the result, so stage in code[] (uint16) first
+                while (i < nsym) {
+                    bits_fill(b);
+                    uint32_t e = s.cl[bits_peek(b, 7)];
+                    if (((e >> 4) & 15) != K_LIT) return HGPU_BGZF_ERR_ZLIB;
+                    bits_drop(b, e & 15);
+                    uint32_t sym = e >> 16;
+                    if (sym < 16) {
+                        if (lane == 0) s.code[i] = (uint16_t)sym;
+                        prev = sym; i++;
+                    } else {
+                        uint32_t rep, val = 0;
+                        if (sym == 16) { if (i == 0) return HGPU_BGZF_ERR_ZLIB; val = prev; rep = 3 + bits_get(b, 2); }
+                        else if (sym == 17) rep = 3 + bits_get(b, 3);
+                        else rep = 11 + bits_get(b, 7);
+                        if (i + rep > nsym) return HGPU_BGZF_ERR_ZLIB;
+                        for (uint32_t k = lane; k < rep; k += 32) s.code[i + k] = (uint16_t)val;
+                        i += rep;
+                        prev = val;
+                    }
+                    if (bits_overrun(b)) return HGPU_BGZF_ERR_ZLIB;
+                }
+                __syncwarp();
+                if (s.code[256] == 0) return HGPU_BGZF_ERR_ZLIB;         // no end-of-block code
+                // distance lengths first (they sit after the literal lengths in code[])
+                uint32_t dl = lane < hdist ? s.code[hlit + lane] : 0;
+                uint32_t ll[9];
+#pragma unroll
+                for (int k = 0; k < 9; k++) { uint32_t j = lane + 32 * k; ll[k] = j < hlit ? s.code[j] : 0; }
+                __syncwarp();
+#pragma unroll
+                for (int k = 0; k < 9; k++) { uint32_t j = lane + 32 * k; if (j < 288) s.lens[j] = (uint8_t)ll[k]; }
+                __syncwarp();
+                rc = build_table<LIT_ROOT, LIT_TABLE>(s, s.lit, (int)hlit, true, lit_entry);
+                if (rc) return HGPU_BGZF_ERR_ZLIB;
+                __syncwarp();
+                s.lens[lane] = (uint8_t)dl;
+                __syncwarp();
+                rc = build_table<DST_ROOT, DST_TABLE>(s, s.dst, (int)hdist, true, dst_entry);
+                if (rc) return HGPU_BGZF_ERR_ZLIB;
+            }
+            __syncwarp();
+            // ---- token loop (warp-uniform) ----
+            for (;;) {
+                bits_fill(b);
+                uint32_t e = lookup<LIT_ROOT>(s.lit, b);
+                uint32_t kind = (e >> 4) & 15;
+                if (kind == K_LIT) {
+                    if (o >= cap) return HGPU_BGZF_ERR_SPACE;
+                    if (lane == 0) out[o] = (uint8_t)(e >> 16);
+                    o++;
+                    continue;
+                }
+                if (kind == K_EOB) break;
+                if (kind != K_LEN) return HGPU_BGZF_ERR_ZLIB;
+                uint32_t len = (e >> 16) + bits_get(b, (e >> 8) & 0xff);
+                bits_fill(b);
+                uint32_t d = lookup<DST_ROOT>(s.dst, b);
+                if (((d >> 4) & 15) != K_DIST) return HGPU_BGZF_ERR_ZLIB;
+                uint32_t dist = (d >> 16) + bits_get(b, (d >> 8) & 0xff);
+                if (bits_overrun(b)) return HGPU_BGZF_ERR_ZLIB;
+                if (dist > o) return HGPU_BGZF_ERR_ZLIB;
+                if (o + len > cap) return HGPU_BGZF_ERR_SPACE;
+                __syncwarp();                      // earlier stores (other lanes) visible to this warp
+                const uint8_t *from = out + o - dist;
+                if (dist >= len) {
+                    for (uint32_t i = lane; i < len; i += 32) out[o + i] = from[i];
+                } else {
+                    for (uint32_t i = lane; i < len; i += 32) out[o + i] = from[i % dist];
+                }
+                __syncwarp();
+                o += len;
+            }
+            if (bits_overrun(b)) return HGPU_BGZF_ERR_ZLIB;
+        } else
+            return HGPU_BGZF_ERR_ZLIB;
+        if (final) break;
+    }
+    olen = o;
+    return HGPU_OK;
+}
+
+__device__ int check_header(const uint8_t *h)
+{
+    if (h[0] != 31 || h[1] != 139 || h[2] != 8) return -2;
+    return ((h[3] & 4) && (h[10] | h[11] << 8) == 6 && h[12] == 'B' && h[13] == 'C' && (h[14] | h[15] << 8) == 2) ? 0 : -1;
+}
+
+__global__ void __launch_bounds__(32)
+bgzf_inflate_kernel(const uint8_t *__restrict__ in, const uint64_t *__restrict__ in_off,
+                    const uint32_t *__restrict__ in_len, uint32_t n, uint8_t *out,
+                    const uint64_t *__restrict__ out_off, const uint32_t *__restrict__ out_cap,
+                    uint32_t *out_len, int32_t *status, uint32_t *counter)
+{
+    __shared__ InflateSmem s;
+    const uint32_t lane = hgpu_lane();
+    for (;;) {
+        uint32_t job = 0;
+        if (lane == 0) job = atomicAdd(counter, 1u);
+        job = __shfl_sync(0xffffffffu, job, 0);
+        if (job >= n) break;
+        const uint8_t *blk = in + in_off[job];
+        uint32_t blen = in_len[job];
+        uint8_t *dst = out + out_off[job];
+        uint32_t cap = out_cap[job];
+        if (cap > 65536u) cap = 65536u;                    // BGZF_MAX_BLOCK_SIZE, bgzf.c:810
+        int rc = HGPU_OK;
+        uint32_t got = 0;
+        if (blen < 26 || check_header(blk) != 0 || (uint32_t)(blk[16] | blk[17] << 8) + 1u != blen)
+            rc = HGPU_BGZF_ERR_HEADER;
+        else {
+            // inflate_block hands zlib block_length-18 bytes: deflate data plus the 8-byte footer
+            rc = inflate_member(s, blk + 18, blen - 18, dst, cap, got);
+            if (rc == HGPU_OK) {
+                __syncwarp();
+                __threadfence_block();
+                uint32_t want = blk[blen - 8] | blk[blen - 7] << 8 | blk[blen - 6] << 16 | (uint32_t)blk[blen - 5] << 24;
+                uint32_t crc = warp_crc32(dst, got);
+                if (crc != want) rc = HGPU_BGZF_ERR_CRC;
+            }
+        }
+        __syncwarp();
+        if (lane == 0) { status[job] = rc; out_len[job] = rc == HGPU_OK ? got : 0; }
+    }
+}
+
+__global__ void crc32_chunks_kernel(const uint8_t *buf, size_t len, size_t chunk, uint32_t *partial)
+{
+    // one warp per chunk
+    size_t w = (size_t)blockIdx.x;
+    size_t beg = w * chunk;
+    if (beg >= len) return;
+    size_t n = len - beg < chunk ? len - beg : chunk;
+    uint32_t crc = warp_crc32(buf + beg, (uint32_t)n);
+    if (hgpu_lane() == 0) partial[w] = crc;
+}
+
+bool g_crc_ready[64];
+
+int ensure_crc_tables(hgpu_ctx *ctx, cudaStream_t st)
+{
+    if (g_crc_ready[ctx->device & 63]) return HGPU_OK;
+    crc_init_kernel<<<1, 256, 0, st>>>();
+    hgpu_count_launch();
+    if (hgpu_check(cudaGetLastError(), "crc init")) return HGPU_ERR_CUDA;
+    if (hgpu_check(cudaStreamSynchronize(st), "crc init sync")) return HGPU_ERR_CUDA;   // once per device
+    g_crc_ready[ctx->device & 63] = true;
+    return HGPU_OK;
+}
+
+} // namespace
+
+int hgpu_launch_bgzf_inflate(hgpu_ctx *ctx, const uint8_t *d_in, const uint64_t *d_in_off,
+                             const uint32_t *d_in_len, uint32_t n, uint8_t *d_out,
+                             const uint64_t *d_out_off, const uint32_t *d_out_cap,
+                             uint32_t *d_out_len, int32_t *d_status, cudaStream_t st)
+{
+    if (n == 0) return HGPU_OK;
+    int rc = ensure_crc_tables(ctx, st);
+    if (rc) return rc;
+    int per_sm = 0;
+    if (hgpu_check(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, bgzf_inflate_kernel, 32, 0), "inflate occupancy"))
+        return HGPU_ERR_CUDA;
+    if (per_sm < 1) per_sm = 1;
+    uint32_t grid = (uint32_t)ctx->sm_count * (uint32_t)per_sm;
+    if (grid > n) grid = n;
+    uint32_t *counter = hgpu_take_counter(ctx, st);
+    if (!counter) return HGPU_ERR_CUDA;
+    bgzf_inflate_kernel<<<grid, 32, 0, st>>>(d_in, d_in_off, d_in_len, n, d_out, d_out_off, d_out_cap,
+                                             d_out_len, d_status, counter);
+    hgpu_count_launch();
+    return hgpu_check(cudaGetLastError(), "inflate launch");
+}
+
+// CRC-32 of a device buffer: per-chunk warp CRCs, combined on the host side of the ABI by the
+// caller (hgpu_api.cu) with the same x^n arithmetic.
+int hgpu_launch_crc32(hgpu_ctx *ctx, const uint8_t *d_buf, size_t len, uint32_t *d_partial,
+                      uint32_t *h_result, uint32_t crc0, cudaStream_t st)
+{
+    (void)h_result; (void)crc0;
+    int rc = ensure_crc_tables(ctx, st);
+    if (rc) return rc;
+    const size_t chunk = 1u << 20;
+    size_t nchunk = (len + chunk - 1) / chunk;
+    if (nchunk == 0) return HGPU_OK;
+    crc32_chunks_kernel<<<(unsigned)nchunk, 32, 0, st>>>(d_buf, len, chunk, d_partial);
+    hgpu_count_launch();
+    return hgpu_check(cudaGetLastError(), "crc launch");
+}

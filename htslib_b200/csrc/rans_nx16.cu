@@ -1,0 +1,730 @@
+// rANS Nx16 ("RANS_PR", CRAM 3.1 block method 5) decoder for sm_100a.
+//
+// Replaces rans_uncompress_to_4x16 and the four symbol loops behind it
+// (htscodecs rANS_static4x16pr.c:1586-1873, :213-328, :504-800; rANS_static32x16pr.c:254-408,
+// :527-754) with ONE warp-per-stream kernel: the N (4 or 32) interleaved rANS states live one
+// per lane, and the shared 16-bit renormalisation word stream is indexed with
+// __ballot_sync / __popc — lane k takes word  base + popc(ballot(R < 2^15) & lanemask_lt(k)),
+// which is exactly the "states renormalise in index order" rule of the scalar code
+// (rANS_static32x16pr.c:334-337, :657-666).
+//
+// Table layout (B200-first, not the reference's): per context row a BYTE lookup
+//   lut[row][m] -> compact symbol index       (1<<shift bytes)
+// plus a small per-(row,symbol) record
+//   fb[row][k]  -> { f | start<<16 , byte }   (8 bytes)
+// so an order-1 table for a 4-symbol NovaSeq alphabet is ~4 KiB (vs 16 KiB for the reference's
+// 32-bit s3 table and 1 MiB for its full 256-context array).  Small tables are what lets tens
+// of streams be resident per SM, which is where the throughput of a 32-lane-wide serial
+// recurrence comes from.  Rows are indexed by compact symbol index, so "next context" is the
+// index just looked up.  Tables that do not fit the CTA's shared memory go to a per-CTA slot in
+// global memory (L1/L2 resident).
+//
+// One CTA = one warp.  CTAs pull streams from an atomic work counter (persistent grid sized to
+// the SM count), largest streams first if the caller sorted them.
+#include "hgpu_internal.h"
+
+namespace {
+
+constexpr uint32_t RANS_L = 1u << 15;               // RANS_BYTE_L, rANS_word.h:64
+constexpr int SM_F      = 0;                        // u32 F[256]          1024 B
+constexpr int SM_CUM    = 1024;                     // u32 cum[257]        1028 B -> 1040
+constexpr int SM_ROWOF  = 2064;                     // u8 rowof[256]  byte -> compact row / 0xff
+constexpr int SM_SYMOF  = 2320;                     // u8 symof[256]  compact index -> byte
+constexpr int SM_TAB    = 2576;                     // table area (8-byte aligned)
+constexpr uint32_t GTAB_BYTES = 256u * 4096u + 256u * 256u * 8u;   // worst-case order-1 table
+constexpr uint32_t TBLBUF_BYTES = 256u * 1024u;     // decoded (was-compressed) order-1 table text
+
+struct WarpScratch {
+    uint8_t *tmp;      // max_out bytes : RLE / PACK intermediate
+    uint8_t *planes;   // max_out bytes : STRIPE planes
+    uint8_t *meta;     // max_out+1024  : decoded RLE meta
+    uint8_t *tblbuf;   // TBLBUF_BYTES  : decoded order-1 table text
+    uint8_t *gtab;     // GTAB_BYTES    : table overflow
+    uint32_t max_out;
+    uint32_t smem_tab_bytes;
+};
+
+// ---------------------------------------------------------------------------------------------
+// Warp-uniform scalar helpers: every lane runs the same code on the same addresses (loads
+// broadcast), so no shuffles are needed and control flow never diverges.
+// ---------------------------------------------------------------------------------------------
+
+// 7-bit big-endian varint (var_get_u32, varint.h:267-299)
+__device__ int vget(const uint8_t *p, const uint8_t *end, uint32_t &v)
+{
+    const uint8_t *s = p;
+    uint32_t acc = 0;
+    uint8_t c;
+    if (end - p >= 6) {
+        int budget = 5;
+        do { c = *p++; acc = (acc << 7) | (c & 0x7f); } while ((c & 0x80) && budget-- > 0);
+    } else {
+        if (p >= end) { v = 0; return 0; }
+        do { c = *p++; acc = (acc << 7) | (c & 0x7f); } while ((c & 0x80) && p < end);
+    }
+    v = acc;
+    return (int)(p - s);
+}
+
+// decode_alphabet (rANS_static16_int.h:191-238): marks F[sym] = 1.  F must be zeroed.
+__device__ int read_alphabet(const uint8_t *p, const uint8_t *end, uint32_t *F)
+{
+    const uint8_t *s = p;
+    int run = 0, sym;
+    if (p >= end) return 0;
+    sym = *p++;
+    if (sym == 0 && p + 2 >= end) return (int)(p - s);
+    for (;;) {
+        F[sym] = 1;
+        if (p >= end) return 0;
+        if (run == 0 && sym + 1 == *p) {
+            if (p + 1 >= end) return 0;
+            sym = *p++;
+            run = *p++;
+        } else if (run) {
+            run--;
+            if (++sym > 255) return 0;
+        } else {
+            sym = *p++;
+        }
+        if (sym == 0 || p >= end) break;
+    }
+    return (int)(p - s);
+}
+
+struct Table {
+    uint8_t *lut;      // [rows][1<<shift]
+    uint2   *fb;       // [rows][ncol]
+    uint32_t ncol;     // compact alphabet size
+    uint32_t shift;
+    bool     in_smem;
+};
+
+// Inclusive-free cumulative sums of cnt[0..n) (n <= 256) into cum[0..n]; returns the total.
+__device__ uint32_t warp_cumsum(const uint32_t *val, uint32_t *cum, int n)
+{
+    const uint32_t lane = hgpu_lane();
+    uint32_t loc[8], sum = 0;
+#pragma unroll
+    for (int k = 0; k < 8; k++) {
+        int j = lane * 8 + k;
+        loc[k] = j < n ? val[j] : 0;
+        sum += loc[k];
+    }
+    uint32_t inc = sum;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        uint32_t t = __shfl_up_sync(0xffffffffu, inc, d);
+        if (lane >= (uint32_t)d) inc += t;
+    }
+    uint32_t run = inc - sum;
+#pragma unroll
+    for (int k = 0; k < 8; k++) {
+        int j = lane * 8 + k;
+        if (j <= n) cum[j] = run;
+        run += loc[k];
+    }
+    uint32_t total = __shfl_sync(0xffffffffu, inc, 31);
+    __syncwarp();
+    return total;
+}
+
+// Fill one table row from compact frequencies f[0..ncol) whose cumulative sums are cum[].
+__device__ void fill_row(const Table &t, uint32_t row, const uint32_t *f, const uint32_t *cum,
+                         const uint8_t *symof, bool wrap12)
+{
+    const uint32_t lane = hgpu_lane();
+    uint8_t *lrow = t.lut + ((size_t)row << t.shift);
+    uint2 *frow = t.fb + (size_t)row * t.ncol;
+    for (uint32_t k = 0; k < t.ncol; k++) {
+        uint32_t fk = f[k], c0 = cum[k];
+        if (!fk) continue;
+        for (uint32_t y = lane; y < fk; y += 32) lrow[c0 + y] = (uint8_t)k;
+    }
+    for (uint32_t k = lane; k < t.ncol; k += 32) {
+        uint32_t fk = wrap12 ? (f[k] & 0xfffu) : f[k];
+        frow[k] = make_uint2(fk | (cum[k] << 16), symof[k]);
+    }
+}
+
+// A row that no valid stream enters: symbol 0, f 0, bias = slot (see oracle/orc_rans_nx16.c).
+__device__ void fill_null_row(const Table &t, uint32_t row)
+{
+    const uint32_t lane = hgpu_lane();
+    uint8_t *lrow = t.lut + ((size_t)row << t.shift);
+    for (uint32_t y = lane; y < (1u << t.shift); y += 32) lrow[y] = 0;
+    if (lane == 0) t.fb[(size_t)row * t.ncol] = make_uint2(0, 0);
+}
+
+// ---------------------------------------------------------------------------------------------
+// The symbol loops.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ void renorm(uint32_t &R, bool active, const uint8_t *in, uint32_t &ipos,
+                                       uint32_t in_len)
+{
+    bool need = active && R < RANS_L;
+    uint32_t bal = __ballot_sync(0xffffffffu, need);
+    if (bal) {
+        uint32_t wpos = ipos + 2u * __popc(bal & hgpu_lanemask_lt());
+        bool ok = need && wpos + 2u <= in_len;           // RansDecRenormSafe, rANS_word.h:441
+        if (ok) R = (R << 16) | in[wpos] | ((uint32_t)in[wpos + 1] << 8);
+        uint32_t took = __ballot_sync(0xffffffffu, ok);
+        ipos += 2u * __popc(took);
+    }
+}
+
+template <bool SMEM>
+__device__ void loop_order0(const Table &t, const uint8_t *in, uint32_t in_len, uint32_t ipos,
+                            uint8_t *out, uint32_t U, uint32_t N, uint32_t R)
+{
+    const uint32_t lane = hgpu_lane();
+    const uint32_t mask = (1u << t.shift) - 1, shift = t.shift;
+    const uint8_t *lut = t.lut;
+    const uint2 *fb = t.fb;
+    const bool mine = lane < N;
+    for (uint32_t i = lane; __any_sync(0xffffffffu, mine && i < U); i += N) {
+        bool act = mine && i < U;
+        uint32_t m = R & mask;
+        uint32_t k = lut[m];
+        uint2 e = fb[k];
+        if (act) {
+            R = (e.x & 0xffffu) * (R >> shift) + m - (e.x >> 16);
+            out[i] = (uint8_t)e.y;
+        }
+        renorm(R, act, in, ipos, in_len);
+    }
+}
+
+template <bool SMEM>
+__device__ void loop_order1(const Table &t, const uint8_t *in, uint32_t in_len, uint32_t ipos,
+                            uint8_t *out, uint32_t U, uint32_t N, uint32_t R, uint32_t row0)
+{
+    const uint32_t lane = hgpu_lane();
+    const uint32_t mask = (1u << t.shift) - 1, shift = t.shift, ncol = t.ncol;
+    const uint8_t *lut = t.lut;
+    const uint2 *fb = t.fb;
+    const bool mine = lane < N;
+    const uint32_t seg = U / N;
+    uint8_t *op = out + (size_t)(mine ? lane : 0) * seg;
+    uint32_t row = row0;
+    for (uint32_t s = 0; s < seg; s++) {
+        uint32_t m = R & mask;
+        uint32_t k = lut[(row << shift) + m];
+        uint2 e = fb[row * ncol + k];
+        if (mine) {
+            R = (e.x & 0xffffu) * (R >> shift) + m - (e.x >> 16);
+            op[s] = (uint8_t)e.y;
+            row = k;
+        }
+        renorm(R, mine, in, ipos, in_len);
+    }
+    // the last state also produces the U mod N tail (rANS_static32x16pr.c:669-680)
+    const bool last = lane == N - 1;
+    for (uint32_t s = seg * N; s < U; s++) {
+        uint32_t m = R & mask;
+        uint32_t k = lut[(row << shift) + m];
+        uint2 e = fb[row * ncol + k];
+        if (last) {
+            R = (e.x & 0xffffu) * (R >> shift) + m - (e.x >> 16);
+            out[s] = (uint8_t)e.y;
+            row = k;
+        }
+        renorm(R, last, in, ipos, in_len);
+    }
+}
+
+// Read the N initial states (RansDecInit, rANS_word.h:123) — lane z takes state z.
+__device__ int load_states(const uint8_t *p, const uint8_t *end, uint32_t N, uint32_t &R)
+{
+    const uint32_t lane = hgpu_lane();
+    if (end - p < (ptrdiff_t)(4 * N)) return -1;
+    R = RANS_L;
+    if (lane < N) {
+        const uint8_t *q = p + 4 * lane;
+        R = q[0] | (uint32_t)q[1] << 8 | (uint32_t)q[2] << 16 | (uint32_t)q[3] << 24;
+    }
+    return __any_sync(0xffffffffu, R < RANS_L) ? -1 : 0;
+}
+
+__device__ Table place_table(uint8_t *smem, const WarpScratch &ws, uint32_t rows, uint32_t ncol, uint32_t shift)
+{
+    Table t;
+    uint32_t lut_bytes = ((rows << shift) + 7u) & ~7u;
+    uint32_t need = lut_bytes + rows * ncol * 8u;
+    uint8_t *base = need <= ws.smem_tab_bytes ? smem + SM_TAB : ws.gtab;
+    t.in_smem = need <= ws.smem_tab_bytes;
+    t.lut = base;
+    t.fb = reinterpret_cast<uint2 *>(base + lut_bytes);
+    t.ncol = ncol;
+    t.shift = shift;
+    return t;
+}
+
+// order-0 stream: table + states + words  (rans_uncompress_O0_4x16 / _32x16)
+__device__ int dec_order0(uint8_t *smem, const WarpScratch &ws, const uint8_t *in, uint32_t in_len,
+                          uint8_t *out, uint32_t U, uint32_t N)
+{
+    uint32_t *F = reinterpret_cast<uint32_t *>(smem + SM_F);
+    uint32_t *cum = reinterpret_cast<uint32_t *>(smem + SM_CUM);
+    uint8_t *symof = smem + SM_SYMOF;
+    const uint32_t lane = hgpu_lane();
+    if (in_len < 16) return -1;
+    const uint8_t *p = in, *end = in + in_len;
+    // the 4-way decoder parses its table against end-8 (rANS_static4x16pr.c:228), the 32-way
+    // one against the true end (rANS_static32x16pr.c:272)
+    const uint8_t *tend = N == 4 ? end - 8 : end;
+    __syncwarp();
+    for (int j = lane; j < 256; j += 32) F[j] = 0;
+    __syncwarp();
+    if (p == tend) return -1;
+    p += read_alphabet(p, tend, F);
+    __syncwarp();
+    // compact alphabet, then one varint per present symbol (decode_freq :254-272)
+    uint32_t ncol = 0, tot = 0;
+    for (int j = 0; j < 256; j++) {
+        if (F[j]) {
+            uint32_t f;
+            p += vget(p, tend, f);
+            tot += f;
+            __syncwarp();
+            if (lane == 0) { F[ncol] = f; symof[ncol] = (uint8_t)j; }
+            __syncwarp();
+            ncol++;
+        }
+    }
+    if (p == in) return -1;
+    // normalise_freq_shift (:151-162)
+    if (tot != 0 && tot != 4096) {
+        int sh = 0;
+        while (tot < 4096) { tot *= 2; sh++; }
+        __syncwarp();
+        for (uint32_t k = lane; k < ncol; k += 32) F[k] <<= sh;
+        __syncwarp();
+    }
+    // rans_F_to_s3 (:540-551): every F must fit what is left, and they must sum to 4096
+    bool bad = false;
+    for (uint32_t k = lane; k < ncol; k += 32) bad |= F[k] > 4096u;
+    if (__any_sync(0xffffffffu, bad)) return -1;
+    if (warp_cumsum(F, cum, (int)ncol) != 4096u) return -1;
+    if (ncol == 0) return -1;
+    Table t = place_table(smem, ws, 1, ncol, 12);
+    fill_row(t, 0, F, cum, symof, N == 32);
+    __syncwarp();
+    uint32_t R;
+    if (load_states(p, end, N, R)) return -1;
+    uint32_t ipos = (uint32_t)(p - in) + 4 * N;
+    if (t.in_smem) loop_order0<true>(t, in, in_len, ipos, out, U, N, R);
+    else           loop_order0<false>(t, in, in_len, ipos, out, U, N, R);
+    __syncwarp();
+    return 0;
+}
+
+// order-1 stream (rans_uncompress_O1_4x16 / _32x16; table = decode_freq1, :468-536)
+__device__ int dec_order1(uint8_t *smem, const WarpScratch &ws, const uint8_t *in, uint32_t in_len,
+                          uint8_t *out, uint32_t U, uint32_t N)
+{
+    uint32_t *F = reinterpret_cast<uint32_t *>(smem + SM_F);
+    uint32_t *cum = reinterpret_cast<uint32_t *>(smem + SM_CUM);
+    uint8_t *rowof = smem + SM_ROWOF;
+    uint8_t *symof = smem + SM_SYMOF;
+    const uint32_t lane = hgpu_lane();
+    if (in_len < (N == 4 ? 16u : 4u * N)) return -1;
+    const uint8_t *p = in, *end = in + in_len, *tend = end, *after_tab = nullptr;
+    const uint32_t shift = *p >> 4;
+    if (*p++ & 1) {                       // table is itself order-0 4-way coded (:555-566)
+        uint32_t usz, csz;
+        p += vget(p, end, usz);
+        p += vget(p, end, csz);
+        if (csz > (uint32_t)(end - p)) return -1;
+        if (usz > TBLBUF_BYTES) return -1;        // documented limit (a real table is < 200 KiB)
+        after_tab = p + csz;
+        if (dec_order0(smem, ws, p, csz, ws.tblbuf, usz, 4)) return -1;
+        __syncwarp();
+        __threadfence_block();
+        p = ws.tblbuf;
+        tend = ws.tblbuf + usz;
+    }
+    if (shift != 10 && shift != 12) return -1;     // anything else is out of bounds in the reference
+    __syncwarp();
+    for (int j = lane; j < 256; j += 32) { F[j] = 0; rowof[j] = 0xff; }
+    __syncwarp();
+    int n = read_alphabet(p, tend, F);
+    if (!n) return -1;
+    p += n;
+    if (p >= tend) return -1;
+    __syncwarp();
+    // compact alphabet A' = A0 + {0}: byte 0 always owns row/column 0 so the start context
+    // exists even in streams that never emit a zero byte.
+    uint32_t ncol = 0;
+    bool zero_in_a0 = F[0] != 0;
+    for (int j = 0; j < 256; j++) {
+        if (F[j] || j == 0) {
+            __syncwarp();
+            if (lane == 0) { rowof[j] = (uint8_t)ncol; symof[ncol] = (uint8_t)j; }
+            ncol++;
+        }
+    }
+    __syncwarp();
+    Table t = place_table(smem, ws, ncol, ncol, shift);
+    const uint32_t total = 1u << shift;
+    for (uint32_t r = 0; r < ncol; r++) {
+        if (r == 0 && !zero_in_a0) { fill_null_row(t, 0); continue; }
+        // decode_freq_d (:425-456): one varint per alphabet symbol, zero followed by a run of zeros
+        const uint8_t *q = p;
+        uint32_t T = 0;
+        int dz = 0;
+        if (q == tend) return -1;
+        __syncwarp();
+        for (uint32_t k = lane; k < ncol; k += 32) F[k] = 0;
+        __syncwarp();
+        for (uint32_t k = zero_in_a0 ? 0 : 1; k < ncol && q < tend; k++) {
+            uint32_t f;
+            if (dz) { f = 0; dz--; }
+            else {
+                q += vget(q, tend, f);
+                if (f == 0) { if (q >= tend) return -1; dz = *q++; }
+            }
+            if (lane == 0) F[k] = f;
+            T += f;
+        }
+        __syncwarp();
+        if (q == p) return -1;
+        p = q;
+        if (!T) { fill_null_row(t, r); continue; }
+        if (T != total) {                         // normalise_freq_shift
+            int sh = 0; uint32_t tt = T;
+            while (tt < total) { tt *= 2; sh++; }
+            for (uint32_t k = lane; k < ncol; k += 32) F[k] <<= sh;
+            __syncwarp();
+        }
+        bool bad = false;
+        for (uint32_t k = lane; k < ncol; k += 32) bad |= F[k] > total;
+        if (__any_sync(0xffffffffu, bad)) return -1;
+        if (warp_cumsum(F, cum, (int)ncol) != total) return -1;
+        fill_row(t, r, F, cum, symof, false);
+        __syncwarp();
+    }
+    __syncwarp();
+    if (!t.in_smem) __threadfence_block();
+    if (after_tab) p = after_tab;
+    // p now points into `in` again in every case (an uncompressed table was parsed in place)
+    uint32_t R;
+    if (load_states(p, end, N, R)) return -1;
+    uint32_t ipos = (uint32_t)(p - in) + 4 * N;
+    if (t.in_smem) loop_order1<true>(t, in, in_len, ipos, out, U, N, R, 0);
+    else           loop_order1<false>(t, in, in_len, ipos, out, U, N, R, 0);
+    __syncwarp();
+    return 0;
+}
+
+// hts_unpack_meta (pack.c:161-196): returns bytes consumed or 0
+__device__ int unpack_meta(const uint8_t *d, uint32_t len, uint8_t *map, int &per_byte)
+{
+    if (!len) return 0;
+    uint32_t n = d[0] ? d[0] : 256, j = 1, c = 0;
+    if (n <= 1) per_byte = 0;
+    else if (n <= 2) per_byte = 8;
+    else if (n <= 4) per_byte = 4;
+    else if (n <= 16) per_byte = 2;
+    else { per_byte = 1; return 1; }
+    if (len <= 1) return 0;
+    do { map[c++] = d[j++]; } while (c < n && j < len);
+    return c < n ? 0 : (int)j;
+}
+
+// hts_unpack (pack.c:207-330): out[i] = map[field i of data]; fully parallel.
+__device__ int unpack(const uint8_t *d, uint64_t len, uint8_t *out, uint64_t olen, int per_byte,
+                      const uint8_t *map)
+{
+    const uint32_t lane = hgpu_lane();
+    if (per_byte == 1) { for (uint64_t i = lane; i < len; i += 32) out[i] = d[i]; return 0; }
+    if (per_byte == 0) { for (uint64_t i = lane; i < olen; i += 32) out[i] = map[0]; return 0; }
+    int bits = per_byte == 8 ? 1 : per_byte == 4 ? 2 : 4;
+    if ((olen + per_byte - 1) / per_byte > len) return -1;
+    for (uint64_t i = lane; i < olen; i += 32)
+        out[i] = map[(d[i / per_byte] >> (bits * (i % per_byte))) & ((1 << bits) - 1)];
+    return 0;
+}
+
+// hts_rle_decode (rle.c:142-190).  32 literals per round: ballot which of them carry a run,
+// lane 0 walks the run-length varints for those (the only serial part), an exclusive scan of
+// the expanded lengths gives every literal its output offset, then all lanes write.
+__device__ int unrle(uint8_t *smem, const uint8_t *lit, uint64_t nlit, const uint8_t *run, uint64_t nrun,
+                     const uint8_t *syms, int nsyms, uint8_t *out, uint64_t cap, uint64_t &olen)
+{
+    const uint32_t lane = hgpu_lane();
+    uint8_t *flag = smem + SM_ROWOF;                 // 256 B, free outside table building
+    uint32_t *rl = reinterpret_cast<uint32_t *>(smem + SM_F);   // 32 run lengths per round
+    __syncwarp();
+    for (int j = lane; j < 256; j += 32) flag[j] = 0;
+    __syncwarp();
+    for (int j = lane; j < nsyms; j += 32) flag[syms[j]] = 1;
+    __syncwarp();
+    const uint8_t *rp = run, *rend = run + nrun;
+    uint64_t o = 0;
+    for (uint64_t base = 0; base < nlit; base += 32) {
+        uint64_t i = base + lane;
+        uint8_t b = i < nlit ? lit[i] : 0;
+        bool has = i < nlit && flag[b];
+        uint32_t bal = __ballot_sync(0xffffffffu, has);
+        if (lane == 0) {
+            uint32_t mm = bal;
+            while (mm) {
+                int z = __ffs(mm) - 1;
+                mm &= mm - 1;
+                uint32_t r;
+                rp += vget(rp, rend, r);
+                rl[z] = r;
+            }
+        }
+        // every lane must see lane 0's pointer advance
+        unsigned long long rp_bits = __shfl_sync(0xffffffffu, (unsigned long long)rp, 0);
+        rp = reinterpret_cast<const uint8_t *>(rp_bits);
+        __syncwarp();
+        uint32_t mylen = i < nlit ? (has ? rl[lane] + 1u : 1u) : 0u;
+        // the reference checks literal by literal: a run must leave room for one more byte
+        // (outp + rlen >= out_end fails), a plain literal needs outp < out_end
+        uint64_t inc = mylen;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            uint64_t tv = __shfl_up_sync(0xffffffffu, inc, d);
+            if (lane >= (uint32_t)d) inc += tv;
+        }
+        uint64_t my_o = o + inc - mylen;
+        bool bad = false;
+        if (i < nlit) {
+            if (my_o >= cap) bad = true;
+            else if (has && mylen > 1 && my_o + (mylen - 1) >= cap) bad = true;
+        }
+        if (__any_sync(0xffffffffu, bad)) return -1;
+        if (i < nlit)
+            for (uint32_t k = 0; k < mylen; k++) out[my_o + k] = b;
+        o += __shfl_sync(0xffffffffu, inc, 31);
+        __syncwarp();
+    }
+    olen = o;
+    return 0;
+}
+
+// Everything except STRIPE (rans_uncompress_to_4x16, :1675-1873).
+__device__ int decode_plain(uint8_t *smem, const WarpScratch &ws, const uint8_t *in, uint32_t in_size,
+                            uint8_t *out, uint32_t out_cap, uint32_t &out_size)
+{
+    const uint32_t lane = hgpu_lane();
+    const uint8_t *end = in + in_size;
+    uint8_t fmt = *in++; in_size--;
+    const uint32_t N = (fmt & 0x04) ? 32 : 4;
+    const int order = fmt & 1;
+    uint32_t osz;
+    if (!(fmt & 0x10)) { int s = vget(in, end, osz); in += s; in_size -= s; }
+    else osz = out_cap;
+    if (out_cap < osz) return -1;
+    if (osz > ws.max_out) return -1;                // scratch was sized from the caller's bound
+    out_size = osz;
+    uint32_t t1_size = osz;
+    uint8_t *t1, *t2, *t3, *tmp = ws.tmp;
+    if ((fmt & 0xc0) == 0xc0) { t1 = out; t2 = tmp; t3 = out; }
+    else if (fmt & 0x80)      { t1 = tmp; t2 = tmp; t3 = out; }
+    else if (fmt & 0x40)      { t1 = tmp; t2 = out; t3 = out; }
+    else                      { t1 = t2 = t3 = out; }
+
+    uint8_t map[16];
+    for (int k = 0; k < 16; k++) map[k] = 0;
+    int per_byte = 0;
+    uint64_t unpacked = 0;
+    if (fmt & 0x80) {                               // PACK meta (:1748-1767)
+        int m = unpack_meta(in, in_size, map, per_byte);
+        if (!m) return -1;
+        unpacked = osz;
+        in += m; in_size -= m;
+        uint32_t psz;
+        int s = vget(in, end, psz);
+        in += s; in_size -= s;
+        if (psz > t1_size) return -1;
+        t1_size = psz;
+    }
+    const uint8_t *meta = nullptr;
+    uint32_t u_meta = 0;
+    if (fmt & 0x40) {                               // RLE meta (:1769-1796)
+        uint32_t rle_len, c_meta, s;
+        s = vget(in, end, u_meta);
+        s += vget(in + s, end, rle_len);
+        if (rle_len > t1_size) return -1;
+        if (u_meta & 1) {
+            meta = in + s;
+            u_meta = (u_meta / 2 > (uint32_t)(end - meta)) ? (uint32_t)(end - meta) : u_meta / 2;
+            c_meta = u_meta;
+        } else {
+            s += vget(in + s, end, c_meta);
+            u_meta /= 2;
+            if (u_meta > ws.max_out + 1024u) return -1;      // documented limit
+            if (s > in_size) return -1;
+            if (dec_order0(smem, ws, in + s, in_size - s, ws.meta, u_meta, N)) return -1;
+            __syncwarp();
+            __threadfence_block();
+            meta = ws.meta;
+        }
+        if (c_meta + s > in_size) return -1;
+        in += c_meta + s; in_size -= c_meta + s;
+        t1_size = rle_len;
+    }
+    if (in_size) {
+        if (fmt & 0x20) {                           // CAT
+            if (t1_size > in_size || t1_size > out_size) return -1;
+            for (uint32_t i = lane; i < t1_size; i += 32) t1[i] = in[i];
+        } else {
+            int rc = order ? dec_order1(smem, ws, in, in_size, t1, t1_size, N)
+                           : dec_order0(smem, ws, in, in_size, t1, t1_size, N);
+            if (rc) return -1;
+        }
+    } else
+        t1_size = 0;
+    __syncwarp();
+    __threadfence_block();
+    uint64_t t2_size = t1_size, t3_size;
+    if (fmt & 0x40) {
+        if (u_meta == 0) return -1;
+        int ns = meta[0] ? meta[0] : 256;
+        if (u_meta < (uint32_t)(1 + ns)) return -1;
+        uint64_t got = 0;
+        if (unrle(smem, t1, t1_size, meta + 1 + ns, u_meta - (1 + ns), meta + 1, ns, t2, out_size, got)) return -1;
+        t2_size = got;
+        __syncwarp();
+        __threadfence_block();
+    }
+    t3_size = t2_size;
+    if (fmt & 0x80) {
+        if (per_byte == 1) unpacked = t2_size;
+        if (unpack(t2, t2_size, t3, unpacked, per_byte, map)) return -1;
+        t3_size = unpacked;
+    }
+    out_size = (uint32_t)t3_size;
+    return 0;
+}
+
+__device__ int decode_stream(uint8_t *smem, const WarpScratch &ws, const uint8_t *in, uint32_t in_size,
+                             uint8_t *out, uint32_t out_cap, uint32_t &out_size)
+{
+    const uint32_t lane = hgpu_lane();
+    if (in_size == 0) return -1;
+    if (!(in[0] & 0x08)) return decode_plain(smem, ws, in, in_size, out, out_cap, out_size);
+
+    // STRIPE (:1594-1673): N sub-streams, byte-plane transposed
+    const uint8_t *end = in + in_size;
+    uint32_t ulen, off = 1;
+    off += vget(in + off, end, ulen);
+    if (off >= in_size) return -1;
+    uint32_t n = in[off++];
+    if (n < 1) return -1;
+    if (ulen != out_cap) return -1;
+    if (ulen > ws.max_out) return -1;
+    // first pass over the length table: validate exactly as the reference does
+    uint64_t ctot = 0;
+    uint32_t off2 = off;
+    for (uint32_t k = 0; k < n; k++) {
+        uint32_t cl;
+        off2 += vget(in + off2, end, cl);
+        ctot += cl;
+        if (off2 > in_size || cl > in_size || cl < 1) return -1;
+    }
+    if (off2 + ctot > in_size) return -1;
+    in_size = (uint32_t)(off2 + ctot);
+    uint32_t data = off2, idx = 0;
+    for (uint32_t k = 0; k < n; k++) {
+        uint32_t cl;
+        off += vget(in + off, end, cl);
+        uint32_t ul = ulen / n + ((ulen % n) > k), got = 0;
+        if (in_size < data) return -1;
+        if (in_size - data == 0) return -1;
+        if (in[data] & 0x08) return -1;             // nested STRIPE: never written by the encoder; unsupported
+        if (decode_plain(smem, ws, in + data, in_size - data, ws.planes + idx, ul, got) || got != ul) return -1;
+        data += cl;
+        idx += ul;
+    }
+    __syncwarp();
+    __threadfence_block();
+    // unstripe (utils.h:79-138): out[j] = plane[j % n][j / n]
+    const uint32_t q = ulen / n, r = ulen % n;
+    for (uint32_t j = lane; j < ulen; j += 32) {
+        uint32_t k = j % n, i = j / n;
+        uint32_t start = k * q + (k < r ? k : r);
+        out[j] = ws.planes[start + i];
+    }
+    out_size = ulen;
+    return 0;
+}
+
+__global__ void __launch_bounds__(32)
+rans_nx16_decode_kernel(const uint8_t *__restrict__ in, const uint64_t *__restrict__ in_off,
+                        const uint32_t *__restrict__ in_len, uint32_t n, uint8_t *out,
+                        const uint64_t *__restrict__ out_off, const uint32_t *__restrict__ out_len,
+                        uint32_t *got_len, int32_t *status, uint8_t *scratch, size_t scratch_per_cta,
+                        uint32_t max_out, uint32_t smem_tab_bytes, uint32_t *counter)
+{
+    extern __shared__ __align__(16) uint8_t smem[];
+    WarpScratch ws;
+    uint8_t *base = scratch + (size_t)blockIdx.x * scratch_per_cta;
+    size_t mo = ((size_t)max_out + 255) & ~(size_t)255;
+    ws.tmp = base;
+    ws.planes = base + mo;
+    ws.meta = base + 2 * mo;
+    ws.tblbuf = base + 3 * mo + 1024;
+    ws.gtab = ws.tblbuf + TBLBUF_BYTES;
+    ws.max_out = max_out;
+    ws.smem_tab_bytes = smem_tab_bytes;
+    for (;;) {
+        uint32_t job = 0;
+        if (hgpu_lane() == 0) job = atomicAdd(counter, 1u);
+        job = __shfl_sync(0xffffffffu, job, 0);
+        if (job >= n) break;
+        uint32_t got = 0;
+        int rc = decode_stream(smem, ws, in + in_off[job], in_len[job], out + out_off[job], out_len[job], got);
+        __syncwarp();
+        if (hgpu_lane() == 0) {
+            status[job] = rc ? HGPU_RANS_ERR : HGPU_OK;
+            got_len[job] = rc ? 0 : got;
+        }
+    }
+}
+
+} // namespace
+
+int hgpu_launch_rans_nx16(hgpu_ctx *ctx, const uint8_t *d_in, const uint64_t *d_in_off,
+                          const uint32_t *d_in_len, uint32_t n, uint8_t *d_out,
+                          const uint64_t *d_out_off, const uint32_t *d_out_len,
+                          uint32_t *d_got_len, int32_t *d_status, uint32_t max_out_len,
+                          cudaStream_t st)
+{
+    if (n == 0) return HGPU_OK;
+    // Shared memory per warp-CTA: parsing arrays + table area.  18 KiB of table holds every
+    // order-0 table, and order-1 tables of <= 4 contexts at 12 bits / <= 16 at 10 bits with
+    // small alphabets, while still letting 11 CTAs share an SM.
+    const uint32_t smem_tab = 18 * 1024;
+    const uint32_t smem_total = SM_TAB + smem_tab;
+    static bool attr_set = false;
+    if (!attr_set) {
+        if (hgpu_check(cudaFuncSetAttribute(rans_nx16_decode_kernel,
+                       cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_total), "rans smem attr"))
+            return HGPU_ERR_CUDA;
+        attr_set = true;
+    }
+    int per_sm = 0;
+    if (hgpu_check(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, rans_nx16_decode_kernel, 32, smem_total),
+                   "rans occupancy"))
+        return HGPU_ERR_CUDA;
+    if (per_sm < 1) per_sm = 1;
+    uint32_t grid = (uint32_t)ctx->sm_count * (uint32_t)per_sm;
+    if (grid > n) grid = n;
+    size_t mo = ((size_t)max_out_len + 255) & ~(size_t)255;
+    size_t per_cta = 3 * mo + 1024 + TBLBUF_BYTES + GTAB_BYTES;
+    per_cta = (per_cta + 255) & ~(size_t)255;
+    int rc = hgpu_ensure_scratch(ctx, per_cta * grid);
+    if (rc) return rc;
+    uint32_t *counter = hgpu_take_counter(ctx, st);
+    if (!counter) return HGPU_ERR_CUDA;
+    rans_nx16_decode_kernel<<<grid, 32, smem_total, st>>>(d_in, d_in_off, d_in_len, n, d_out, d_out_off,
+                                                         d_out_len, d_got_len, d_status, ctx->d_scratch,
+                                                         per_cta, max_out_len, smem_tab, counter);
+    hgpu_count_launch();
+    return hgpu_check(cudaGetLastError(), "rans launch");
+}

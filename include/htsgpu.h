@@ -1,0 +1,168 @@
+/*
+ * htsgpu.h — C ABI of libhtsgpu.so, the B200 (sm_100a) implementation of htslib's
+ * compression/decode hot path.  Plain pointers and sizes only; no torch / C++ types.
+ *
+ * Two layers:
+ *  (1) batch entry points (hgpu_*): many BGZF blocks / CRAM blocks / BAM records per launch.
+ *      "_dev" variants take DEVICE pointers and a cudaStream_t (passed as void*); they only
+ *      enqueue work.  "_host" variants take HOST pointers, stage through pinned buffers,
+ *      and return when the results are in host memory.
+ *  (2) reference-named shims with the reference's exact signatures and ownership rules, so a
+ *      maintainer can link this library where htslib links libhtscodecs / calls its own
+ *      static helpers.  Each is a batch of one: correct, not fast.
+ *
+ * Citations (file:line) are relative to the htslib 1.23.1 / htscodecs 1.6.6 tree.
+ * There is NO CPU fallback: every entry point returns HGPU_ERR_NODEVICE when no CUDA device
+ * is usable.
+ */
+#ifndef HTSGPU_H
+#define HTSGPU_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ---- status codes (per call: return value; per unit: status[] arrays) ---- */
+#define HGPU_OK              0
+#define HGPU_ERR_NODEVICE  (-100)  /* no CUDA device / driver */
+#define HGPU_ERR_CUDA      (-101)  /* a CUDA runtime call failed (see hgpu_last_error) */
+#define HGPU_ERR_ARG       (-102)
+#define HGPU_ERR_NOMEM     (-103)
+/* per-block BGZF status, mirroring fp->errcode bits set by inflate_block (bgzf.c:808-824) */
+#define HGPU_BGZF_ERR_ZLIB   (-1)  /* inflate failed          -> BGZF_ERR_ZLIB   */
+#define HGPU_BGZF_ERR_CRC    (-2)  /* CRC32 mismatch          -> BGZF_ERR_CRC    */
+#define HGPU_BGZF_ERR_HEADER (-3)  /* check_header failed     -> BGZF_ERR_HEADER */
+#define HGPU_BGZF_ERR_SPACE  (-4)  /* output longer than the slot the caller gave it */
+/* per-stream rANS status: the reference only has "returns NULL" (rANS_static4x16pr.c:1586) */
+#define HGPU_RANS_ERR        (-1)
+
+typedef struct hgpu_ctx hgpu_ctx;
+
+/* Context = one device + its stream, pinned staging and device scratch.  device < 0 uses the
+ * current device.  Returns NULL (and sets hgpu_last_error) on failure. */
+hgpu_ctx   *hgpu_create(int device);
+void        hgpu_destroy(hgpu_ctx *ctx);
+const char *hgpu_last_error(void);
+const char *hgpu_version(void);
+/* number of kernels this library has launched in this process (bench.py's gpu_launches) */
+uint64_t    hgpu_launch_count(void);
+
+/* ------------------------------------------------------------------------------------------
+ * BGZF — replaces the body of bgzf_decode_func / inflate_block + bgzf_uncompress + the CRC32
+ * check (bgzf.c:1373-1384, :808-824, :762-804) for a batch of blocks, one warp per block.
+ * in_off[i]/in_len[i]: each WHOLE BGZF block (18-byte header .. 8-byte footer, BSIZE+1 bytes).
+ * out_off[i]/out_cap[i]: where block i's bytes go inside `out` and how much room it has
+ *   (htslib gives every block 64 KiB: BGZF_MAX_BLOCK_SIZE, bgzf.c:810).
+ * out_len[i]: inflated length; status[i]: HGPU_OK or HGPU_BGZF_ERR_*.
+ * ---------------------------------------------------------------------------------------- */
+int hgpu_bgzf_inflate_batch_dev(hgpu_ctx *ctx,
+        const uint8_t *d_in, const uint64_t *d_in_off, const uint32_t *d_in_len, uint32_t n,
+        uint8_t *d_out, const uint64_t *d_out_off, const uint32_t *d_out_cap,
+        uint32_t *d_out_len, int32_t *d_status, void *stream);
+
+/* Host-side walk of the BSIZE chain (bgzf_read_block header logic, bgzf.c:1144-1205;
+ * bgzf_mt_read_block :1485-1539).  Fills off/len/isize for up to cap blocks; isize is the
+ * footer's ISIZE field.  Returns the block count, or -1-k when block k has a bad header or is
+ * truncated (the reference sets BGZF_ERR_HEADER / BGZF_ERR_IO there). */
+long hgpu_bgzf_scan(const uint8_t *file, uint64_t file_len,
+                    uint64_t *off, uint32_t *len, uint32_t *isize, long cap);
+
+/* Whole-file-image inflate with HOST buffers: scan + H2D + kernel + D2H, pipelined in chunks.
+ * out must hold out_cap bytes; *out_len receives the total.  Blocks are packed back to back in
+ * `out` in file order (what bgzf_read would deliver).  Returns HGPU_OK, or the first failing
+ * block's status with *bad_block set (the reference reports errors in block order too,
+ * bgzf.c:1037-1044). */
+int hgpu_bgzf_inflate_file_host(hgpu_ctx *ctx, const uint8_t *file, uint64_t file_len,
+                                uint8_t *out, uint64_t out_cap, uint64_t *out_len, long *bad_block);
+
+/* CRC-32 of a host buffer computed on the device == hts_crc32 (bgzf.c:620-622, htslib.map:657) */
+uint32_t hgpu_crc32(hgpu_ctx *ctx, uint32_t crc, const void *buf, size_t len);
+
+/* ------------------------------------------------------------------------------------------
+ * rANS Nx16 ("RANS_PR", CRAM 3.1 block method 5) — replaces rans_uncompress_to_4x16
+ * (rANS_static4x16pr.c:1586-1873) as called per block from cram_uncompress_block
+ * (cram/cram_io.c:1697-1714), for a batch of blocks, one warp per stream.
+ * in_off/in_len: each compressed payload; out_off/out_len: destination and the block's
+ * uncomp_size from the CRAM block header (used as capacity and, for NOSZ streams, as the size).
+ * got_len[i]: bytes produced; status[i]: HGPU_OK or HGPU_RANS_ERR.
+ * max_out_len: >= every out_len[i] (sizes the per-warp scratch; host scalar on purpose).
+ * ---------------------------------------------------------------------------------------- */
+int hgpu_rans_nx16_decode_batch_dev(hgpu_ctx *ctx,
+        const uint8_t *d_in, const uint64_t *d_in_off, const uint32_t *d_in_len, uint32_t n,
+        uint8_t *d_out, const uint64_t *d_out_off, const uint32_t *d_out_len,
+        uint32_t *d_got_len, int32_t *d_status, uint32_t max_out_len, void *stream);
+
+int hgpu_rans_nx16_decode_batch_host(hgpu_ctx *ctx,
+        const uint8_t *in, const uint64_t *in_off, const uint32_t *in_len, uint32_t n,
+        uint8_t *out, const uint64_t *out_off, const uint32_t *out_len,
+        uint32_t *got_len, int32_t *status);
+
+/* ------------------------------------------------------------------------------------------
+ * BAM record unpack — the data movement of bam_read1 (sam.c:784-860) plus the 4-bit SEQ expand
+ * and QUAL+33 of sam_format1_append (sam.c:4324-4404, nibble2base sam_internal.h:63-118) over
+ * an inflated BAM record stream resident in device memory.
+ * ---------------------------------------------------------------------------------------- */
+/* 48-byte mirror of bam1_core_t (htslib/sam.h:214-227) */
+typedef struct hgpu_bam1_core {
+    int64_t  pos;
+    int32_t  tid;
+    uint16_t bin;
+    uint8_t  qual;
+    uint8_t  l_extranul;
+    uint16_t flag;
+    uint16_t l_qname;
+    uint32_t n_cigar;
+    int32_t  l_qseq;
+    int32_t  mtid;
+    int64_t  mpos;
+    int64_t  isize;
+} hgpu_bam1_core;
+
+/* Step 1: find record starts.  d_stream[0..len) holds whole records back to back (the BAM
+ * header already skipped).  Writes d_rec_off[0..n) (byte offset of each record's block_size
+ * field) and *d_n_rec.  Returns HGPU_OK; *d_n_rec = (uint64)-1 flags a malformed chain. */
+int hgpu_bam_index_records_dev(hgpu_ctx *ctx, const uint8_t *d_stream, uint64_t len,
+                               uint64_t *d_rec_off, uint64_t rec_cap, uint64_t *d_n_rec, void *stream);
+
+/* Step 2: unpack n records.  Outputs (all device memory, any may be NULL to skip):
+ *  core[i]            bam1_core_t exactly as bam_read1 leaves it (incl. l_extranul padding and
+ *                     the recomputed bin, sam.c:809-822, :846-851)
+ *  data + data_off[i] the bam1_t::data bytes: qname padded with NULs to a multiple of 4,
+ *                     cigar, seq (4-bit), qual, aux (sam.c:832-840); data_off has n+1 entries
+ *  seq  + seq_off[i]  l_qseq ASCII bases (seq_nt16_str, hts.c:260); seq_off has n+1 entries
+ *  qual (same offsets) l_qseq bytes of QUAL+33, or '*' semantics left to the caller when
+ *                     qual[0]==0xff: raw bytes are copied unchanged in that case
+ *  status[i]          0, or -4 for the reference's "invalid record" conditions (sam.c:824-828)
+ */
+int hgpu_bam_unpack_dev(hgpu_ctx *ctx, const uint8_t *d_stream, uint64_t len,
+                        const uint64_t *d_rec_off, uint64_t n,
+                        hgpu_bam1_core *d_core,
+                        uint8_t *d_data, const uint64_t *d_data_off,
+                        uint8_t *d_seq, uint8_t *d_qual, const uint64_t *d_seq_off,
+                        int32_t *d_status, void *stream);
+
+/* Sizes pass for step 2: fills d_data_off[0..n] and d_seq_off[0..n] (exclusive prefix sums of
+ * l_data and l_qseq) so the caller can allocate; totals are the last entries. */
+int hgpu_bam_layout_dev(hgpu_ctx *ctx, const uint8_t *d_stream, uint64_t len,
+                        const uint64_t *d_rec_off, uint64_t n,
+                        uint64_t *d_data_off, uint64_t *d_seq_off, void *stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Reference-named shims (link seam B1: `./configure --with-external-htscodecs`, configure.ac:278).
+ * Same signatures, same malloc/free ownership, same NULL-on-error as htscodecs
+ * (rANS_static4x16.h:41-64).  Host pointers.  Re-entrant (a process-wide context per device is
+ * created on first use and guarded by a mutex).
+ * ---------------------------------------------------------------------------------------- */
+unsigned char *rans_uncompress_to_4x16(unsigned char *in, unsigned int in_size,
+                                       unsigned char *out, unsigned int *out_size);
+unsigned char *rans_uncompress_4x16(unsigned char *in, unsigned int in_size, unsigned int *out_size);
+/* hts_crc32 (htslib.map:657) */
+uint32_t hts_crc32(uint32_t crc, const void *buf, size_t len);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

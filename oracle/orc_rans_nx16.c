@@ -220,7 +220,12 @@ static int dec_order1(const uint8_t *in, uint32_t in_size, uint8_t *out, uint32_
     for (i = 0; i < 256; i++) nctx += A[i] != 0;
     store = calloc((size_t)(nctx + 1) << shift, sizeof(slot_t));
     if (!store) goto done;
-    for (i = 0; i < 256; i++) lut[i] = store;          /* absent contexts: all-zero row */
+    /* Contexts that are absent, or present with no frequencies, are never entered by a valid
+     * stream; the reference reads whatever its TLS scratch held (rANS_static4x16pr.c:589-591
+     * "continue").  The oracle pins that undefined case to a fixed row: symbol 0, f 0, b = slot
+     * index, which is also what the CUDA decoder produces. */
+    for (i = 0; i < (1 << shift); i++) store[i].b = (uint16_t)i;
+    for (i = 0; i < 256; i++) lut[i] = store;
     nctx = 1;
     for (i = 0; i < 256; i++) {
         uint32_t F[256] = {0}, T = 0;
