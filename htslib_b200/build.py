@@ -9,6 +9,9 @@ OUT = os.path.join(HERE, "libhtsgpu.so")
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
          "-Xcompiler", "-fPIC", "--use_fast_math", "-Xptxas", "-v"]
+FLAGS += os.environ.get("HGPU_DEFS", "").split()
+if os.environ.get("HGPU_PROFILE"):
+    FLAGS.append("-DHGPU_PROFILE")
 
 
 def sources():

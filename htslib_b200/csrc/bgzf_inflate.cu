@@ -21,9 +21,9 @@
 
 namespace {
 
-constexpr int LIT_ROOT = 10, DST_ROOT = 8;
-constexpr int LIT_TABLE = (1 << LIT_ROOT) + 1334;   // zlib "enough 286 10 15" = 1332 sub-table slots
-constexpr int DST_TABLE = (1 << DST_ROOT) + 600;    // generous for 30 symbols / 8 root bits
+constexpr int LIT_ROOT = 9, DST_ROOT = 8;
+constexpr int LIT_TABLE = (1 << LIT_ROOT) + 856;    // zlib "enough 286 9 15" = 852 sub-table slots
+constexpr int DST_TABLE = (1 << DST_ROOT) + 512;    // 30 symbols / 8 root bits: < 4 groups x 128
 constexpr int CL_TABLE = 128;
 
 enum : uint32_t { K_LIT = 0, K_LEN = 1, K_EOB = 2, K_SUB = 3, K_BAD = 4, K_DIST = 5 };
@@ -39,6 +39,8 @@ struct InflateSmem {
     uint32_t count[16];
     uint32_t next[16];
     uint32_t sub_alloc;
+    uint2    ptab[32 * 9];   // piece table of the current match batch (a match has <= 9 pieces)
+    uint2    rbuf[32];       // match records parked by the serial decoder
 };
 
 __constant__ uint16_t c_len_base[29] = {3,4,5,6,7,8,9,10,11,13,15,17,19,23,27,31,35,43,51,59,67,83,99,115,131,163,195,227,258};
@@ -46,6 +48,21 @@ __constant__ uint8_t  c_len_xtra[29] = {0,0,0,0,0,0,0,0,1,1,1,1,2,2,2,2,3,3,3,3,
 __constant__ uint16_t c_dst_base[30] = {1,2,3,4,5,7,9,13,17,25,33,49,65,97,129,193,257,385,513,769,1025,1537,2049,3073,4097,6145,8193,12289,16385,24577};
 __constant__ uint8_t  c_dst_xtra[30] = {0,0,0,0,1,1,2,2,3,3,4,4,5,5,6,6,7,7,8,8,9,9,10,10,11,11,12,12,13,13};
 __constant__ uint8_t  c_cl_order[19] = {16,17,18,0,8,7,9,6,10,5,11,4,12,3,13,2,14,1,15};
+
+// Optional per-phase cycle accounting (build with -DHGPU_PROFILE; read with hgpu_debug_profile).
+#ifdef HGPU_PROFILE
+__device__ unsigned long long g_prof[16];
+struct Prof {
+    long long t;
+    __device__ __forceinline__ void start() { t = clock64(); }
+    __device__ __forceinline__ void mark(int i) { long long n = clock64(); if (hgpu_lane() == 0) atomicAdd(&g_prof[i], (unsigned long long)(n - t)); t = n; }
+};
+#else
+struct Prof {
+    __device__ __forceinline__ void start() {}
+    __device__ __forceinline__ void mark(int) {}
+};
+#endif
 
 __device__ uint32_t g_crc_tab[4][256];      // slice-by-4 tables, filled once by crc_init_kernel
 
@@ -73,10 +90,15 @@ struct Bits {
     uint64_t buf;
     int cnt;               // valid bits in buf
     int64_t avail;         // bits of real input not yet moved into buf (may go negative = overrun)
+    uint32_t end_bits;     // input length in bits, measured from the member's first byte
 };
 
-__device__ __forceinline__ void bits_init(Bits &b, const uint8_t *p, uint32_t nbytes)
+// Start reading at byte `offset` of a member of `slen` bytes.
+__device__ __forceinline__ void bits_init(Bits &b, const uint8_t *src, uint32_t offset, uint32_t slen)
 {
+    const uint8_t *p = src + offset;
+    uint32_t nbytes = slen - offset;
+    b.end_bits = slen * 8;
     uintptr_t a = reinterpret_cast<uintptr_t>(p);
     uint32_t mis = (uint32_t)(a & 3);
     b.w = reinterpret_cast<const uint32_t *>(a - mis);
@@ -108,6 +130,8 @@ __device__ __forceinline__ void bits_drop(Bits &b, int n) { b.buf >>= n; b.cnt -
 __device__ __forceinline__ uint32_t bits_get(Bits &b, int n) { uint32_t v = bits_peek(b, n); bits_drop(b, n); return v; }
 // true once more bits were consumed than the input holds
 __device__ __forceinline__ bool bits_overrun(const Bits &b) { return b.avail + b.cnt < 0; }
+// bit position of the next unread bit, from the member's first byte
+__device__ __forceinline__ uint32_t bits_pos(const Bits &b) { return (uint32_t)((int64_t)b.end_bits - (b.avail + b.cnt)); }
 
 // ---------------------------------------------------------------------------------------------
 // Huffman table construction (warp-parallel).  lens[0..n) in shared memory.
@@ -246,7 +270,7 @@ __device__ uint32_t xpow_bytes(uint32_t nbytes)
 }
 
 // CRC-32 of out[0..n) by the whole warp.  Caller must have made the bytes visible.
-__device__ uint32_t warp_crc32(const uint8_t *out, uint32_t n)
+__device__ uint32_t warp_crc32(const uint32_t (*tab)[256], const uint8_t *out, uint32_t n)
 {
     const uint32_t lane = hgpu_lane();
     uint32_t c = n / 32, r = n % 32;
@@ -255,13 +279,23 @@ __device__ uint32_t warp_crc32(const uint8_t *out, uint32_t n)
     uint32_t len = lane == 0 ? c + r : c;
     uint32_t crc = 0xffffffffu;
     const uint8_t *p = out + beg, *e = p + len;
-    while (p < e && (reinterpret_cast<uintptr_t>(p) & 3)) crc = g_crc_tab[0][(crc ^ *p++) & 0xff] ^ (crc >> 8);
-    while (e - p >= 4) {
-        crc ^= *reinterpret_cast<const uint32_t *>(p);
-        crc = g_crc_tab[3][crc & 0xff] ^ g_crc_tab[2][(crc >> 8) & 0xff] ^ g_crc_tab[1][(crc >> 16) & 0xff] ^ g_crc_tab[0][crc >> 24];
-        p += 4;
+    while (p < e && (reinterpret_cast<uintptr_t>(p) & 15)) crc = tab[0][(crc ^ *p++) & 0xff] ^ (crc >> 8);
+    if (e - p >= 16) {
+        // 16 bytes per load, the next load always in flight (the data sits in L2, ~300 cycles away)
+        uint4 nx = *reinterpret_cast<const uint4 *>(p);
+        while (e - p >= 16) {
+            uint4 cur = nx;
+            p += 16;
+            if (e - p >= 16) nx = *reinterpret_cast<const uint4 *>(p);
+            uint32_t wv[4] = {cur.x, cur.y, cur.z, cur.w};
+#pragma unroll
+            for (int k = 0; k < 4; k++) {
+                crc ^= wv[k];
+                crc = tab[3][crc & 0xff] ^ tab[2][(crc >> 8) & 0xff] ^ tab[1][(crc >> 16) & 0xff] ^ tab[0][crc >> 24];
+            }
+        }
     }
-    while (p < e) crc = g_crc_tab[0][(crc ^ *p++) & 0xff] ^ (crc >> 8);
+    while (p < e) crc = tab[0][(crc ^ *p++) & 0xff] ^ (crc >> 8);
     crc = ~crc;
     if (c == 0) return __shfl_sync(0xffffffffu, crc, 0);
     // combine: crc(A||B) = crc(A) * x^(8|B|) ^ crc(B)   (crc32_combine).  Level d merges blocks
@@ -276,14 +310,358 @@ __device__ uint32_t warp_crc32(const uint8_t *out, uint32_t n)
 }
 
 // ---------------------------------------------------------------------------------------------
-// One BGZF block.
+// LZ77 match execution.
+//
+// A match is never copied on its own: that would be one round trip to L2 per match for bytes
+// this warp wrote a moment ago.  Matches are taken 32 at a time (one record per lane) and
+// executed OUT OF ORDER inside the batch.  Destinations inside a batch are ascending and
+// disjoint, so the earlier records a match reads from form one index range, found with two
+// 5-step binary searches over the lanes (shuffles) and kept as a 32-bit dependency mask.  Then,
+// in rounds, every record whose dependencies are done is cut into pieces of <= 32 bytes in a
+// shared-memory piece table and all those pieces are executed together: lane i moves byte i of
+// each piece (coalesced), and all loads of a chunk of GRP pieces are issued before any store.
+// The number of L2 round trips per batch is the depth of its dependency chain (1-4 for sorted
+// BAM), not the number of matches.  Overlapping matches (dist < len, run-length style) are rare
+// and take a separate cooperative path with a per-byte modulo.
+//
+// piece = { dst:16 | plen:6<<16 ,  src }      (offsets into the member's output)
+// ---------------------------------------------------------------------------------------------
+constexpr int GRP = 16;
+
+__device__ __forceinline__ uint32_t low_mask(uint32_t n) { return n >= 32u ? 0xffffffffu : (1u << n) - 1u; }
+
+__device__ __forceinline__ void exec_batch(uint8_t *out, InflateSmem &s, uint2 rec, uint32_t nrec)
+{
+    const uint32_t lane = hgpu_lane();
+    const bool have = lane < nrec;
+    const uint32_t len = have ? (rec.y & 0xffffu) : 0u, dist = rec.y >> 16;
+    const uint32_t dst = have ? rec.x : 0xffffffffu;            // padding lanes keep the arrays sorted
+    const uint32_t dst_end = have ? dst + len : 0xffffffffu;
+    const bool ov = dist < len;
+    const uint32_t src = dst - dist, src_end = ov ? dst : src + len;
+    uint32_t dep = 0;
+    const uint32_t dst0 = __shfl_sync(0xffffffffu, dst, 0);
+    if (__any_sync(0xffffffffu, have && src_end > dst0)) {
+        uint32_t j1 = 0, j2 = 0;                                 // #records with dst_end <= src ; #records with dst < src_end
+#pragma unroll
+        for (int st = 16; st >= 1; st >>= 1) {
+            uint32_t e = __shfl_sync(0xffffffffu, dst_end, j1 + st - 1);
+            uint32_t d = __shfl_sync(0xffffffffu, dst, j2 + st - 1);
+            if (e <= src) j1 += st;
+            if (d < src_end) j2 += st;
+        }
+        if (have && j2 > j1) dep = low_mask(j2) & ~low_mask(j1) & hgpu_lanemask_lt();
+    }
+    uint32_t done = low_mask(nrec) ^ 0xffffffffu;
+#ifdef HGPU_PROFILE
+    if (lane == 0) atomicAdd(&g_prof[9], 1ull);
+#endif
+    while (done != 0xffffffffu) {
+        const bool ready = !((done >> lane) & 1u) && (dep & ~done) == 0u;
+        const uint32_t R = __ballot_sync(0xffffffffu, ready);
+        const uint32_t Rov = __ballot_sync(0xffffffffu, ready && ov);
+        const uint32_t P = (ready && !ov) ? (len + 31u) >> 5 : 0u;
+        uint32_t inc = P;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            uint32_t t = __shfl_up_sync(0xffffffffu, inc, d);
+            if (lane >= (uint32_t)d) inc += t;
+        }
+        const uint32_t TP = __shfl_sync(0xffffffffu, inc, 31);
+#ifdef HGPU_PROFILE
+        if (lane == 0) { atomicAdd(&g_prof[8], 1ull); atomicAdd(&g_prof[10], (unsigned long long)TP); atomicAdd(&g_prof[11], (unsigned long long)__popc(Rov)); }
+#endif
+        if (P) {
+            uint32_t q = inc - P;
+            for (uint32_t off = 0; off < len; off += 32, q++) {
+                uint32_t plen = len - off < 32u ? len - off : 32u;
+                s.ptab[q] = make_uint2((dst + off) | (plen << 16), src + off);
+            }
+        }
+        __syncwarp();
+        for (uint32_t a = 0; a < TP; a += GRP) {
+            const uint32_t n = TP - a < (uint32_t)GRP ? TP - a : (uint32_t)GRP;
+            const uint2 *pt = s.ptab + a;
+            uint8_t v[GRP];
+            uint32_t px[GRP];
+#pragma unroll
+            for (int j = 0; j < GRP; j++) {
+                if ((uint32_t)j >= n) break;
+                uint2 d = pt[j];
+                px[j] = d.x;
+                if (lane < (d.x >> 16)) v[j] = out[d.y + lane];
+            }
+#pragma unroll
+            for (int j = 0; j < GRP; j++) {
+                if ((uint32_t)j >= n) break;
+                if (lane < (px[j] >> 16)) out[(px[j] & 0xffffu) + lane] = v[j];
+            }
+        }
+        // overlapping matches of this round: the source is the `dist` bytes before the
+        // destination, repeated
+        for (uint32_t m = Rov; m; m &= m - 1) {
+            const int k = __ffs(m) - 1;
+            const uint32_t d0 = __shfl_sync(0xffffffffu, dst, k), ln = __shfl_sync(0xffffffffu, len, k);
+            const uint32_t di = __shfl_sync(0xffffffffu, dist, k);
+            uint8_t w[9];
+            // i % di for i = lane, lane+32, ...: one division pair, then add-and-wrap
+            const uint32_t stepm = 32u % di;
+            uint32_t r = lane % di;
+#pragma unroll
+            for (int t = 0; t < 9; t++) {
+                uint32_t i = lane + 32 * t;
+                if (i < ln) w[t] = out[d0 - di + r];
+                r += stepm;
+                if (r >= di) r -= di;
+            }
+#pragma unroll
+            for (int t = 0; t < 9; t++) { uint32_t i = lane + 32 * t; if (i < ln) out[d0 + i] = w[t]; }
+        }
+        __syncwarp();                               // next round reads what other lanes just stored
+        done |= R;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Serial ("uniform") body decoder: all lanes walk the same bit stream.  Used for small deflate
+// blocks and as the fallback when speculation is not worthwhile.
+// ---------------------------------------------------------------------------------------------
+__device__ int decode_body_uniform(InflateSmem &s, Bits &b, uint8_t *out, uint32_t cap, uint32_t &o)
+{
+    const uint32_t lane = hgpu_lane();
+    uint32_t pend = 0;                             // match records parked in s.rbuf
+    for (;;) {
+        bits_fill(b);
+        uint32_t e = lookup<LIT_ROOT>(s.lit, b);
+        uint32_t kind = (e >> 4) & 15;
+        if (kind == K_LIT) {
+            if (o >= cap) return HGPU_BGZF_ERR_SPACE;
+            if (lane == 0) out[o] = (uint8_t)(e >> 16);
+            o++;
+            continue;
+        }
+        if (kind == K_EOB) break;
+        if (kind != K_LEN) return HGPU_BGZF_ERR_ZLIB;
+        uint32_t len = (e >> 16) + bits_get(b, (e >> 8) & 0xff);
+        bits_fill(b);
+        uint32_t d = lookup<DST_ROOT>(s.dst, b);
+        if (((d >> 4) & 15) != K_DIST) return HGPU_BGZF_ERR_ZLIB;
+        uint32_t dist = (d >> 16) + bits_get(b, (d >> 8) & 0xff);
+        if (bits_overrun(b)) return HGPU_BGZF_ERR_ZLIB;
+        if (dist > o) return HGPU_BGZF_ERR_ZLIB;
+        if (o + len > cap) return HGPU_BGZF_ERR_SPACE;
+        __syncwarp();
+        if (lane == 0) s.rbuf[pend] = make_uint2(o, len | (dist << 16));
+        o += len;
+        if (++pend == 32) { __syncwarp(); exec_batch(out, s, s.rbuf[lane], 32); pend = 0; }
+    }
+    __syncwarp();
+    if (pend) exec_batch(out, s, s.rbuf[lane], pend);
+    __syncwarp();
+    if (bits_overrun(b)) return HGPU_BGZF_ERR_ZLIB;
+    return HGPU_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Lane-parallel body decoder.
+//
+// The bit range of the deflate block body is cut into 32 equal sub-ranges.  Lane i decodes tokens
+// from a guessed start (the cut itself) to the end of its sub-range; Huffman streams
+// self-synchronise, so the position where lane i leaves its range is usually already the true
+// token boundary.  Each round lane i+1 restarts from lane i's exit if that moved; lane 0 is exact,
+// so after k rounds lanes 0..k are exact, and in practice two or three rounds settle all 32.
+// Then output offsets follow from a prefix sum of per-lane byte counts, a last pass writes the
+// literals and lists the matches, and the matches are executed in order through the window.
+// ---------------------------------------------------------------------------------------------
+struct LaneBits {
+    const uint32_t *w;      // next word to prefetch
+    uint64_t buf;
+    uint32_t nxt;           // prefetched word
+    int cnt;                // valid bits in buf
+    int lim;                // (position < end)  <=>  (cnt > lim)
+};
+
+__device__ __forceinline__ void lb_init(LaneBits &b, const uint32_t *wbase, const uint32_t *wend, uint32_t start, uint32_t end)
+{
+    uint32_t wi = start >> 5, off = start & 31;
+    const uint32_t *p = wbase + wi;
+    uint32_t w0 = p < wend ? __ldg(p) : 0;
+    b.nxt = p + 1 < wend ? __ldg(p + 1) : 0;
+    b.w = p + 2;
+    b.buf = w0 >> off;
+    b.cnt = 32 - (int)off;
+    b.lim = (int)((wi + 1) * 32) - (int)end;
+}
+__device__ __forceinline__ void lb_fill(LaneBits &b, const uint32_t *wend)
+{
+    if (b.cnt <= 32) {
+        b.buf |= (uint64_t)b.nxt << b.cnt;
+        b.cnt += 32;
+        b.lim += 32;
+        b.nxt = b.w < wend ? __ldg(b.w) : 0;
+        b.w++;
+    }
+}
+__device__ __forceinline__ uint32_t lb_pos(const LaneBits &b, uint32_t end) { return (uint32_t)(b.lim + (int)end - b.cnt); }
+
+template <int ROOT>
+__device__ __forceinline__ uint32_t lb_lookup(const uint32_t *table, LaneBits &b)
+{
+    uint32_t e = table[(uint32_t)b.buf & ((1u << ROOT) - 1)];
+    if (((e >> 4) & 15) == K_SUB) {
+        b.buf >>= ROOT; b.cnt -= ROOT;
+        e = table[(e >> 16) + ((uint32_t)b.buf & ((1u << ((e >> 8) & 0xff)) - 1))];
+    }
+    b.buf >>= (e & 15); b.cnt -= (int)(e & 15);
+    return e;
+}
+
+enum : uint32_t { ST_RUN = 0, ST_EOB = 1, ST_BAD = 2 };
+
+// Decode tokens in [start, end).  EMIT=false: count output bytes / matches.  EMIT=true: write
+// literals at out[obase..] and match records at mrec[mbase..]; sets bad_dist on a distance that
+// reaches before the start of the output.
+template <bool EMIT>
+__device__ __forceinline__ void lane_decode(const InflateSmem &s, const uint32_t *wbase, const uint32_t *wend,
+                                            uint32_t start, uint32_t end, uint32_t &exitp, uint32_t &nout,
+                                            uint32_t &nmatch, uint32_t &st, uint8_t *out, uint32_t obase,
+                                            uint2 *mrec, uint32_t mbase, bool &bad_dist)
+{
+    LaneBits b;
+    uint32_t n = 0, m = 0, status = ST_RUN;
+    if (start >= end) { exitp = start; nout = 0; nmatch = 0; st = ST_RUN; return; }
+    lb_init(b, wbase, wend, start, end);
+    while (b.cnt > b.lim) {
+        lb_fill(b, wend);
+        uint32_t e = lb_lookup<LIT_ROOT>(s.lit, b);
+        uint32_t kind = (e >> 4) & 15;
+        if (kind == K_LIT) {
+            if (EMIT) out[obase + n] = (uint8_t)(e >> 16);
+            n++;
+        } else if (kind == K_LEN) {
+            uint32_t xb = (e >> 8) & 0xff;
+            uint32_t len = (e >> 16) + ((uint32_t)b.buf & ((1u << xb) - 1));
+            b.buf >>= xb; b.cnt -= (int)xb;
+            lb_fill(b, wend);
+            uint32_t d = lb_lookup<DST_ROOT>(s.dst, b);
+            if (((d >> 4) & 15) != K_DIST) { status = ST_BAD; break; }
+            uint32_t xd = (d >> 8) & 0xff;
+            uint32_t dist = (d >> 16) + ((uint32_t)b.buf & ((1u << xd) - 1));
+            b.buf >>= xd; b.cnt -= (int)xd;
+            if (EMIT) {
+                uint32_t dstpos = obase + n;
+                if (dist > dstpos) bad_dist = true;
+                mrec[mbase + m] = make_uint2(dstpos, len | (dist << 16));
+            }
+            n += len; m++;
+        } else if (kind == K_EOB) { status = ST_EOB; break; }
+        else { status = ST_BAD; break; }
+    }
+    exitp = lb_pos(b, end);
+    nout = n; nmatch = m; st = status;
+}
+
+// Execute mrec[0..total) in order through the window.  Records are fetched 32 at a time
+// (coalesced) and broadcast with shuffles, so every lane sees the same match.
+__device__ void run_matches(InflateSmem &s, uint8_t *out, const uint2 *mrec, uint32_t total)
+{
+    const uint32_t lane = hgpu_lane();
+    uint2 nx = lane < total ? mrec[lane] : make_uint2(0, 0);
+    for (uint32_t base = 0; base < total; base += 32) {
+        uint2 rec = nx;
+        nx = base + 32 + lane < total ? mrec[base + 32 + lane] : make_uint2(0, 0);      // next batch in flight
+        exec_batch(out, s, rec, total - base < 32u ? total - base : 32u);
+    }
+    __syncwarp();
+}
+
+constexpr uint32_t PAR_MIN_BITS = 32 * 96;      // below this a deflate block is decoded serially
+constexpr uint32_t MREC_CAP = 65536 / 3 + 64;   // a match yields >= 3 bytes of a <= 64 KiB member
+
+// Parallel decode of one Huffman block body starting at bit `body` of the member (bit 0 = first
+// bit of word wbase[0], i.e. positions include the alignment offset).  total = end of input.
+__device__ int decode_body_parallel(InflateSmem &s, const uint32_t *wbase, const uint32_t *wend, uint32_t body,
+                                    uint32_t total, uint8_t *out, uint32_t cap, uint32_t &o, uint2 *mrec,
+                                    uint32_t &end_pos, Prof &pf)
+{
+    const uint32_t lane = hgpu_lane();
+    const uint32_t S = (total - body + 31) / 32;
+    uint32_t start = body + lane * S;
+    uint32_t end = lane == 31 ? total : min(total, body + (lane + 1) * S);
+    if (start > total) start = total;
+    uint32_t exitp = 0, n = 0, m = 0, st = ST_RUN;
+    bool need = true, dummy = false;
+    for (int round = 0; round < 34; round++) {
+        if (need) lane_decode<false>(s, wbase, wend, start, end, exitp, n, m, st, nullptr, 0, nullptr, 0, dummy);
+        uint32_t prev = __shfl_up_sync(0xffffffffu, exitp, 1);
+        uint32_t ns = lane == 0 ? start : prev;
+        need = ns != start;
+        start = ns;
+        if (!__any_sync(0xffffffffu, need)) break;
+    }
+    pf.mark(1);
+    // the chain is now consistent: lane i starts where lane i-1 stopped
+    uint32_t eob = __ballot_sync(0xffffffffu, st == ST_EOB);
+    uint32_t bad = __ballot_sync(0xffffffffu, st == ST_BAD);
+    if (!eob) return HGPU_BGZF_ERR_ZLIB;                       // input ends without an end-of-block code
+    uint32_t E = __ffs(eob) - 1;
+    if (bad & ((2u << E) - 1u)) return HGPU_BGZF_ERR_ZLIB;     // invalid code at or before the end of block
+    uint32_t last = __shfl_sync(0xffffffffu, exitp, E);
+    if (last > total) return HGPU_BGZF_ERR_ZLIB;               // the block ran past the input
+    if (lane > E) { n = 0; m = 0; }
+    // exclusive prefix sums of bytes and matches
+    uint32_t on = n, mn = m;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        uint32_t a = __shfl_up_sync(0xffffffffu, on, d), c = __shfl_up_sync(0xffffffffu, mn, d);
+        if (lane >= (uint32_t)d) { on += a; mn += c; }
+    }
+    uint32_t tot_out = __shfl_sync(0xffffffffu, on, 31), tot_m = __shfl_sync(0xffffffffu, mn, 31);
+    if ((uint64_t)o + tot_out > cap) return HGPU_BGZF_ERR_SPACE;
+    if (tot_m > MREC_CAP) return HGPU_BGZF_ERR_ZLIB;           // impossible within 64 KiB of output
+    // Make the destination sectors fully valid in L2 before any byte-granular write lands in
+    // them: a load from a sector that holds only some freshly written bytes has to wait for the
+    // rest of the sector to come from DRAM, and the match copies below read what was just written.
+    // Only 16-byte units entirely inside this block's range are touched (neighbouring blocks are
+    // being written by other warps).
+    {
+        uintptr_t lo = (reinterpret_cast<uintptr_t>(out + o) + 15) & ~(uintptr_t)15;
+        uintptr_t hi = reinterpret_cast<uintptr_t>(out + o + tot_out) & ~(uintptr_t)15;
+        for (uintptr_t a = lo + 16 * lane; a < hi; a += 16 * 32)
+            *reinterpret_cast<uint4 *>(a) = make_uint4(0, 0, 0, 0);
+        __syncwarp();
+    }
+    bool bad_dist = false;
+    if (lane <= E) {
+        uint32_t e2, n2, m2, st2;
+        lane_decode<true>(s, wbase, wend, start, end, e2, n2, m2, st2, out, o + on - n, mrec, mn - m, bad_dist);
+    }
+    if (__any_sync(0xffffffffu, bad_dist)) return HGPU_BGZF_ERR_ZLIB;   // distance too far back
+    __syncwarp();
+    __threadfence_block();
+    pf.mark(2);
+    run_matches(s, out, mrec, tot_m);
+    pf.mark(3);
+    o += tot_out;
+    end_pos = last;
+    return HGPU_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// One BGZF member: headers + table construction are warp-uniform, bodies go to one of the two
+// decoders above.
 // ---------------------------------------------------------------------------------------------
 __device__ int inflate_member(InflateSmem &s, const uint8_t *src, uint32_t slen, uint8_t *out, uint32_t cap,
-                              uint32_t &olen)
+                              uint32_t &olen, uint2 *mrec, Prof &pf)
 {
     const uint32_t lane = hgpu_lane();
     Bits b;
-    bits_init(b, src, slen);
+    bits_init(b, src, 0, slen);
+    const uintptr_t a0 = reinterpret_cast<uintptr_t>(src);
+    const uint32_t mis_bits = (uint32_t)(a0 & 3) * 8;
+    const uint32_t *wbase = reinterpret_cast<const uint32_t *>(a0 - (a0 & 3));
+    const uint32_t *wend = reinterpret_cast<const uint32_t *>((a0 + slen + 3) & ~(uintptr_t)3);
+    const uint32_t total = mis_bits + slen * 8;                // end of input in wbase bit coordinates
     uint32_t o = 0;
     for (;;) {
         bits_fill(b);
@@ -296,14 +674,13 @@ __device__ int inflate_member(InflateSmem &s, const uint8_t *src, uint32_t slen,
             uint32_t nlen = bits_get(b, 16);
             if (bits_overrun(b)) return HGPU_BGZF_ERR_ZLIB;
             if ((len ^ 0xffffu) != nlen) return HGPU_BGZF_ERR_ZLIB;
-            // byte position of the payload inside src
-            int64_t consumed_bits = (int64_t)slen * 8 - (b.avail + b.cnt);
-            uint32_t pos = (uint32_t)(consumed_bits >> 3);
+            uint32_t pos = bits_pos(b) >> 3;
             if ((uint64_t)pos + len > slen) return HGPU_BGZF_ERR_ZLIB;
             if (o + len > cap) return HGPU_BGZF_ERR_SPACE;
             for (uint32_t i = lane; i < len; i += 32) out[o + i] = src[pos + i];
             o += len;
-            bits_init(b, src + pos + len, slen - pos - len);
+            bits_init(b, src, pos + len, slen);
+            __syncwarp();
         } else if (type == 1 || type == 2) {
             int rc;
             if (type == 1) {
@@ -333,9 +710,7 @@ __device__ int inflate_member(InflateSmem &s, const uint8_t *src, uint32_t slen,
                 __syncwarp();
                 rc = build_table<7, CL_TABLE>(s, s.cl, 19, false, cl_entry);
                 if (rc) return HGPU_BGZF_ERR_ZLIB;
-                // code lengths: serial by nature (run-length coded); uniform across lanes
                 uint32_t nsym = hlit + hdist, i = 0, prev = 0;
-                // lens[] is reused for the result, so stage in code[] (uint16) first
                 while (i < nsym) {
                     bits_fill(b);
                     uint32_t e = s.cl[bits_peek(b, 7)];
@@ -359,7 +734,6 @@ __device__ int inflate_member(InflateSmem &s, const uint8_t *src, uint32_t slen,
                 }
                 __syncwarp();
                 if (s.code[256] == 0) return HGPU_BGZF_ERR_ZLIB;         // no end-of-block code
-                // distance lengths first (they sit after the literal lengths in code[])
                 uint32_t dl = lane < hdist ? s.code[hlit + lane] : 0;
                 uint32_t ll[9];
 #pragma unroll
@@ -377,38 +751,24 @@ __device__ int inflate_member(InflateSmem &s, const uint8_t *src, uint32_t slen,
                 if (rc) return HGPU_BGZF_ERR_ZLIB;
             }
             __syncwarp();
-            // ---- token loop (warp-uniform) ----
-            for (;;) {
-                bits_fill(b);
-                uint32_t e = lookup<LIT_ROOT>(s.lit, b);
-                uint32_t kind = (e >> 4) & 15;
-                if (kind == K_LIT) {
-                    if (o >= cap) return HGPU_BGZF_ERR_SPACE;
-                    if (lane == 0) out[o] = (uint8_t)(e >> 16);
-                    o++;
-                    continue;
-                }
-                if (kind == K_EOB) break;
-                if (kind != K_LEN) return HGPU_BGZF_ERR_ZLIB;
-                uint32_t len = (e >> 16) + bits_get(b, (e >> 8) & 0xff);
-                bits_fill(b);
-                uint32_t d = lookup<DST_ROOT>(s.dst, b);
-                if (((d >> 4) & 15) != K_DIST) return HGPU_BGZF_ERR_ZLIB;
-                uint32_t dist = (d >> 16) + bits_get(b, (d >> 8) & 0xff);
-                if (bits_overrun(b)) return HGPU_BGZF_ERR_ZLIB;
-                if (dist > o) return HGPU_BGZF_ERR_ZLIB;
-                if (o + len > cap) return HGPU_BGZF_ERR_SPACE;
-                __syncwarp();                      // earlier stores (other lanes) visible to this warp
-                const uint8_t *from = out + o - dist;
-                if (dist >= len) {
-                    for (uint32_t i = lane; i < len; i += 32) out[o + i] = from[i];
-                } else {
-                    for (uint32_t i = lane; i < len; i += 32) out[o + i] = from[i % dist];
-                }
-                __syncwarp();
-                o += len;
-            }
+            // position of the first body bit, in wbase coordinates
             if (bits_overrun(b)) return HGPU_BGZF_ERR_ZLIB;
+            uint32_t body = mis_bits + bits_pos(b);
+            pf.mark(0);
+            if (total - body >= PAR_MIN_BITS) {
+                uint32_t end_pos = 0;
+                rc = decode_body_parallel(s, wbase, wend, body, total, out, cap, o, mrec, end_pos, pf);
+                if (rc) return rc;
+                // continue the uniform reader right after the end-of-block code
+                uint32_t byte = (end_pos - mis_bits) >> 3, bit = (end_pos - mis_bits) & 7;
+                bits_init(b, src, byte, slen);
+                bits_fill(b);
+                bits_drop(b, bit);
+            } else {
+                rc = decode_body_uniform(s, b, out, cap, o);
+                if (rc) return rc;
+                pf.mark(5);
+            }
         } else
             return HGPU_BGZF_ERR_ZLIB;
         if (final) break;
@@ -423,13 +783,21 @@ __device__ int check_header(const uint8_t *h)
     return ((h[3] & 4) && (h[10] | h[11] << 8) == 6 && h[12] == 'B' && h[13] == 'C' && (h[14] | h[15] << 8) == 2) ? 0 : -1;
 }
 
-__global__ void __launch_bounds__(32)
+constexpr int INFLATE_WARPS = 4;      // warps per CTA; they share only the CRC tables
+
+__global__ void __launch_bounds__(32 * INFLATE_WARPS, 3)
 bgzf_inflate_kernel(const uint8_t *__restrict__ in, const uint64_t *__restrict__ in_off,
                     const uint32_t *__restrict__ in_len, uint32_t n, uint8_t *out,
                     const uint64_t *__restrict__ out_off, const uint32_t *__restrict__ out_cap,
-                    uint32_t *out_len, int32_t *status, uint32_t *counter)
+                    uint32_t *out_len, int32_t *status, uint32_t *counter, uint2 *mrec_all)
 {
-    __shared__ InflateSmem s;
+    extern __shared__ __align__(16) uint8_t dyn_smem[];
+    uint32_t (*crc_tab)[256] = reinterpret_cast<uint32_t (*)[256]>(dyn_smem);
+    InflateSmem *smem_all = reinterpret_cast<InflateSmem *>(dyn_smem + 4096);
+    for (int i = threadIdx.x; i < 1024; i += blockDim.x) (&crc_tab[0][0])[i] = (&g_crc_tab[0][0])[i];
+    __syncthreads();                                   // the only block-wide barrier: warps are independent below
+    InflateSmem &s = smem_all[threadIdx.x >> 5];
+    uint2 *mrec = mrec_all + ((size_t)blockIdx.x * INFLATE_WARPS + (threadIdx.x >> 5)) * MREC_CAP;
     const uint32_t lane = hgpu_lane();
     for (;;) {
         uint32_t job = 0;
@@ -447,13 +815,17 @@ bgzf_inflate_kernel(const uint8_t *__restrict__ in, const uint64_t *__restrict__
             rc = HGPU_BGZF_ERR_HEADER;
         else {
             // inflate_block hands zlib block_length-18 bytes: deflate data plus the 8-byte footer
-            rc = inflate_member(s, blk + 18, blen - 18, dst, cap, got);
+            Prof pf;
+            pf.start();
+            rc = inflate_member(s, blk + 18, blen - 18, dst, cap, got, mrec, pf);
             if (rc == HGPU_OK) {
                 __syncwarp();
                 __threadfence_block();
                 uint32_t want = blk[blen - 8] | blk[blen - 7] << 8 | blk[blen - 6] << 16 | (uint32_t)blk[blen - 5] << 24;
-                uint32_t crc = warp_crc32(dst, got);
+                pf.mark(6);
+                uint32_t crc = warp_crc32(crc_tab, dst, got);
                 if (crc != want) rc = HGPU_BGZF_ERR_CRC;
+                pf.mark(4);
             }
         }
         __syncwarp();
@@ -468,7 +840,7 @@ __global__ void crc32_chunks_kernel(const uint8_t *buf, size_t len, size_t chunk
     size_t beg = w * chunk;
     if (beg >= len) return;
     size_t n = len - beg < chunk ? len - beg : chunk;
-    uint32_t crc = warp_crc32(buf + beg, (uint32_t)n);
+    uint32_t crc = warp_crc32(g_crc_tab, buf + beg, (uint32_t)n);
     if (hgpu_lane() == 0) partial[w] = crc;
 }
 
@@ -496,17 +868,44 @@ int hgpu_launch_bgzf_inflate(hgpu_ctx *ctx, const uint8_t *d_in, const uint64_t 
     int rc = ensure_crc_tables(ctx, st);
     if (rc) return rc;
     int per_sm = 0;
-    if (hgpu_check(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, bgzf_inflate_kernel, 32, 0), "inflate occupancy"))
+    const size_t dyn = 4096 + INFLATE_WARPS * sizeof(InflateSmem);
+    static bool attr_set = false;
+    if (!attr_set) {
+        if (hgpu_check(cudaFuncSetAttribute(bgzf_inflate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn), "inflate smem attr"))
+            return HGPU_ERR_CUDA;
+        attr_set = true;
+    }
+    if (hgpu_check(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, bgzf_inflate_kernel, 32 * INFLATE_WARPS, dyn), "inflate occupancy"))
         return HGPU_ERR_CUDA;
     if (per_sm < 1) per_sm = 1;
     uint32_t grid = (uint32_t)ctx->sm_count * (uint32_t)per_sm;
-    if (grid > n) grid = n;
+    if (grid > (n + INFLATE_WARPS - 1) / INFLATE_WARPS) grid = (n + INFLATE_WARPS - 1) / INFLATE_WARPS;
     uint32_t *counter = hgpu_take_counter(ctx, st);
     if (!counter) return HGPU_ERR_CUDA;
-    bgzf_inflate_kernel<<<grid, 32, 0, st>>>(d_in, d_in_off, d_in_len, n, d_out, d_out_off, d_out_cap,
-                                             d_out_len, d_status, counter);
+    // match-record scratch, one slot per resident warp, sized for the full grid so concurrent
+    // launches on other streams (the pipelined host path) can share the same layout
+    uint32_t full_grid = (uint32_t)ctx->sm_count * (uint32_t)per_sm;
+    full_grid *= INFLATE_WARPS;                        // one record slot per resident warp
+    rc = hgpu_ensure_mrec(ctx, (size_t)full_grid * MREC_CAP * sizeof(uint2) * 3);
+    if (rc) return rc;
+    uint2 *mrec = reinterpret_cast<uint2 *>(ctx->d_mrec) + (size_t)(ctx->next_counter % 3) * full_grid * MREC_CAP;
+    bgzf_inflate_kernel<<<grid, 32 * INFLATE_WARPS, dyn, st>>>(d_in, d_in_off, d_in_len, n, d_out, d_out_off, d_out_cap,
+                                             d_out_len, d_status, counter, mrec);
     hgpu_count_launch();
     return hgpu_check(cudaGetLastError(), "inflate launch");
+}
+
+extern "C" int hgpu_debug_profile(unsigned long long *out8)
+{
+#ifdef HGPU_PROFILE
+    unsigned long long z[16] = {0};
+    if (cudaMemcpyFromSymbol(out8, g_prof, sizeof(z)) != cudaSuccess) return -1;
+    cudaMemcpyToSymbol(g_prof, z, sizeof(z));
+    return 0;
+#else
+    (void)out8;
+    return -1;
+#endif
 }
 
 // CRC-32 of a device buffer: per-chunk warp CRCs, combined on the host side of the ABI by the
