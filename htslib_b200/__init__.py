@@ -47,6 +47,9 @@ def lib():
     L.hgpu_crc32.argtypes = [vp, u32, vp, C.c_size_t]
     L.hgpu_rans_nx16_decode_batch_dev.argtypes = [vp, vp, vp, vp, u32, vp, vp, vp, vp, vp, u32, vp]
     L.hgpu_rans_nx16_decode_batch_host.argtypes = [vp, vp, vp, vp, u32, vp, vp, vp, vp, vp]
+    L.hgpu_bam_index_records_dev.argtypes = [vp, vp, u64, vp, u64, vp, u64, vp, vp]
+    L.hgpu_bam_layout_dev.argtypes = [vp, vp, u64, vp, u64, vp, vp, vp]
+    L.hgpu_bam_unpack_dev.argtypes = [vp, vp, u64, vp, u64, vp, vp, vp, vp, vp, vp, vp, vp]
     L.rans_uncompress_to_4x16.restype = vp
     L.rans_uncompress_to_4x16.argtypes = [vp, C.c_uint, vp, C.POINTER(C.c_uint)]
     L.rans_uncompress_4x16.restype = vp
@@ -98,6 +101,37 @@ class Context:
                                                     d_out.data_ptr(), d_out_off.data_ptr(), d_out_len.data_ptr(),
                                                     d_got.data_ptr(), d_status.data_ptr(), int(max_out_len), stream),
               "rans_nx16_decode_batch_dev")
+
+    def bam_unpack_dev(self, d_stream, length, d_hint=None, want_text=True, stream=0):
+        """index -> layout -> unpack of an inflated BAM record stream resident on the device.
+        Returns dict of torch tensors: rec_off, core (n x 48 bytes), data, data_off, seq, qual, seq_off, status."""
+        import torch
+        dev = d_stream.device
+        L = lib()
+        d_n = torch.zeros(1, dtype=torch.int64, device=dev)
+        nh = d_hint.numel() if d_hint is not None else 0
+        hp = d_hint.data_ptr() if d_hint is not None else None
+        check(L.hgpu_bam_index_records_dev(self.h, d_stream.data_ptr(), length, hp, nh, None, 0, d_n.data_ptr(), stream), "bam_index(count)")
+        torch.cuda.synchronize()
+        n = int(d_n.item())
+        if n < 0:
+            raise HgpuError("malformed BAM record chain")
+        rec_off = torch.empty(max(1, n), dtype=torch.int64, device=dev)
+        check(L.hgpu_bam_index_records_dev(self.h, d_stream.data_ptr(), length, hp, nh, rec_off.data_ptr(), n, d_n.data_ptr(), stream), "bam_index")
+        data_off = torch.empty(n + 1, dtype=torch.int64, device=dev)
+        seq_off = torch.empty(n + 1, dtype=torch.int64, device=dev)
+        check(L.hgpu_bam_layout_dev(self.h, d_stream.data_ptr(), length, rec_off.data_ptr(), n, data_off.data_ptr(), seq_off.data_ptr(), stream), "bam_layout")
+        torch.cuda.synchronize()
+        nd, ns = int(data_off[n].item()), int(seq_off[n].item())
+        core = torch.empty((max(1, n), 48), dtype=torch.uint8, device=dev)
+        data = torch.empty(max(1, nd), dtype=torch.uint8, device=dev)
+        seq = torch.empty(max(1, ns), dtype=torch.uint8, device=dev) if want_text else None
+        qual = torch.empty(max(1, ns), dtype=torch.uint8, device=dev) if want_text else None
+        status = torch.empty(max(1, n), dtype=torch.int32, device=dev)
+        check(L.hgpu_bam_unpack_dev(self.h, d_stream.data_ptr(), length, rec_off.data_ptr(), n, core.data_ptr(), data.data_ptr(),
+                                    data_off.data_ptr(), seq.data_ptr() if want_text else None, qual.data_ptr() if want_text else None,
+                                    seq_off.data_ptr(), status.data_ptr(), stream), "bam_unpack")
+        return dict(n=n, rec_off=rec_off, core=core, data=data, data_off=data_off, seq=seq, qual=qual, seq_off=seq_off, status=status)
 
     # ---- host-pointer entry points; buffers are numpy uint8 arrays (or pinned torch tensors' .numpy()) ----
     def bgzf_inflate_file_host(self, file_np, out_np):

@@ -1,0 +1,367 @@
+// BAM record unpack for sm_100a: the data movement of bam_read1 (htslib sam.c:784-860) plus the
+// 4-bit SEQ expand and QUAL+33 of sam_format1_append (sam.c:4324-4404; nibble2base,
+// sam_internal.h:63-118; add33, sam.c:4317-4322), over an inflated BAM record stream that is
+// already resident in device memory (the output of the BGZF inflate kernel).
+//
+// Three steps, all on the device:
+//  1. record index.  Records are a length-prefixed chain (block_size, sam.c:793-799), serial by
+//     nature.  The caller passes candidate record starts (the BGZF block boundaries: htslib's
+//     writer does not split records across blocks when it can avoid it, bgzf_flush_try sam.c:888),
+//     one thread walks the chain of each segment speculatively, a fix-up pass re-walks only the
+//     segments whose guessed start was not where the previous segment ended, a prefix sum of the
+//     per-segment counts gives every record its global index.
+//  2. layout: per-record l_data / l_qseq -> exclusive prefix sums (offsets of the SoA blobs).
+//  3. unpack: one warp per record: bam1_core_t exactly as bam_read1 leaves it (l_extranul
+//     padding, recomputed bin, CIGAR/qlen check), the bam1_t::data bytes, ASCII bases, QUAL+33.
+#include "hgpu_internal.h"
+
+namespace {
+
+constexpr uint64_t BROKEN = ~0ull;
+
+__device__ __forceinline__ uint32_t ld32(const uint8_t *p)
+{
+    return p[0] | (uint32_t)p[1] << 8 | (uint32_t)p[2] << 16 | (uint32_t)p[3] << 24;
+}
+
+// walk records from `pos` while pos < end; returns count (or BROKEN) and the exit position
+__device__ uint64_t walk(const uint8_t *st, uint64_t len, uint64_t pos, uint64_t end, uint64_t &exitp,
+                         uint64_t *emit, uint64_t emit_cap, uint64_t emit_base)
+{
+    uint64_t n = 0;
+    while (pos < end) {
+        if (len - pos < 4) { exitp = pos; return BROKEN; }
+        int32_t bl = (int32_t)ld32(st + pos);
+        if (bl < 32 || pos + 4 + (uint64_t)bl > len) { exitp = pos; return BROKEN; }
+        if (emit && emit_base + n < emit_cap) emit[emit_base + n] = pos;
+        n++;
+        pos += 4 + (uint64_t)bl;
+    }
+    exitp = pos;
+    return n;
+}
+
+__global__ void bam_seg_scan_kernel(const uint8_t *st, uint64_t len, const uint64_t *hint, uint64_t nseg,
+                                    uint64_t *seg_start, uint64_t *seg_cnt, uint64_t *seg_exit)
+{
+    uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nseg) return;
+    uint64_t s = hint ? hint[i] : 0, e = (hint && i + 1 < nseg) ? hint[i + 1] : len;
+    if (s > len) s = len;
+    if (e > len) e = len;
+    uint64_t ex;
+    seg_start[i] = s;
+    seg_cnt[i] = walk(st, len, s, e, ex, nullptr, 0, 0);
+    seg_exit[i] = ex;
+}
+
+// single CTA: make the chain consistent, then exclusive-scan the counts
+__global__ void __launch_bounds__(1024)
+bam_seg_fix_kernel(const uint8_t *st, uint64_t len, const uint64_t *hint, uint64_t nseg, uint64_t *seg_start,
+                   uint64_t *seg_cnt, uint64_t *seg_exit, uint64_t *seg_base, uint64_t *n_rec)
+{
+    __shared__ uint64_t part[1024];
+    __shared__ int again;
+    const uint32_t t = threadIdx.x;
+    for (;;) {
+        if (t == 0) again = 0;
+        __syncthreads();
+        // phase A: who starts in the wrong place?
+        for (uint64_t base = 0; base < nseg; base += 1024) {
+            uint64_t i = base + t;
+            bool fix = false;
+            uint64_t want = 0;
+            if (i >= 1 && i < nseg) {
+                uint64_t pe = seg_exit[i - 1];
+                // a broken predecessor leaves its exit where it stopped; successors keep their guess
+                if (seg_cnt[i - 1] != BROKEN && pe != seg_start[i]) { fix = true; want = pe; }
+            }
+            __syncthreads();
+            if (fix) {
+                uint64_t e = i + 1 < nseg ? hint[i + 1] : len, ex;
+                if (e > len) e = len;
+                seg_start[i] = want;
+                seg_cnt[i] = walk(st, len, want, e, ex, nullptr, 0, 0);
+                seg_exit[i] = ex;
+                again = 1;
+            }
+            __syncthreads();
+        }
+        if (!again) break;
+        __syncthreads();
+    }
+    // exclusive scan of counts (chunked over the CTA)
+    const uint64_t per = (nseg + 1023) / 1024;
+    uint64_t lo = (uint64_t)t * per, hi = lo + per < nseg ? lo + per : nseg, sum = 0;
+    bool broken = false;
+    for (uint64_t i = lo; i < hi; i++) { uint64_t c = seg_cnt[i]; if (c == BROKEN) broken = true; else sum += c; }
+    part[t] = sum;
+    __syncthreads();
+    if (__syncthreads_or(broken)) { if (t == 0) *n_rec = BROKEN; return; }
+    if (t == 0) {
+        uint64_t run = 0;
+        for (int k = 0; k < 1024; k++) { uint64_t v = part[k]; part[k] = run; run += v; }
+        *n_rec = run;
+    }
+    __syncthreads();
+    uint64_t run = part[t];
+    for (uint64_t i = lo; i < hi; i++) { seg_base[i] = run; run += seg_cnt[i]; }
+}
+
+__global__ void bam_seg_emit_kernel(const uint8_t *st, uint64_t len, const uint64_t *hint, uint64_t nseg,
+                                    const uint64_t *seg_start, const uint64_t *seg_base, uint64_t *rec_off,
+                                    uint64_t rec_cap)
+{
+    uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nseg) return;
+    uint64_t e = (hint && i + 1 < nseg) ? hint[i + 1] : len, ex;
+    if (e > len) e = len;
+    walk(st, len, seg_start[i], e, ex, rec_off, rec_cap, seg_base[i]);
+}
+
+// ---------------------------------------------------------------------------------------------
+// sizes + generic u64 exclusive scan (three passes, 1024-element tiles)
+// ---------------------------------------------------------------------------------------------
+struct RecGeom { int32_t bl; uint32_t qn, xn, n_cigar, lq; bool ok, missing_nul; uint32_t l_data; };
+
+// the validity rules of bam_read1 (sam.c:799, :824-828) and fixup_missing_qname_nul (:763-778)
+__device__ __forceinline__ RecGeom geom(const uint8_t *rec)
+{
+    RecGeom g;
+    g.bl = (int32_t)ld32(rec);
+    g.qn = rec[12];
+    g.n_cigar = ld32(rec + 16) & 0xffffu;
+    int32_t lq = (int32_t)ld32(rec + 20);
+    g.lq = (uint32_t)lq;
+    g.xn = (g.qn & 3) ? 4 - (g.qn & 3) : 0;
+    uint64_t nl = (uint64_t)(uint32_t)(g.bl - 32) + g.xn;
+    g.ok = !(g.bl < 32 || nl > 0x7fffffffull || lq < 0 || g.qn < 1);
+    if (g.ok && ((uint64_t)g.n_cigar << 2) + g.qn + g.xn + (((uint64_t)g.lq + 1) >> 1) + (uint64_t)g.lq > nl) g.ok = false;
+    g.missing_nul = g.ok && rec[36 + g.qn - 1] != 0;
+    if (g.missing_nul && g.xn == 0) nl += 4;
+    g.l_data = g.ok ? (uint32_t)nl : 0;
+    if (!g.ok) g.lq = 0;
+    return g;
+}
+
+__global__ void bam_sizes_kernel(const uint8_t *st, const uint64_t *rec_off, uint64_t n, uint64_t *data_sz, uint64_t *seq_sz)
+{
+    uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i > n) return;
+    if (i == n) { data_sz[n] = 0; seq_sz[n] = 0; return; }
+    RecGeom g = geom(st + rec_off[i]);
+    data_sz[i] = g.l_data;
+    seq_sz[i] = g.lq;
+}
+
+constexpr int TILE = 1024;
+
+__global__ void __launch_bounds__(256) scan_tiles_reduce(const uint64_t *a, const uint64_t *b, uint64_t n, uint64_t *ta, uint64_t *tb)
+{
+    __shared__ uint64_t sa[256], sb[256];
+    uint64_t base = (uint64_t)blockIdx.x * TILE, va = 0, vb = 0;
+    for (int k = 0; k < 4; k++) { uint64_t i = base + threadIdx.x + 256 * k; if (i < n) { va += a[i]; vb += b[i]; } }
+    sa[threadIdx.x] = va; sb[threadIdx.x] = vb;
+    __syncthreads();
+    for (int s = 128; s > 0; s >>= 1) {
+        if ((int)threadIdx.x < s) { sa[threadIdx.x] += sa[threadIdx.x + s]; sb[threadIdx.x] += sb[threadIdx.x + s]; }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) { ta[blockIdx.x] = sa[0]; tb[blockIdx.x] = sb[0]; }
+}
+
+__global__ void __launch_bounds__(1024) scan_tile_sums(uint64_t *ta, uint64_t *tb, uint64_t nt)
+{
+    __shared__ uint64_t pa[1024], pb[1024];
+    const uint32_t t = threadIdx.x;
+    const uint64_t per = (nt + 1023) / 1024;
+    uint64_t lo = (uint64_t)t * per, hi = lo + per < nt ? lo + per : nt, sa = 0, sb = 0;
+    for (uint64_t i = lo; i < hi; i++) { sa += ta[i]; sb += tb[i]; }
+    pa[t] = sa; pb[t] = sb;
+    __syncthreads();
+    if (t == 0) {
+        uint64_t ra = 0, rb = 0;
+        for (int k = 0; k < 1024; k++) { uint64_t x = pa[k], y = pb[k]; pa[k] = ra; pb[k] = rb; ra += x; rb += y; }
+    }
+    __syncthreads();
+    uint64_t ra = pa[t], rb = pb[t];
+    for (uint64_t i = lo; i < hi; i++) { uint64_t x = ta[i], y = tb[i]; ta[i] = ra; tb[i] = rb; ra += x; rb += y; }
+}
+
+__global__ void __launch_bounds__(256) scan_tiles_apply(uint64_t *a, uint64_t *b, uint64_t n, const uint64_t *ta, const uint64_t *tb)
+{
+    // one warp-shuffle scan per 1024-element tile: 256 threads x 4 consecutive elements
+    __shared__ uint64_t wa[8], wb[8];
+    uint64_t base = (uint64_t)blockIdx.x * TILE + (uint64_t)threadIdx.x * 4;
+    uint64_t xa[4], xb[4], sa = 0, sb = 0;
+    for (int k = 0; k < 4; k++) { uint64_t i = base + k; xa[k] = i < n ? a[i] : 0; xb[k] = i < n ? b[i] : 0; sa += xa[k]; sb += xb[k]; }
+    uint64_t ia = sa, ib = sb;
+    const uint32_t lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    for (int d = 1; d < 32; d <<= 1) {
+        uint64_t ya = __shfl_up_sync(0xffffffffu, ia, d), yb = __shfl_up_sync(0xffffffffu, ib, d);
+        if (lane >= (uint32_t)d) { ia += ya; ib += yb; }
+    }
+    if (lane == 31) { wa[w] = ia; wb[w] = ib; }
+    __syncthreads();
+    uint64_t oa = ta[blockIdx.x], ob = tb[blockIdx.x];
+    for (uint32_t k = 0; k < w; k++) { oa += wa[k]; ob += wb[k]; }
+    uint64_t ra = oa + ia - sa, rb = ob + ib - sb;
+    for (int k = 0; k < 4; k++) { uint64_t i = base + k; if (i < n) { a[i] = ra; b[i] = rb; } ra += xa[k]; rb += xb[k]; }
+}
+
+// ---------------------------------------------------------------------------------------------
+// unpack: one warp per record
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint8_t nt16(uint32_t k)
+{
+    // "=ACMGRSVTWYHKDBN" (seq_nt16_str, hts.c:260) as two 64-bit immediates
+    const uint64_t a = ((uint64_t)'=') | ((uint64_t)'A' << 8) | ((uint64_t)'C' << 16) | ((uint64_t)'M' << 24) |
+                       ((uint64_t)'G' << 32) | ((uint64_t)'R' << 40) | ((uint64_t)'S' << 48) | ((uint64_t)'V' << 56);
+    const uint64_t b = ((uint64_t)'T') | ((uint64_t)'W' << 8) | ((uint64_t)'Y' << 16) | ((uint64_t)'H' << 24) |
+                       ((uint64_t)'K' << 32) | ((uint64_t)'D' << 40) | ((uint64_t)'B' << 48) | ((uint64_t)'N' << 56);
+    return (uint8_t)(((k & 8) ? b : a) >> (8 * (k & 7)));
+}
+
+__device__ __forceinline__ int reg2bin(int64_t beg, int64_t end)       // hts_reg2bin(beg,end,14,5), hts.h:1516
+{
+    --end;
+    if (beg >> 14 == end >> 14) return 4681 + (int)(beg >> 14);
+    if (beg >> 17 == end >> 17) return 585 + (int)(beg >> 17);
+    if (beg >> 20 == end >> 20) return 73 + (int)(beg >> 20);
+    if (beg >> 23 == end >> 23) return 9 + (int)(beg >> 23);
+    if (beg >> 26 == end >> 26) return 1 + (int)(beg >> 26);
+    return 0;
+}
+
+__global__ void __launch_bounds__(256)
+bam_unpack_kernel(const uint8_t *st, const uint64_t *rec_off, uint64_t n, hgpu_bam1_core *core, uint8_t *data,
+                  const uint64_t *data_off, uint8_t *seq, uint8_t *qual, const uint64_t *seq_off, int32_t *status)
+{
+    const uint32_t lane = threadIdx.x & 31;
+    uint64_t r = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (r >= n) return;
+    const uint8_t *rec = st + rec_off[r];
+    RecGeom g = geom(rec);
+    if (!g.ok) {
+        if (lane == 0) {
+            if (status) status[r] = -4;
+            if (core) { hgpu_bam1_core z = {}; core[r] = z; }
+        }
+        return;
+    }
+    const uint8_t *x = rec + 4, *body = rec + 36;
+    hgpu_bam1_core c;
+    c.tid = (int32_t)ld32(x);
+    c.pos = (int32_t)ld32(x + 4);
+    uint32_t x2 = ld32(x + 8), x3 = ld32(x + 12);
+    c.bin = (uint16_t)(x2 >> 16);
+    c.qual = (x2 >> 8) & 0xff;
+    c.flag = (uint16_t)(x3 >> 16);
+    c.n_cigar = x3 & 0xffff;
+    c.l_qseq = (int32_t)g.lq;
+    c.mtid = (int32_t)ld32(x + 20);
+    c.mpos = (int32_t)ld32(x + 24);
+    c.isize = (int32_t)ld32(x + 28);
+    uint32_t xn = g.xn, lqn = g.qn;
+    if (g.missing_nul) { xn = xn ? xn - 1 : 3; lqn++; }
+    c.l_extranul = (uint8_t)xn;
+    c.l_qname = (uint16_t)(lqn + xn);
+    const uint32_t rest = (uint32_t)(g.bl - 32) - g.qn;
+    if (data) {
+        uint8_t *o = data + data_off[r];
+        for (uint32_t i = lane; i < g.qn; i += 32) o[i] = body[i];
+        if (lane < (g.missing_nul ? 1u : 0u) + xn) o[g.qn + lane] = 0;
+        const uint8_t *from = body + g.qn;
+        uint8_t *to = o + lqn + xn;
+        for (uint32_t i = lane; i < rest; i += 32) to[i] = from[i];
+    }
+    const uint8_t *cig = body + g.qn, *sq = cig + 4 * (size_t)c.n_cigar, *ql = sq + ((g.lq + 1) >> 1);
+    int st_code = 0;
+    if (c.n_cigar > 0) {
+        int64_t rlen = 0, qlen = 0;
+        for (uint32_t k = lane; k < c.n_cigar; k += 32) {
+            uint32_t op = ld32(cig + 4 * (size_t)k);
+            uint32_t type = (0x3C1A7u >> ((op & 0xf) << 1)) & 3;
+            if (type & 1) qlen += op >> 4;
+            if (type & 2) rlen += op >> 4;
+        }
+        for (int d = 16; d > 0; d >>= 1) {
+            rlen += __shfl_xor_sync(0xffffffffu, rlen, d);
+            qlen += __shfl_xor_sync(0xffffffffu, qlen, d);
+        }
+        if (ld32(cig) == (4u | (g.lq << 4)) && c.tid >= 0 && c.pos >= 0) st_code = 1;   // bam_tag2cigar's trigger, sam.c:685-692
+        if ((c.flag & 4) || rlen == 0) rlen = 1;
+        c.bin = (uint16_t)reg2bin(c.pos, c.pos + rlen);
+        if (g.lq > 0 && !(c.flag & 4) && qlen != (int64_t)g.lq) st_code = -4;
+    }
+    if (lane == 0) {
+        if (core) core[r] = c;
+        if (status) status[r] = st_code;
+    }
+    if (seq) {
+        uint8_t *o = seq + seq_off[r];
+        for (uint32_t i = lane; i < g.lq; i += 32) o[i] = nt16((sq[i >> 1] >> ((~i & 1) << 2)) & 0xf);
+    }
+    if (qual) {
+        uint8_t *o = qual + seq_off[r];
+        const bool absent = g.lq && ql[0] == 0xff;
+        for (uint32_t i = lane; i < g.lq; i += 32) o[i] = absent ? ql[i] : (uint8_t)(ql[i] + 33);
+    }
+}
+
+} // namespace
+
+extern "C" int hgpu_bam_index_records_dev(hgpu_ctx *ctx, const uint8_t *d_stream, uint64_t len,
+                                          const uint64_t *d_hint_off, uint64_t n_hint, uint64_t *d_rec_off,
+                                          uint64_t rec_cap, uint64_t *d_n_rec, void *stream)
+{
+    if (!ctx || !d_stream || !d_n_rec) { hgpu_set_error("bad argument"); return HGPU_ERR_ARG; }
+    cudaStream_t st = stream ? (cudaStream_t)stream : ctx->stream;
+    uint64_t nseg = d_hint_off && n_hint ? n_hint : 1;
+    int rc = hgpu_ensure_bam(ctx, nseg * 4 * sizeof(uint64_t));
+    if (rc) return rc;
+    uint64_t *seg_start = (uint64_t *)ctx->d_bam, *seg_cnt = seg_start + nseg, *seg_exit = seg_cnt + nseg, *seg_base = seg_exit + nseg;
+    const uint64_t *hint = nseg > 1 || (d_hint_off && n_hint) ? d_hint_off : nullptr;
+    unsigned blocks = (unsigned)((nseg + 127) / 128);
+    bam_seg_scan_kernel<<<blocks, 128, 0, st>>>(d_stream, len, hint, nseg, seg_start, seg_cnt, seg_exit);
+    bam_seg_fix_kernel<<<1, 1024, 0, st>>>(d_stream, len, hint, nseg, seg_start, seg_cnt, seg_exit, seg_base, d_n_rec);
+    if (d_rec_off)
+        bam_seg_emit_kernel<<<blocks, 128, 0, st>>>(d_stream, len, hint, nseg, seg_start, seg_base, d_rec_off, rec_cap);
+    hgpu_count_launch(d_rec_off ? 3 : 2);
+    return hgpu_check(cudaGetLastError(), "bam index launch");
+}
+
+extern "C" int hgpu_bam_layout_dev(hgpu_ctx *ctx, const uint8_t *d_stream, uint64_t len, const uint64_t *d_rec_off,
+                                   uint64_t n, uint64_t *d_data_off, uint64_t *d_seq_off, void *stream)
+{
+    (void)len;
+    if (!ctx || !d_stream || !d_data_off || !d_seq_off) { hgpu_set_error("bad argument"); return HGPU_ERR_ARG; }
+    cudaStream_t st = stream ? (cudaStream_t)stream : ctx->stream;
+    uint64_t m = n + 1, nt = (m + TILE - 1) / TILE;
+    int rc = hgpu_ensure_bam(ctx, nt * 2 * sizeof(uint64_t) + 64);
+    if (rc) return rc;
+    uint64_t *ta = (uint64_t *)ctx->d_bam, *tb = ta + nt;
+    bam_sizes_kernel<<<(unsigned)((m + 255) / 256), 256, 0, st>>>(d_stream, d_rec_off, n, d_data_off, d_seq_off);
+    scan_tiles_reduce<<<(unsigned)nt, 256, 0, st>>>(d_data_off, d_seq_off, m, ta, tb);
+    scan_tile_sums<<<1, 1024, 0, st>>>(ta, tb, nt);
+    scan_tiles_apply<<<(unsigned)nt, 256, 0, st>>>(d_data_off, d_seq_off, m, ta, tb);
+    hgpu_count_launch(4);
+    return hgpu_check(cudaGetLastError(), "bam layout launch");
+}
+
+extern "C" int hgpu_bam_unpack_dev(hgpu_ctx *ctx, const uint8_t *d_stream, uint64_t len, const uint64_t *d_rec_off,
+                                   uint64_t n, hgpu_bam1_core *d_core, uint8_t *d_data, const uint64_t *d_data_off,
+                                   uint8_t *d_seq, uint8_t *d_qual, const uint64_t *d_seq_off, int32_t *d_status,
+                                   void *stream)
+{
+    (void)len;
+    if (!ctx || !d_stream || !d_rec_off) { hgpu_set_error("bad argument"); return HGPU_ERR_ARG; }
+    if ((d_data && !d_data_off) || ((d_seq || d_qual) && !d_seq_off)) { hgpu_set_error("offsets missing"); return HGPU_ERR_ARG; }
+    if (n == 0) return HGPU_OK;
+    cudaStream_t st = stream ? (cudaStream_t)stream : ctx->stream;
+    uint64_t blocks = (n * 32 + 255) / 256;
+    bam_unpack_kernel<<<(unsigned)blocks, 256, 0, st>>>(d_stream, d_rec_off, n, d_core, d_data, d_data_off, d_seq, d_qual,
+                                                       d_seq_off, d_status);
+    hgpu_count_launch();
+    return hgpu_check(cudaGetLastError(), "bam unpack launch");
+}

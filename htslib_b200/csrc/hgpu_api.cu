@@ -49,6 +49,7 @@ static int grow(uint8_t **p, size_t *cap, size_t want, bool pinned)
 int hgpu_ensure_scratch(hgpu_ctx *c, size_t b) { return grow(&c->d_scratch, &c->d_scratch_cap, b, false); }
 int hgpu_ensure_stage(hgpu_ctx *c, size_t b)   { return grow(&c->d_stage, &c->d_stage_cap, b, false); }
 int hgpu_ensure_mrec(hgpu_ctx *c, size_t b)    { return grow(&c->d_mrec, &c->d_mrec_cap, b, false); }
+int hgpu_ensure_bam(hgpu_ctx *c, size_t b)     { return grow(&c->d_bam, &c->d_bam_cap, b, false); }
 int hgpu_ensure_pinned(hgpu_ctx *c, size_t b)  { return grow(&c->h_pinned, &c->h_pinned_cap, b, true); }
 uint32_t *hgpu_take_counter(hgpu_ctx *c, cudaStream_t st)
 {
@@ -93,6 +94,7 @@ extern "C" void hgpu_destroy(hgpu_ctx *c)
     if (c->d_scratch) cudaFree(c->d_scratch);
     if (c->d_stage) cudaFree(c->d_stage);
     if (c->d_mrec) cudaFree(c->d_mrec);
+    if (c->d_bam) cudaFree(c->d_bam);
     if (c->h_pinned) cudaFreeHost(c->h_pinned);
     if (c->d_counter) cudaFree(c->d_counter);
     cudaStreamDestroy(c->stream);

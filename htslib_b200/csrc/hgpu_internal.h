@@ -16,6 +16,7 @@ struct hgpu_ctx {
     // device scratch, grown on demand
     uint8_t *d_scratch;  size_t d_scratch_cap;     // rANS per-warp scratch
     uint8_t *d_mrec;     size_t d_mrec_cap;        // inflate match-record scratch
+    uint8_t *d_bam;      size_t d_bam_cap;         // BAM index / scan scratch
     uint8_t *d_stage;    size_t d_stage_cap;     // device staging for _host entry points
     uint8_t *h_pinned;   size_t h_pinned_cap;    // pinned host staging
     uint32_t *d_counter;                          // 64 work-queue counters, handed out round-robin
@@ -29,6 +30,7 @@ void hgpu_count_launch(int n = 1);
 int  hgpu_ensure_scratch(hgpu_ctx *ctx, size_t bytes);
 int  hgpu_ensure_stage(hgpu_ctx *ctx, size_t bytes);
 int  hgpu_ensure_mrec(hgpu_ctx *ctx, size_t bytes);
+int  hgpu_ensure_bam(hgpu_ctx *ctx, size_t bytes);
 int  hgpu_ensure_pinned(hgpu_ctx *ctx, size_t bytes);
 // a zeroed (stream-ordered) work counter; slots rotate so launches in flight on different streams never share one
 uint32_t *hgpu_take_counter(hgpu_ctx *ctx, cudaStream_t st);

@@ -122,9 +122,14 @@ typedef struct hgpu_bam1_core {
 } hgpu_bam1_core;
 
 /* Step 1: find record starts.  d_stream[0..len) holds whole records back to back (the BAM
- * header already skipped).  Writes d_rec_off[0..n) (byte offset of each record's block_size
- * field) and *d_n_rec.  Returns HGPU_OK; *d_n_rec = (uint64)-1 flags a malformed chain. */
+ * header already skipped).  d_hint_off[0..n_hint): ascending candidate record starts — normally
+ * the offsets at which the inflated BGZF blocks begin (htslib's writer avoids splitting a record
+ * across blocks, bgzf_flush_try sam.c:888); d_hint_off[0] must be a true record start (0).  Wrong
+ * hints only cost time.  NULL / 0 walks the chain serially.  Writes d_rec_off[0..n) (byte offset
+ * of each record's block_size field; may be NULL to only count) and *d_n_rec (device memory);
+ * *d_n_rec = (uint64)-1 flags a malformed chain (bam_read1 would return -4/-3/-2 there). */
 int hgpu_bam_index_records_dev(hgpu_ctx *ctx, const uint8_t *d_stream, uint64_t len,
+                               const uint64_t *d_hint_off, uint64_t n_hint,
                                uint64_t *d_rec_off, uint64_t rec_cap, uint64_t *d_n_rec, void *stream);
 
 /* Step 2: unpack n records.  Outputs (all device memory, any may be NULL to skip):
@@ -135,7 +140,9 @@ int hgpu_bam_index_records_dev(hgpu_ctx *ctx, const uint8_t *d_stream, uint64_t 
  *  seq  + seq_off[i]  l_qseq ASCII bases (seq_nt16_str, hts.c:260); seq_off has n+1 entries
  *  qual (same offsets) l_qseq bytes of QUAL+33, or '*' semantics left to the caller when
  *                     qual[0]==0xff: raw bytes are copied unchanged in that case
- *  status[i]          0, or -4 for the reference's "invalid record" conditions (sam.c:824-828)
+ *  status[i]          0; -4 for the reference's "invalid record" conditions (sam.c:799, :824-828,
+ *                     :852-856); 1 when the record meets bam_tag2cigar's trigger (first CIGAR op ==
+ *                     <l_qseq>S, sam.c:685-692): unpacked verbatim, the host must apply the CG rewrite
  */
 int hgpu_bam_unpack_dev(hgpu_ctx *ctx, const uint8_t *d_stream, uint64_t len,
                         const uint64_t *d_rec_off, uint64_t n,

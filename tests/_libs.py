@@ -178,3 +178,100 @@ def ref_bgzf_read_all(data, threads=0):
         out += bytes(chunk[:n])
     r.bgzf_close(fp)
     return bytes(out), err
+
+
+# ---------------------------------------------------------------- BAM helpers
+class BamCore(C.Structure):
+    _fields_ = [("pos", C.c_int64), ("tid", C.c_int32), ("bin", C.c_uint16), ("qual", C.c_uint8),
+                ("l_extranul", C.c_uint8), ("flag", C.c_uint16), ("l_qname", C.c_uint16),
+                ("n_cigar", C.c_uint32), ("l_qseq", C.c_int32), ("mtid", C.c_int32),
+                ("mpos", C.c_int64), ("isize", C.c_int64)]
+
+    def astuple(self):
+        return tuple(getattr(self, f) for f, _ in self._fields_)
+
+
+class Bam1(C.Structure):          # bam1_t, htslib/sam.h:253-260
+    _fields_ = [("core", BamCore), ("id", C.c_uint64), ("data", C.POINTER(C.c_uint8)), ("l_data", C.c_int),
+                ("m_data", C.c_uint32), ("mempolicy", C.c_uint32)]
+
+
+def bam_header_len(stream):
+    """Length of the BAM header at the start of an inflated BAM stream (SAM spec 4.2)."""
+    assert stream[:4] == b"BAM\1"
+    l_text = struct.unpack_from("<i", stream, 4)[0]
+    p = 8 + l_text
+    n_ref = struct.unpack_from("<i", stream, p)[0]
+    p += 4
+    for _ in range(n_ref):
+        l_name = struct.unpack_from("<i", stream, p)[0]
+        p += 4 + l_name + 4
+    return p
+
+
+def bam_header(n_ref=1, name=b"chr1", length=250000000):
+    text = b"@HD\tVN:1.6\tSO:coordinate\n@SQ\tSN:%s\tLN:%d\n@RG\tID:grp1\n" % (name, length)
+    return b"BAM\1" + struct.pack("<i", len(text)) + text + struct.pack("<i", n_ref) + \
+        struct.pack("<i", len(name) + 1) + name + b"\0" + struct.pack("<i", length)
+
+
+def ref_bam_read_all(img):
+    """Every record of a BGZF BAM image through the compiled reference's bam_hdr_read + bam_read1.
+    Returns list of (core tuple, data bytes, return code)."""
+    r = ref()
+    r.hopen.restype = C.c_void_p
+    r.hopen.argtypes = [C.c_char_p, C.c_char_p, C.c_void_p, C.c_size_t]
+    r.bgzf_hopen.restype = C.c_void_p
+    r.bgzf_hopen.argtypes = [C.c_void_p, C.c_char_p]
+    r.bgzf_close.argtypes = [C.c_void_p]
+    r.bam_hdr_read.restype = C.c_void_p
+    r.bam_hdr_read.argtypes = [C.c_void_p]
+    r.sam_hdr_destroy.argtypes = [C.c_void_p]
+    r.bam_init1.restype = C.POINTER(Bam1)
+    r.bam_read1.argtypes = [C.c_void_p, C.POINTER(Bam1)]
+    r.bam_destroy1.argtypes = [C.POINTER(Bam1)]
+    libc = C.CDLL(None)
+    libc.malloc.restype = C.c_void_p
+    libc.malloc.argtypes = [C.c_size_t]
+    mem = libc.malloc(max(1, len(img)))
+    C.memmove(mem, bytes(img), len(img))
+    fp = r.bgzf_hopen(r.hopen(b"mem:", b"r:", mem, len(img)), b"r")
+    hdr = r.bam_hdr_read(fp)
+    assert hdr
+    b = r.bam_init1()
+    out = []
+    while True:
+        rc = r.bam_read1(fp, b)
+        if rc < 0:
+            if rc != -1:
+                out.append((None, None, rc))
+            break
+        out.append((b.contents.core.astuple(), bytes(b.contents.data[: b.contents.l_data]), rc))
+    r.bam_destroy1(b)
+    r.sam_hdr_destroy(hdr)
+    r.bgzf_close(fp)
+    return out
+
+
+def orc_bam_unpack_all(stream):
+    """Records of an inflated BAM record stream (header already removed) through the oracle.
+    Returns list of (status, core tuple, data, seq, qual) or raises on a broken chain."""
+    o = orc()
+    o.orc_bam_index.restype = C.c_long
+    sb = buf(stream)
+    cap = len(stream) // 36 + 1
+    offs = (C.c_uint64 * cap)()
+    n = o.orc_bam_index(sb, C.c_uint64(len(stream)), offs, C.c_long(cap))
+    if n < 0:
+        raise ValueError("broken chain at record %d" % (-1 - n))
+    res = []
+    base = C.addressof(sb)
+    for i in range(n):
+        ld, lq = C.c_uint32(0), C.c_uint32(0)
+        p = C.cast(base + offs[i], C.POINTER(C.c_uint8))
+        o.orc_bam_sizes(p, C.byref(ld), C.byref(lq))
+        core = BamCore()
+        data = (C.c_uint8 * max(1, ld.value))(); seq = (C.c_uint8 * max(1, lq.value))(); qual = (C.c_uint8 * max(1, lq.value))()
+        st = o.orc_bam_unpack1(p, C.byref(core), data, seq, qual)
+        res.append((st, core.astuple(), bytes(data[: ld.value]), bytes(seq[: lq.value]), bytes(qual[: lq.value])))
+    return res, [offs[i] for i in range(n)]
