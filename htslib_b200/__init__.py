@@ -43,6 +43,8 @@ def lib():
     L.hgpu_bgzf_scan.restype = C.c_long
     L.hgpu_bgzf_scan.argtypes = [vp, u64, vp, vp, vp, C.c_long]
     L.hgpu_bgzf_inflate_file_host.argtypes = [vp, vp, u64, vp, u64, C.POINTER(u64), C.POINTER(C.c_long)]
+    L.hgpu_bgzf_inflate_blocks_host.argtypes = [vp, vp, vp, vp, u32, vp, vp, vp, vp, vp]
+    L.hgpu_shard_range.argtypes = [u64, vp, C.c_int, C.c_int, C.POINTER(u64), C.POINTER(u64), C.POINTER(u64)]
     L.hgpu_crc32.restype = u32
     L.hgpu_crc32.argtypes = [vp, u32, vp, C.c_size_t]
     L.hgpu_rans_nx16_decode_batch_dev.argtypes = [vp, vp, vp, vp, u32, vp, vp, vp, vp, vp, u32, vp]
@@ -155,6 +157,15 @@ class Context:
         import numpy as np
         a = np.frombuffer(data, dtype=np.uint8)
         return lib().hgpu_crc32(self.h, crc, a.ctypes.data if a.size else None, a.size)
+
+
+def shard_range(unit_out_len, world, rank):
+    """(first, count, out_base) of this rank's contiguous unit range (hgpu_shard_range)."""
+    import numpy as np
+    a = np.ascontiguousarray(unit_out_len, dtype=np.uint32)
+    f, c, b = C.c_uint64(0), C.c_uint64(0), C.c_uint64(0)
+    check(lib().hgpu_shard_range(a.size, a.ctypes.data, world, rank, C.byref(f), C.byref(c), C.byref(b)), "shard_range")
+    return f.value, c.value, b.value
 
 
 def bgzf_scan(file_np):

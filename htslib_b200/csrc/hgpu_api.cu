@@ -227,6 +227,64 @@ extern "C" int hgpu_bgzf_inflate_file_host(hgpu_ctx *ctx, const uint8_t *file, u
     return HGPU_OK;
 }
 
+// Multi-GPU sharding rule: unit i goes to rank floor(i*world/n), i.e. rank r owns
+// the contiguous range [ceil(r*n/world), ceil((r+1)*n/world)), so every rank's output is one
+// contiguous byte range of the decompressed stream and no data-path collective is needed.
+extern "C" int hgpu_shard_range(uint64_t n_units, const uint32_t *unit_out_len, int world, int rank,
+                                uint64_t *first, uint64_t *count, uint64_t *out_base)
+{
+    if (world < 1 || rank < 0 || rank >= world || !first || !count) { hgpu_set_error("bad shard arguments"); return HGPU_ERR_ARG; }
+    uint64_t lo = ((uint64_t)rank * n_units + world - 1) / world, hi = ((uint64_t)(rank + 1) * n_units + world - 1) / world;
+    if (hi > n_units) hi = n_units;
+    if (lo > hi) lo = hi;
+    *first = lo; *count = hi - lo;
+    if (out_base) {
+        uint64_t b = 0;
+        if (unit_out_len) for (uint64_t i = 0; i < lo; i++) b += unit_out_len[i];
+        *out_base = b;
+    }
+    return HGPU_OK;
+}
+
+// A batch of individual blocks with HOST buffers (the thread-pool job seam):
+// H2D of the gathered compressed blocks, one launch, D2H of the slots and the per-block results.
+extern "C" int hgpu_bgzf_inflate_blocks_host(hgpu_ctx *ctx, const uint8_t *in, const uint64_t *in_off,
+        const uint32_t *in_len, uint32_t n, uint8_t *out, const uint64_t *out_off, const uint32_t *out_cap,
+        uint32_t *out_len, int32_t *status)
+{
+    if (!ctx || (n && (!in || !in_off || !in_len || !out || !out_off || !out_cap))) { hgpu_set_error("bad argument"); return HGPU_ERR_ARG; }
+    if (n == 0) return HGPU_OK;
+    if (hgpu_check(cudaSetDevice(ctx->device), "cudaSetDevice")) return HGPU_ERR_CUDA;
+    uint64_t in_end = 0, out_end = 0;
+    for (uint32_t i = 0; i < n; i++) {
+        if (in_off[i] + in_len[i] > in_end) in_end = in_off[i] + in_len[i];
+        if (out_off[i] + out_cap[i] > out_end) out_end = out_off[i] + out_cap[i];
+    }
+    size_t in_bytes = ((size_t)in_end + 4 + 255) & ~(size_t)255, out_bytes = ((size_t)out_end + 255) & ~(size_t)255;
+    int rc = hgpu_ensure_stage(ctx, in_bytes + out_bytes + (size_t)n * 32 + 1024);
+    if (rc) return rc;
+    uint8_t *d_in = ctx->d_stage, *d_out = d_in + in_bytes;
+    uint64_t *d_ioff = (uint64_t *)(d_out + out_bytes), *d_ooff = d_ioff + n;
+    uint32_t *d_ilen = (uint32_t *)(d_ooff + n), *d_cap = d_ilen + n, *d_got = d_cap + n;
+    int32_t *d_st = (int32_t *)(d_got + n);
+    cudaStream_t s = ctx->stream;
+    if (hgpu_check(cudaMemcpyAsync(d_in, in, in_end, cudaMemcpyHostToDevice, s), "H2D")) return HGPU_ERR_CUDA;
+    if (hgpu_check(cudaMemcpyAsync(d_ioff, in_off, n * 8, cudaMemcpyHostToDevice, s), "H2D")) return HGPU_ERR_CUDA;
+    if (hgpu_check(cudaMemcpyAsync(d_ooff, out_off, n * 8, cudaMemcpyHostToDevice, s), "H2D")) return HGPU_ERR_CUDA;
+    if (hgpu_check(cudaMemcpyAsync(d_ilen, in_len, n * 4, cudaMemcpyHostToDevice, s), "H2D")) return HGPU_ERR_CUDA;
+    if (hgpu_check(cudaMemcpyAsync(d_cap, out_cap, n * 4, cudaMemcpyHostToDevice, s), "H2D")) return HGPU_ERR_CUDA;
+    rc = hgpu_launch_bgzf_inflate(ctx, d_in, d_ioff, d_ilen, n, d_out, d_ooff, d_cap, d_got, d_st, s);
+    if (rc) return rc;
+    if (hgpu_check(cudaMemcpyAsync(out, d_out, out_end, cudaMemcpyDeviceToHost, s), "D2H")) return HGPU_ERR_CUDA;
+    std::vector<uint32_t> got(n);
+    std::vector<int32_t> st(n);
+    if (hgpu_check(cudaMemcpyAsync(got.data(), d_got, n * 4, cudaMemcpyDeviceToHost, s), "D2H")) return HGPU_ERR_CUDA;
+    if (hgpu_check(cudaMemcpyAsync(st.data(), d_st, n * 4, cudaMemcpyDeviceToHost, s), "D2H")) return HGPU_ERR_CUDA;
+    if (hgpu_check(cudaStreamSynchronize(s), "sync")) return HGPU_ERR_CUDA;
+    for (uint32_t i = 0; i < n; i++) { if (out_len) out_len[i] = got[i]; if (status) status[i] = st[i]; }
+    return HGPU_OK;
+}
+
 // zlib-compatible combine on the host side of the ABI: crc(A||B) from crc(A), crc(B), |B|
 static uint32_t h_multmodp(uint32_t a, uint32_t b)
 {

@@ -63,6 +63,20 @@ int hgpu_bgzf_inflate_batch_dev(hgpu_ctx *ctx,
         uint8_t *d_out, const uint64_t *d_out_off, const uint32_t *d_out_cap,
         uint32_t *d_out_len, int32_t *d_status, void *stream);
 
+/* The same with HOST buffers: H2D, one launch, D2H.  This is the body a GPU-backed
+ * bgzf_mt_reader gives a batch of bgzf_job (bgzf.c:92-101, :1598-1738; INTEGRATION.md seam B3). */
+int hgpu_bgzf_inflate_blocks_host(hgpu_ctx *ctx,
+        const uint8_t *in, const uint64_t *in_off, const uint32_t *in_len, uint32_t n,
+        uint8_t *out, const uint64_t *out_off, const uint32_t *out_cap,
+        uint32_t *out_len, int32_t *status);
+
+/* Multi-GPU sharding rule: rank r of `world` owns the contiguous unit range
+ * [first, first+count) and, if unit_out_len is given, writes at byte out_base of the global
+ * decompressed stream.  Blocks / slices are independent (bgzf.c:775, cram_decode.c:2140), so there
+ * is no collective on the data path. */
+int hgpu_shard_range(uint64_t n_units, const uint32_t *unit_out_len, int world, int rank,
+                     uint64_t *first, uint64_t *count, uint64_t *out_base);
+
 /* Host-side walk of the BSIZE chain (bgzf_read_block header logic, bgzf.c:1144-1205;
  * bgzf_mt_read_block :1485-1539).  Fills off/len/isize for up to cap blocks; isize is the
  * footer's ISIZE field.  Returns the block count, or -1-k when block k has a bad header or is
