@@ -49,6 +49,9 @@ def lib():
     L.hgpu_crc32.argtypes = [vp, u32, vp, C.c_size_t]
     L.hgpu_rans_nx16_decode_batch_dev.argtypes = [vp, vp, vp, vp, u32, vp, vp, vp, vp, vp, u32, vp]
     L.hgpu_rans_nx16_decode_batch_host.argtypes = [vp, vp, vp, vp, u32, vp, vp, vp, vp, vp]
+    L.hgpu_rans_nx16_compress_bound.restype = u32
+    L.hgpu_rans_nx16_compress_bound.argtypes = [u32, C.c_int]
+    L.hgpu_rans_nx16_encode_batch_dev.argtypes = [vp, vp, vp, vp, vp, u32, vp, vp, vp, vp, vp, vp]
     L.hgpu_bam_index_records_dev.argtypes = [vp, vp, u64, vp, u64, vp, u64, vp, vp]
     L.hgpu_bam_layout_dev.argtypes = [vp, vp, u64, vp, u64, vp, vp, vp]
     L.hgpu_bam_unpack_dev.argtypes = [vp, vp, u64, vp, u64, vp, vp, vp, vp, vp, vp, vp, vp]
@@ -103,6 +106,32 @@ class Context:
                                                     d_out.data_ptr(), d_out_off.data_ptr(), d_out_len.data_ptr(),
                                                     d_got.data_ptr(), d_status.data_ptr(), int(max_out_len), stream),
               "rans_nx16_decode_batch_dev")
+
+    def rans_nx16_encode(self, raws, orders, stream=0):
+        """Encode a list of byte strings on the device (hgpu_rans_nx16_encode_batch_dev).  Returns
+        list of compressed byte strings (None where the kernel reported failure)."""
+        import numpy as np
+        import torch
+        L = lib()
+        n = len(raws)
+        dev = torch.device("cuda", torch.cuda.current_device())
+        in_len = np.array([len(r) for r in raws], dtype=np.uint32)
+        in_off = np.concatenate([[0], np.cumsum(in_len.astype(np.int64))[:-1]]).astype(np.int64)
+        cap = np.array([L.hgpu_rans_nx16_compress_bound(int(l), int(o)) for l, o in zip(in_len, orders)], dtype=np.uint32)
+        out_off = np.concatenate([[0], np.cumsum((cap.astype(np.int64) + 15) // 16 * 16)[:-1]]).astype(np.int64)
+        blob = np.frombuffer(b"".join(raws) + b"\0" * 8, dtype=np.uint8).copy()
+        d_in = torch.from_numpy(blob).to(dev)
+        d_out = torch.zeros(int(out_off[-1]) + int(cap[-1]) + 64, dtype=torch.uint8, device=dev)
+        t = lambda a: torch.from_numpy(a).to(dev)
+        d_io, d_il, d_or = t(in_off), t(in_len.view(np.int32)), t(np.array(orders, dtype=np.int32))
+        d_oo, d_oc = t(out_off), t(cap.view(np.int32))
+        d_ol = torch.zeros(n, dtype=torch.int32, device=dev); d_st = torch.zeros(n, dtype=torch.int32, device=dev)
+        check(L.hgpu_rans_nx16_encode_batch_dev(self.h, d_in.data_ptr(), d_io.data_ptr(), d_il.data_ptr(), d_or.data_ptr(), n,
+                                                d_out.data_ptr(), d_oo.data_ptr(), d_oc.data_ptr(), d_ol.data_ptr(),
+                                                d_st.data_ptr(), stream), "rans_nx16_encode_batch_dev")
+        torch.cuda.synchronize()
+        out = d_out.cpu().numpy(); ol = d_ol.cpu().numpy(); st = d_st.cpu().numpy()
+        return [out[int(o):int(o) + int(l)].tobytes() if s == 0 else None for o, l, s in zip(out_off, ol, st)]
 
     def bam_unpack_dev(self, d_stream, length, d_hint=None, want_text=True, stream=0):
         """index -> layout -> unpack of an inflated BAM record stream resident on the device.

@@ -30,7 +30,8 @@ constexpr int SM_F      = 0;                        // u32 F[256]          1024 
 constexpr int SM_CUM    = 1024;                     // u32 cum[257]        1028 B -> 1040
 constexpr int SM_ROWOF  = 2064;                     // u8 rowof[256]  byte -> compact row / 0xff
 constexpr int SM_SYMOF  = 2320;                     // u8 symof[256]  compact index -> byte
-constexpr int SM_TAB    = 2576;                     // table area (8-byte aligned)
+constexpr int SM_RING   = 2576;                     // 512 B ring mirroring the compressed word stream
+constexpr int SM_TAB    = 3088;                     // table area (8-byte aligned)
 constexpr uint32_t GTAB_BYTES = 256u * 4096u + 256u * 256u * 8u;   // worst-case order-1 table
 constexpr uint32_t TBLBUF_BYTES = 256u * 1024u;     // decoded (was-compressed) order-1 table text
 
@@ -42,6 +43,8 @@ struct WarpScratch {
     uint8_t *gtab;     // GTAB_BYTES    : table overflow
     uint32_t max_out;
     uint32_t smem_tab_bytes;
+    int pass;                // 0: small-table fast pass (defers what it cannot hold), 1: everything else
+    mutable bool defer;      // set when pass 0 hands the stream to pass 1
 };
 
 // ---------------------------------------------------------------------------------------------
@@ -158,31 +161,87 @@ __device__ void fill_null_row(const Table &t, uint32_t row)
 
 // ---------------------------------------------------------------------------------------------
 // The symbol loops.
+//
+// Renormalisation words come from a 512-byte ring in shared memory that mirrors the compressed
+// stream (refilled 128 bytes at a time with coalesced 32-bit loads, realigned with a funnel
+// shift), so the per-step word fetch is one LDS.U16 instead of a global round trip.
+// Order-1 output: every lane owns a contiguous segment; bytes are shifted into a 32-bit
+// accumulator and stored as aligned words at the step where the lane's address crosses a 4-byte
+// boundary (a per-lane phase, constant across the 4-step unrolled loop), so a step costs one
+// predicated STG.32 per warp and 8 instead of 32 L2 transactions.
 // ---------------------------------------------------------------------------------------------
-__device__ __forceinline__ void renorm(uint32_t &R, bool active, const uint8_t *in, uint32_t &ipos,
-                                       uint32_t in_len)
+struct WordRing {
+    const uint8_t *in;       // stream start (global)
+    uintptr_t lim;           // first aligned word address entirely past the input
+    uint32_t ipos0;          // stream offset mirrored at ring offset 0
+    uint32_t avail;          // stream bytes [ipos0, avail) have been loaded (multiple of 128 past ipos0)
+};
+
+__device__ __forceinline__ void ring_load_chunk(uint8_t *ring, WordRing &wr)
+{
+    const uint32_t lane = hgpu_lane();
+    const uint32_t c = (wr.avail - wr.ipos0) >> 7;                 // chunk index
+    uintptr_t g = reinterpret_cast<uintptr_t>(wr.in) + wr.avail + 4u * lane;
+    uintptr_t ga = g & ~(uintptr_t)3;
+    uint32_t sh = (uint32_t)(g & 3) * 8;
+    uint32_t w0 = ga < wr.lim ? *reinterpret_cast<const uint32_t *>(ga) : 0u;
+    uint32_t w1 = ga + 4 < wr.lim ? *reinterpret_cast<const uint32_t *>(ga + 4) : 0u;
+    reinterpret_cast<uint32_t *>(ring)[(c & 3) * 32 + lane] = __funnelshift_r(w0, w1, sh);
+    wr.avail += 128;
+}
+
+// make sure the next `margin` bytes past ipos are in the ring (warp-uniform)
+__device__ __forceinline__ void ring_ensure(uint8_t *ring, WordRing &wr, uint32_t ipos, uint32_t margin)
+{
+    if (ipos + margin > wr.avail) {
+        __syncwarp();
+        while (ipos + margin > wr.avail) ring_load_chunk(ring, wr);
+        __syncwarp();
+    }
+}
+
+__device__ __forceinline__ void ring_init(uint8_t *ring, WordRing &wr, const uint8_t *in, uint32_t in_len, uint32_t ipos)
+{
+    wr.in = in;
+    wr.lim = (reinterpret_cast<uintptr_t>(in) + in_len + 3) & ~(uintptr_t)3;
+    wr.ipos0 = ipos;
+    wr.avail = ipos;
+    ring_ensure(ring, wr, ipos, 256);
+}
+
+__device__ __forceinline__ void renorm(uint32_t &R, bool active, const uint8_t *ring, const WordRing &wr,
+                                       uint32_t &ipos, uint32_t in_len)
 {
     bool need = active && R < RANS_L;
     uint32_t bal = __ballot_sync(0xffffffffu, need);
     if (bal) {
         uint32_t wpos = ipos + 2u * __popc(bal & hgpu_lanemask_lt());
-        bool ok = need && wpos + 2u <= in_len;           // RansDecRenormSafe, rANS_word.h:441
-        if (ok) R = (R << 16) | in[wpos] | ((uint32_t)in[wpos + 1] << 8);
-        uint32_t took = __ballot_sync(0xffffffffu, ok);
-        ipos += 2u * __popc(took);
+        uint32_t w = *reinterpret_cast<const uint16_t *>(ring + ((wpos - wr.ipos0) & 511u));
+        if (ipos + 64u <= in_len) {                      // every candidate word is inside the input
+            if (need) R = (R << 16) | w;
+            ipos += 2u * __popc(bal);
+        } else {                                         // RansDecRenormSafe, rANS_word.h:441
+            bool ok = need && wpos + 2u <= in_len;
+            if (ok) R = (R << 16) | w;
+            ipos += 2u * __popc(__ballot_sync(0xffffffffu, ok));
+        }
     }
 }
 
 template <bool SMEM>
-__device__ void loop_order0(const Table &t, const uint8_t *in, uint32_t in_len, uint32_t ipos,
+__device__ void loop_order0(uint8_t *smem, const Table &t, const uint8_t *in, uint32_t in_len, uint32_t ipos,
                             uint8_t *out, uint32_t U, uint32_t N, uint32_t R)
 {
     const uint32_t lane = hgpu_lane();
     const uint32_t mask = (1u << t.shift) - 1, shift = t.shift;
-    const uint8_t *lut = t.lut;
-    const uint2 *fb = t.fb;
+    const uint8_t *lut = SMEM ? smem + SM_TAB : t.lut;
+    const uint2 *fb = SMEM ? reinterpret_cast<const uint2 *>(smem + SM_TAB + (((1u << t.shift) + 7u) & ~7u)) : t.fb;
+    uint8_t *ring = smem + SM_RING;
+    WordRing wr;
+    ring_init(ring, wr, in, in_len, ipos);
     const bool mine = lane < N;
     for (uint32_t i = lane; __any_sync(0xffffffffu, mine && i < U); i += N) {
+        ring_ensure(ring, wr, ipos, 64);
         bool act = mine && i < U;
         uint32_t m = R & mask;
         uint32_t k = lut[m];
@@ -191,46 +250,81 @@ __device__ void loop_order0(const Table &t, const uint8_t *in, uint32_t in_len, 
             R = (e.x & 0xffffu) * (R >> shift) + m - (e.x >> 16);
             out[i] = (uint8_t)e.y;
         }
-        renorm(R, act, in, ipos, in_len);
+        renorm(R, act, ring, wr, ipos, in_len);
     }
 }
 
 template <bool SMEM>
-__device__ void loop_order1(const Table &t, const uint8_t *in, uint32_t in_len, uint32_t ipos,
+__device__ void loop_order1(uint8_t *smem, const Table &t, const uint8_t *in, uint32_t in_len, uint32_t ipos,
                             uint8_t *out, uint32_t U, uint32_t N, uint32_t R, uint32_t row0)
 {
     const uint32_t lane = hgpu_lane();
     const uint32_t mask = (1u << t.shift) - 1, shift = t.shift, ncol = t.ncol;
-    const uint8_t *lut = t.lut;
-    const uint2 *fb = t.fb;
+    const uint8_t *lut = SMEM ? smem + SM_TAB : t.lut;
+    const uint2 *fb = SMEM ? reinterpret_cast<const uint2 *>(smem + SM_TAB + (((t.ncol << t.shift) + 7u) & ~7u)) : t.fb;
+    uint8_t *ring = smem + SM_RING;
+    WordRing wr;
+    ring_init(ring, wr, in, in_len, ipos);
     const bool mine = lane < N;
     const uint32_t seg = U / N;
     uint8_t *op = out + (size_t)(mine ? lane : 0) * seg;
-    uint32_t row = row0;
-    for (uint32_t s = 0; s < seg; s++) {
-        uint32_t m = R & mask;
-        uint32_t k = lut[(row << shift) + m];
-        uint2 e = fb[row * ncol + k];
-        if (mine) {
-            R = (e.x & 0xffffu) * (R >> shift) + m - (e.x >> 16);
-            op[s] = (uint8_t)e.y;
-            row = k;
+    uint32_t row = row0, acc = 0;
+
+#define RANS_O1_STEP(ACTIVE)                                                                       \
+    {                                                                                              \
+        uint32_t m = R & mask;                                                                     \
+        uint32_t k = lut[(row << shift) + m];                                                      \
+        uint2 e = fb[row * ncol + k];                                                              \
+        if (ACTIVE) {                                                                              \
+            R = (e.x & 0xffffu) * (R >> shift) + m - (e.x >> 16);                                  \
+            acc = (acc >> 8) | (e.y << 24);                                                        \
+            row = k;                                                                               \
+        }                                                                                          \
+        renorm(R, ACTIVE, ring, wr, ipos, in_len);                                                 \
+    }
+
+    uint32_t s = 0;
+    // head: the first word of a segment may be shared with the previous segment -> byte stores
+    for (; s < 4 && s < seg; s++) {
+        ring_ensure(ring, wr, ipos, 64);
+        RANS_O1_STEP(mine)
+        if (mine) op[s] = (uint8_t)(acc >> 24);
+    }
+    if (s == 4) {
+        // phase: at unrolled position j the lane's address ends a 4-byte word iff (op+s+j)&3 == 3
+        const uint32_t ph = (uint32_t)(reinterpret_cast<uintptr_t>(op) + 4u) & 3u;
+        const bool p0 = mine && ph == 3u, p1 = mine && ph == 2u, p2 = mine && ph == 1u, p3 = mine && ph == 0u;
+        for (; s + 4 <= seg; s += 4) {
+            ring_ensure(ring, wr, ipos, 256);
+            RANS_O1_STEP(mine)
+            if (p0) *reinterpret_cast<uint32_t *>(op + s - 3) = acc;
+            RANS_O1_STEP(mine)
+            if (p1) *reinterpret_cast<uint32_t *>(op + s - 2) = acc;
+            RANS_O1_STEP(mine)
+            if (p2) *reinterpret_cast<uint32_t *>(op + s - 1) = acc;
+            RANS_O1_STEP(mine)
+            if (p3) *reinterpret_cast<uint32_t *>(op + s) = acc;
         }
-        renorm(R, mine, in, ipos, in_len);
+        // the last (up to 3) bytes produced by the unrolled loop may not have completed a word
+        if (mine) {
+            op[s - 1] = (uint8_t)(acc >> 24);
+            op[s - 2] = (uint8_t)(acc >> 16);
+            op[s - 3] = (uint8_t)(acc >> 8);
+        }
+        for (; s < seg; s++) {
+            ring_ensure(ring, wr, ipos, 64);
+            RANS_O1_STEP(mine)
+            if (mine) op[s] = (uint8_t)(acc >> 24);
+        }
     }
     // the last state also produces the U mod N tail (rANS_static32x16pr.c:669-680)
     const bool last = lane == N - 1;
-    for (uint32_t s = seg * N; s < U; s++) {
-        uint32_t m = R & mask;
-        uint32_t k = lut[(row << shift) + m];
-        uint2 e = fb[row * ncol + k];
-        if (last) {
-            R = (e.x & 0xffffu) * (R >> shift) + m - (e.x >> 16);
-            out[s] = (uint8_t)e.y;
-            row = k;
-        }
-        renorm(R, last, in, ipos, in_len);
+    for (uint32_t s2 = seg * N; s2 < U; s2++) {
+        ring_ensure(ring, wr, ipos, 64);
+        RANS_O1_STEP(last)
+        if (last) out[s2] = (uint8_t)(acc >> 24);
     }
+#undef RANS_O1_STEP
 }
 
 // Read the N initial states (RansDecInit, rANS_word.h:123) — lane z takes state z.
@@ -251,6 +345,7 @@ __device__ Table place_table(uint8_t *smem, const WarpScratch &ws, uint32_t rows
     Table t;
     uint32_t lut_bytes = ((rows << shift) + 7u) & ~7u;
     uint32_t need = lut_bytes + rows * ncol * 8u;
+    if (need > ws.smem_tab_bytes && ws.pass == 0) ws.defer = true;      // caller bails out
     uint8_t *base = need <= ws.smem_tab_bytes ? smem + SM_TAB : ws.gtab;
     t.in_smem = need <= ws.smem_tab_bytes;
     t.lut = base;
@@ -308,13 +403,14 @@ __device__ int dec_order0(uint8_t *smem, const WarpScratch &ws, const uint8_t *i
     if (warp_cumsum(F, cum, (int)ncol) != 4096u) return -1;
     if (ncol == 0) return -1;
     Table t = place_table(smem, ws, 1, ncol, 12);
+    if (ws.defer) return -1;
     fill_row(t, 0, F, cum, symof, N == 32);
     __syncwarp();
     uint32_t R;
     if (load_states(p, end, N, R)) return -1;
     uint32_t ipos = (uint32_t)(p - in) + 4 * N;
-    if (t.in_smem) loop_order0<true>(t, in, in_len, ipos, out, U, N, R);
-    else           loop_order0<false>(t, in, in_len, ipos, out, U, N, R);
+    if (t.in_smem) loop_order0<true>(smem, t, in, in_len, ipos, out, U, N, R);
+    else           loop_order0<false>(smem, t, in, in_len, ipos, out, U, N, R);
     __syncwarp();
     return 0;
 }
@@ -366,6 +462,7 @@ __device__ int dec_order1(uint8_t *smem, const WarpScratch &ws, const uint8_t *i
     }
     __syncwarp();
     Table t = place_table(smem, ws, ncol, ncol, shift);
+    if (ws.defer) return -1;
     const uint32_t total = 1u << shift;
     for (uint32_t r = 0; r < ncol; r++) {
         if (r == 0 && !zero_in_a0) { fill_null_row(t, 0); continue; }
@@ -411,8 +508,8 @@ __device__ int dec_order1(uint8_t *smem, const WarpScratch &ws, const uint8_t *i
     uint32_t R;
     if (load_states(p, end, N, R)) return -1;
     uint32_t ipos = (uint32_t)(p - in) + 4 * N;
-    if (t.in_smem) loop_order1<true>(t, in, in_len, ipos, out, U, N, R, 0);
-    else           loop_order1<false>(t, in, in_len, ipos, out, U, N, R, 0);
+    if (t.in_smem) loop_order1<true>(smem, t, in, in_len, ipos, out, U, N, R, 0);
+    else           loop_order1<false>(smem, t, in, in_len, ipos, out, U, N, R, 0);
     __syncwarp();
     return 0;
 }
@@ -607,6 +704,8 @@ __device__ int decode_stream(uint8_t *smem, const WarpScratch &ws, const uint8_t
 {
     const uint32_t lane = hgpu_lane();
     if (in_size == 0) return -1;
+    // pass 0 runs with no transform scratch: PACK / RLE / STRIPE streams go to pass 1
+    if (ws.pass == 0 && (in[0] & 0xc8)) { ws.defer = true; return -1; }
     if (!(in[0] & 0x08)) return decode_plain(smem, ws, in, in_size, out, out_cap, out_size);
 
     // STRIPE (:1594-1673): N sub-streams, byte-plane transposed
@@ -654,7 +753,10 @@ __device__ int decode_stream(uint8_t *smem, const WarpScratch &ws, const uint8_t
     return 0;
 }
 
-__global__ void __launch_bounds__(32)
+constexpr int32_t RANS_DEFERRED = 1;       // internal: written by pass 0, consumed by pass 1
+
+template <int PASS>
+__global__ void __launch_bounds__(32, PASS == 0 ? 24 : 10)
 rans_nx16_decode_kernel(const uint8_t *__restrict__ in, const uint64_t *__restrict__ in_off,
                         const uint32_t *__restrict__ in_len, uint32_t n, uint8_t *out,
                         const uint64_t *__restrict__ out_off, const uint32_t *__restrict__ out_len,
@@ -672,18 +774,23 @@ rans_nx16_decode_kernel(const uint8_t *__restrict__ in, const uint64_t *__restri
     ws.gtab = ws.tblbuf + TBLBUF_BYTES;
     ws.max_out = max_out;
     ws.smem_tab_bytes = smem_tab_bytes;
+    ws.pass = PASS;
+    ws.defer = false;
+    if (PASS == 0) { ws.tmp = ws.planes = ws.meta = ws.gtab = nullptr; ws.tblbuf = base; }
     for (;;) {
         uint32_t job = 0;
         if (hgpu_lane() == 0) job = atomicAdd(counter, 1u);
         job = __shfl_sync(0xffffffffu, job, 0);
         if (job >= n) break;
+        if (PASS == 1 && status[job] != RANS_DEFERRED) continue;
         uint32_t got = 0;
         int rc = decode_stream(smem, ws, in + in_off[job], in_len[job], out + out_off[job], out_len[job], got);
         __syncwarp();
         if (hgpu_lane() == 0) {
-            status[job] = rc ? HGPU_RANS_ERR : HGPU_OK;
+            status[job] = ws.defer ? RANS_DEFERRED : rc ? HGPU_RANS_ERR : HGPU_OK;
             got_len[job] = rc ? 0 : got;
         }
+        ws.defer = false;
     }
 }
 
@@ -696,35 +803,44 @@ int hgpu_launch_rans_nx16(hgpu_ctx *ctx, const uint8_t *d_in, const uint64_t *d_
                           cudaStream_t st)
 {
     if (n == 0) return HGPU_OK;
-    // Shared memory per warp-CTA: parsing arrays + table area.  18 KiB of table holds every
-    // order-0 table, and order-1 tables of <= 4 contexts at 12 bits / <= 16 at 10 bits with
-    // small alphabets, while still letting 11 CTAs share an SM.
-    const uint32_t smem_tab = 18 * 1024;
-    const uint32_t smem_total = SM_TAB + smem_tab;
+    // Two passes over the same job list, no host synchronisation in between.
+    //  pass 0: plain streams (no PACK/RLE/STRIPE) whose table fits 6.5 KiB of shared memory — every
+    //          order-0 table and order-1 tables of small alphabets (NovaSeq qualities) — at up to
+    //          24 single-warp CTAs per SM and 256 KiB of scratch per CTA;
+    //  pass 1: whatever pass 0 deferred, with 18 KiB of table space, the transform scratch and
+    //          the global-memory table fallback.
+    const uint32_t smem_tab0 = 6656, smem_tab1 = 18 * 1024;
+    const uint32_t smem0 = SM_TAB + smem_tab0, smem1 = SM_TAB + smem_tab1;
     static bool attr_set = false;
     if (!attr_set) {
-        if (hgpu_check(cudaFuncSetAttribute(rans_nx16_decode_kernel,
-                       cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_total), "rans smem attr"))
+        if (hgpu_check(cudaFuncSetAttribute(rans_nx16_decode_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem0), "rans smem attr") ||
+            hgpu_check(cudaFuncSetAttribute(rans_nx16_decode_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem1), "rans smem attr"))
             return HGPU_ERR_CUDA;
         attr_set = true;
     }
-    int per_sm = 0;
-    if (hgpu_check(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, rans_nx16_decode_kernel, 32, smem_total),
-                   "rans occupancy"))
+    int per_sm0 = 0, per_sm1 = 0;
+    if (hgpu_check(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm0, rans_nx16_decode_kernel<0>, 32, smem0), "rans occupancy") ||
+        hgpu_check(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm1, rans_nx16_decode_kernel<1>, 32, smem1), "rans occupancy"))
         return HGPU_ERR_CUDA;
-    if (per_sm < 1) per_sm = 1;
-    uint32_t grid = (uint32_t)ctx->sm_count * (uint32_t)per_sm;
-    if (grid > n) grid = n;
+    if (per_sm0 < 1) per_sm0 = 1;
+    if (per_sm1 < 1) per_sm1 = 1;
+    uint32_t grid0 = (uint32_t)ctx->sm_count * (uint32_t)per_sm0, grid1 = (uint32_t)ctx->sm_count * (uint32_t)per_sm1;
+    if (grid0 > n) grid0 = n;
+    if (grid1 > n) grid1 = n;
     size_t mo = ((size_t)max_out_len + 255) & ~(size_t)255;
-    size_t per_cta = 3 * mo + 1024 + TBLBUF_BYTES + GTAB_BYTES;
-    per_cta = (per_cta + 255) & ~(size_t)255;
-    int rc = hgpu_ensure_scratch(ctx, per_cta * grid);
+    size_t per_cta0 = TBLBUF_BYTES;
+    size_t per_cta1 = (3 * mo + 1024 + TBLBUF_BYTES + GTAB_BYTES + 255) & ~(size_t)255;
+    size_t need0 = per_cta0 * grid0, need1 = per_cta1 * grid1;
+    int rc = hgpu_ensure_scratch(ctx, need0 > need1 ? need0 : need1);
     if (rc) return rc;
-    uint32_t *counter = hgpu_take_counter(ctx, st);
-    if (!counter) return HGPU_ERR_CUDA;
-    rans_nx16_decode_kernel<<<grid, 32, smem_total, st>>>(d_in, d_in_off, d_in_len, n, d_out, d_out_off,
-                                                         d_out_len, d_got_len, d_status, ctx->d_scratch,
-                                                         per_cta, max_out_len, smem_tab, counter);
-    hgpu_count_launch();
+    uint32_t *c0 = hgpu_take_counter(ctx, st), *c1 = hgpu_take_counter(ctx, st);
+    if (!c0 || !c1) return HGPU_ERR_CUDA;
+    rans_nx16_decode_kernel<0><<<grid0, 32, smem0, st>>>(d_in, d_in_off, d_in_len, n, d_out, d_out_off, d_out_len,
+                                                         d_got_len, d_status, ctx->d_scratch, per_cta0,
+                                                         max_out_len, smem_tab0, c0);
+    rans_nx16_decode_kernel<1><<<grid1, 32, smem1, st>>>(d_in, d_in_off, d_in_len, n, d_out, d_out_off, d_out_len,
+                                                         d_got_len, d_status, ctx->d_scratch, per_cta1,
+                                                         max_out_len, smem_tab1, c1);
+    hgpu_count_launch(2);
     return hgpu_check(cudaGetLastError(), "rans launch");
 }

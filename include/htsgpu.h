@@ -114,6 +114,18 @@ int hgpu_rans_nx16_decode_batch_host(hgpu_ctx *ctx,
         uint8_t *out, const uint64_t *out_off, const uint32_t *out_len,
         uint32_t *got_len, int32_t *status);
 
+/* rANS Nx16 ENCODE — stands where rans_compress_to_4x16 stands (rANS_static4x16pr.c:1203-1579) for
+ * a batch of streams, one warp per stream.  order[i]: bit 0 = order-1, bit 2 (value 4) = 32-way
+ * (RANS_ORDER_X32); other transform bits are not produced yet.  out_cap[i] >=
+ * hgpu_rans_nx16_compress_bound(in_len[i], order[i]).  The output is a complete RANS_PR stream
+ * (format byte, size, table, states, words; CAT fallback when that is smaller) that the reference's
+ * rans_uncompress_to_4x16 decodes; bytes need not equal the reference encoder's. */
+uint32_t hgpu_rans_nx16_compress_bound(uint32_t size, int order);
+int hgpu_rans_nx16_encode_batch_dev(hgpu_ctx *ctx,
+        const uint8_t *d_in, const uint64_t *d_in_off, const uint32_t *d_in_len, const uint32_t *d_order,
+        uint32_t n, uint8_t *d_out, const uint64_t *d_out_off, const uint32_t *d_out_cap,
+        uint32_t *d_out_len, int32_t *d_status, void *stream);
+
 /* ------------------------------------------------------------------------------------------
  * BAM record unpack — the data movement of bam_read1 (sam.c:784-860) plus the 4-bit SEQ expand
  * and QUAL+33 of sam_format1_append (sam.c:4324-4404, nibble2base sam_internal.h:63-118) over
