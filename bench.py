@@ -37,7 +37,7 @@ def parse():
     ap.add_argument("--gb", type=float, default=10.0, help="uncompressed BAM gigabytes per GPU (10 = BASELINE configs[1])")
     ap.add_argument("--level", type=int, default=6)
     ap.add_argument("--quals", default="novaseq")
-    ap.add_argument("--rans-slices", type=int, default=4096, help="CRAM slices for the rANS leg (0 = skip)")
+    ap.add_argument("--rans-slices", type=int, default=-2, help="CRAM slices for the rANS leg (0 = skip)")
     ap.add_argument("--cpu-sample-gb", type=float, default=4.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
@@ -172,11 +172,12 @@ def make_corpus(args, rank):
 
 
 def rans_leg(args, ctx, torch, dev):
+    import htslib_b200 as H
     """CRAM 3.1 'normal'-profile shaped rANS blocks per slice of 10 000 x 150 bp reads: QS 1.5 MB
     32-way order-1, BF 15 kB 4-way order-1, CF/AP/NF/FN/BS 10 kB 4-way order-0 (SURVEY.md §8a').
     Streams are produced by the product's own GPU encoder."""
     from tools import synth
-    if args.rans_slices <= 0:
+    if args.rans_slices == 0:
         return None
     rng = np.random.default_rng(4242)
     uniq = 16                                   # unique slices, tiled to rans_slices (distinct addresses)
@@ -191,14 +192,21 @@ def rans_leg(args, ctx, torch, dev):
     comps = ctx.rans_nx16_encode(raws, orders, torch.cuda.current_stream().cuda_stream)
     assert all(c is not None for c in comps)
     ulens = [len(r) for r in raws]
-    per = len(comps) // uniq
-    reps = (args.rans_slices + uniq - 1) // uniq
-    in_len = np.tile(np.array([len(c) for c in comps], dtype=np.uint32), reps)
-    out_len = np.tile(np.array(ulens, dtype=np.uint32), reps)
+    if os.environ.get("RANS_ONLY_QS"):
+        keep = [i for i in range(len(comps)) if ulens[i] > 100000]
+        comps = [comps[i] for i in keep]; raws = [raws[i] for i in keep]; ulens = [ulens[i] for i in keep]
+    wave = H.lib().hgpu_rans_nx16_wave_size(ctx.h)
+    if args.rans_slices < 0:                      # -k: k full waves of quality blocks
+        args.rans_slices = -args.rans_slices * wave
+    per = len(comps) // uniq                    # streams per slice
+    nsl = args.rans_slices                      # exactly this many slices (unique ones tiled round-robin)
+    sel = np.concatenate([np.arange(per) + per * (s_ % uniq) for s_ in range(nsl)])
+    in_len = np.array([len(comps[i]) for i in sel], dtype=np.uint32)
+    out_len = np.array([ulens[i] for i in sel], dtype=np.uint32)
     # largest streams first so the persistent grid's tail is short
     order = np.argsort(-out_len.astype(np.int64), kind="stable")
     in_len, out_len = in_len[order], out_len[order]
-    src_idx = (np.arange(len(comps) * reps) % len(comps))[order]
+    src_idx = sel[order]
     in_off = np.concatenate([[0], np.cumsum((in_len.astype(np.int64) + 15) // 16 * 16)[:-1]]).astype(np.uint64)
     out_off = np.concatenate([[0], np.cumsum((out_len.astype(np.int64) + 15) // 16 * 16)[:-1]]).astype(np.uint64)
     blob = np.zeros(int(in_off[-1]) + int(in_len[-1]) + 64, dtype=np.uint8)
@@ -233,8 +241,8 @@ def rans_leg(args, ctx, torch, dev):
     U, Cb = int(out_len.astype(np.int64).sum()), int(in_len.astype(np.int64).sum())
     hbm, how = peaks()
     return {"workload": "CRAM3.1 rANS-Nx16 decode, %d slices x (QS 1.5MB X32-O1 + BF 15kB O1 + 5x10kB O0), NovaSeq 4-bin quals, %d unique slices tiled"
-                        % (reps * uniq, uniq),
-            "streams": n, "uncompressed_GB": U / 1e9, "compressed_GB": Cb / 1e9, "ms": ms,
+                        % (nsl, uniq),
+            "streams": n, "resident_streams_per_wave": int(wave), "uncompressed_GB": U / 1e9, "compressed_GB": Cb / 1e9, "ms": ms,
             "value": U / ms / 1e6, "unit": "GB/s (uncompressed)",
             "roofline": {"bound": "hbm", "achieved": (U + Cb) / ms / 1e6, "peak": hbm, "unit": "GB/s",
                          "frac": (U + Cb) / ms / 1e6 / hbm, "traffic": None, "peak_source": how}}

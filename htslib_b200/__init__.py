@@ -49,6 +49,8 @@ def lib():
     L.hgpu_crc32.argtypes = [vp, u32, vp, C.c_size_t]
     L.hgpu_rans_nx16_decode_batch_dev.argtypes = [vp, vp, vp, vp, u32, vp, vp, vp, vp, vp, u32, vp]
     L.hgpu_rans_nx16_decode_batch_host.argtypes = [vp, vp, vp, vp, u32, vp, vp, vp, vp, vp]
+    L.hgpu_rans_nx16_wave_size.restype = u32
+    L.hgpu_rans_nx16_wave_size.argtypes = [vp]
     L.hgpu_rans_nx16_compress_bound.restype = u32
     L.hgpu_rans_nx16_compress_bound.argtypes = [u32, C.c_int]
     L.hgpu_rans_nx16_encode_batch_dev.argtypes = [vp, vp, vp, vp, vp, u32, vp, vp, vp, vp, vp, vp]

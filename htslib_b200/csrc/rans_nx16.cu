@@ -31,8 +31,8 @@ constexpr int SM_CUM    = 1024;                     // u32 cum[257]        1028 
 constexpr int SM_ROWOF  = 2064;                     // u8 rowof[256]  byte -> compact row / 0xff
 constexpr int SM_SYMOF  = 2320;                     // u8 symof[256]  compact index -> byte
 constexpr int SM_RING   = 2576;                     // 512 B ring mirroring the compressed word stream
-constexpr int SM_TAB    = 3088;                     // table area (8-byte aligned)
-constexpr uint32_t GTAB_BYTES = 256u * 4096u + 256u * 256u * 8u;   // worst-case order-1 table
+constexpr int SM_TAB    = 3088;                     // table area (16-byte aligned)
+constexpr uint32_t GTAB_BYTES = 256u * 4096u + 256u * 256u * 4u;   // worst-case order-1 table
 constexpr uint32_t TBLBUF_BYTES = 256u * 1024u;     // decoded (was-compressed) order-1 table text
 
 struct WarpScratch {
@@ -97,7 +97,7 @@ __device__ int read_alphabet(const uint8_t *p, const uint8_t *end, uint32_t *F)
 
 struct Table {
     uint8_t *lut;      // [rows][1<<shift]
-    uint2   *fb;       // [rows][ncol]
+    uint32_t *fb;      // [rows][ncol]  byte | start<<8 | (f-1)<<20
     uint32_t ncol;     // compact alphabet size
     uint32_t shift;
     bool     in_smem;
@@ -138,15 +138,16 @@ __device__ void fill_row(const Table &t, uint32_t row, const uint32_t *f, const 
 {
     const uint32_t lane = hgpu_lane();
     uint8_t *lrow = t.lut + ((size_t)row << t.shift);
-    uint2 *frow = t.fb + (size_t)row * t.ncol;
+    uint32_t *frow = t.fb + (size_t)row * t.ncol;
     for (uint32_t k = 0; k < t.ncol; k++) {
         uint32_t fk = f[k], c0 = cum[k];
         if (!fk) continue;
         for (uint32_t y = lane; y < fk; y += 32) lrow[c0 + y] = (uint8_t)k;
     }
     for (uint32_t k = lane; k < t.ncol; k += 32) {
-        uint32_t fk = wrap12 ? (f[k] & 0xfffu) : f[k];
-        frow[k] = make_uint2(fk | (cum[k] << 16), symof[k]);
+        uint32_t fk = f[k];
+        (void)wrap12;     // F == 4096 only occurs for a one-symbol table, whose output does not depend on the state
+        frow[k] = fk ? ((uint32_t)symof[k] | (cum[k] << 8) | ((fk - 1u) << 20)) : 0u;
     }
 }
 
@@ -156,7 +157,7 @@ __device__ void fill_null_row(const Table &t, uint32_t row)
     const uint32_t lane = hgpu_lane();
     uint8_t *lrow = t.lut + ((size_t)row << t.shift);
     for (uint32_t y = lane; y < (1u << t.shift); y += 32) lrow[y] = 0;
-    if (lane == 0) t.fb[(size_t)row * t.ncol] = make_uint2(0, 0);
+    if (lane == 0) t.fb[(size_t)row * t.ncol] = 0;     // byte 0, start 0, f 1
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -169,7 +170,15 @@ __device__ void fill_null_row(const Table &t, uint32_t row)
 // accumulator and stored as aligned words at the step where the lane's address crosses a 4-byte
 // boundary (a per-lane phase, constant across the 4-step unrolled loop), so a step costs one
 // predicated STG.32 per warp and 8 instead of 32 L2 transactions.
+// Table records are 4 bytes (byte | start<<8 | (f-1)<<20): shared-memory bandwidth, not issue, is
+// what bounds this loop (24 warps x 3 LDS per step), so the record is as narrow as it can be.
 // ---------------------------------------------------------------------------------------------
+// Explicit shared-space accesses with 32-bit addresses: the generic pointer of the dynamic shared
+// array would otherwise be rebuilt (S2UR/ULEA/IMAD) at every access inside the hot loop.
+__device__ __forceinline__ uint32_t lds_u8(uint32_t a) { uint32_t v; asm volatile("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(a) : "memory"); return v; }
+__device__ __forceinline__ uint32_t lds_u16(uint32_t a) { uint32_t v; asm volatile("ld.shared.u16 %0, [%1];" : "=r"(v) : "r"(a) : "memory"); return v; }
+__device__ __forceinline__ uint32_t lds_u32(uint32_t a) { uint32_t v; asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a) : "memory"); return v; }
+
 struct WordRing {
     const uint8_t *in;       // stream start (global)
     uintptr_t lim;           // first aligned word address entirely past the input
@@ -209,23 +218,30 @@ __device__ __forceinline__ void ring_init(uint8_t *ring, WordRing &wr, const uin
     ring_ensure(ring, wr, ipos, 256);
 }
 
-__device__ __forceinline__ void renorm(uint32_t &R, bool active, const uint8_t *ring, const WordRing &wr,
-                                       uint32_t &ipos, uint32_t in_len)
+// renormalise with bounds care (RansDecRenormSafe, rANS_word.h:441): used near the end of input
+__device__ __forceinline__ void renorm_safe(uint32_t &R, bool active, const uint8_t *ring, const WordRing &wr,
+                                            uint32_t &ipos, uint32_t in_len)
 {
     bool need = active && R < RANS_L;
     uint32_t bal = __ballot_sync(0xffffffffu, need);
     if (bal) {
         uint32_t wpos = ipos + 2u * __popc(bal & hgpu_lanemask_lt());
         uint32_t w = *reinterpret_cast<const uint16_t *>(ring + ((wpos - wr.ipos0) & 511u));
-        if (ipos + 64u <= in_len) {                      // every candidate word is inside the input
-            if (need) R = (R << 16) | w;
-            ipos += 2u * __popc(bal);
-        } else {                                         // RansDecRenormSafe, rANS_word.h:441
-            bool ok = need && wpos + 2u <= in_len;
-            if (ok) R = (R << 16) | w;
-            ipos += 2u * __popc(__ballot_sync(0xffffffffu, ok));
-        }
+        bool ok = need && wpos + 2u <= in_len;
+        if (ok) R = (R << 16) | w;
+        ipos += 2u * __popc(__ballot_sync(0xffffffffu, ok));
     }
+}
+
+// branch-free renormalise; the caller guarantees ipos + 64 <= in_len.  rel = ipos - ipos0.
+__device__ __forceinline__ void renorm_fast(uint32_t &R, bool active, const uint8_t *ring, uint32_t &rel)
+{
+    bool need = active && R < RANS_L;
+    uint32_t bal = __ballot_sync(0xffffffffu, need);
+    uint32_t rank = __popc(bal & hgpu_lanemask_lt());
+    uint32_t w = *reinterpret_cast<const uint16_t *>(ring + ((rel + 2u * rank) & 511u));
+    if (need) R = (R << 16) | w;
+    rel += 2u * __popc(bal);
 }
 
 template <bool SMEM>
@@ -235,76 +251,113 @@ __device__ void loop_order0(uint8_t *smem, const Table &t, const uint8_t *in, ui
     const uint32_t lane = hgpu_lane();
     const uint32_t mask = (1u << t.shift) - 1, shift = t.shift;
     const uint8_t *lut = SMEM ? smem + SM_TAB : t.lut;
-    const uint2 *fb = SMEM ? reinterpret_cast<const uint2 *>(smem + SM_TAB + (((1u << t.shift) + 7u) & ~7u)) : t.fb;
+    const uint32_t *fb = SMEM ? reinterpret_cast<const uint32_t *>(smem + SM_TAB + (((1u << t.shift) + 15u) & ~15u)) : t.fb;
     uint8_t *ring = smem + SM_RING;
     WordRing wr;
     ring_init(ring, wr, in, in_len, ipos);
     const bool mine = lane < N;
-    for (uint32_t i = lane; __any_sync(0xffffffffu, mine && i < U); i += N) {
+    uint32_t i = lane;
+    // fast rows: every lane of the row active and the input far from its end
+    if (N == 32) {
+        uint32_t rel = 0;
+        while (i + (32u - lane) <= U && ipos + rel + 64u <= in_len) {
+            ring_ensure(ring, wr, ipos + rel, 64);
+            uint32_t m = R & mask;
+            uint32_t e = fb[lut[m]], q = R >> shift;
+            R = (e >> 20) * q + q + m - ((e >> 8) & 0xfffu);
+            out[i] = (uint8_t)e;
+            renorm_fast(R, true, ring, rel);
+            i += 32;
+        }
+        ipos += rel;
+    }
+    for (; __any_sync(0xffffffffu, mine && i < U); i += N) {
         ring_ensure(ring, wr, ipos, 64);
         bool act = mine && i < U;
         uint32_t m = R & mask;
-        uint32_t k = lut[m];
-        uint2 e = fb[k];
+        uint32_t e = fb[lut[m]], q = R >> shift;
         if (act) {
-            R = (e.x & 0xffffu) * (R >> shift) + m - (e.x >> 16);
-            out[i] = (uint8_t)e.y;
+            R = (e >> 20) * q + q + m - ((e >> 8) & 0xfffu);
+            out[i] = (uint8_t)e;
         }
-        renorm(R, act, ring, wr, ipos, in_len);
+        renorm_safe(R, act, ring, wr, ipos, in_len);
     }
 }
 
-template <bool SMEM>
+// branch-free renormalise on a 32-bit shared address of the ring; caller guarantees the next 64
+// input bytes exist.  rel = ipos - ipos0.
+__device__ __forceinline__ void renorm_fast_s(uint32_t &R, bool active, uint32_t ring_a, uint32_t &rel)
+{
+    bool need = active && R < RANS_L;
+    uint32_t bal = __ballot_sync(0xffffffffu, need);
+    uint32_t rank = __popc(bal & hgpu_lanemask_lt());
+    uint32_t w = lds_u16(ring_a + ((rel + 2u * rank) & 511u));
+    R = need ? (R << 16) | w : R;
+    rel += 2u * __popc(bal);
+}
+
+template <bool SMEM, bool FULL>
 __device__ void loop_order1(uint8_t *smem, const Table &t, const uint8_t *in, uint32_t in_len, uint32_t ipos,
                             uint8_t *out, uint32_t U, uint32_t N, uint32_t R, uint32_t row0)
 {
     const uint32_t lane = hgpu_lane();
-    const uint32_t mask = (1u << t.shift) - 1, shift = t.shift, ncol = t.ncol;
+    const uint32_t mask = (1u << t.shift) - 1, shift = t.shift;
+    const uint32_t fb_off = ((t.ncol << t.shift) + 15u) & ~15u;
     const uint8_t *lut = SMEM ? smem + SM_TAB : t.lut;
-    const uint2 *fb = SMEM ? reinterpret_cast<const uint2 *>(smem + SM_TAB + (((t.ncol << t.shift) + 7u) & ~7u)) : t.fb;
+    const uint8_t *fbb = SMEM ? smem + SM_TAB + fb_off : reinterpret_cast<const uint8_t *>(t.fb);
+    const uint32_t sm_base = (uint32_t)__cvta_generic_to_shared(smem);
+    const uint32_t lut_a = sm_base + SM_TAB, fb_a = sm_base + SM_TAB + fb_off, ring_a = sm_base + SM_RING;
     uint8_t *ring = smem + SM_RING;
     WordRing wr;
     ring_init(ring, wr, in, in_len, ipos);
-    const bool mine = lane < N;
+    const bool mine = FULL ? true : lane < N;
     const uint32_t seg = U / N;
     uint8_t *op = out + (size_t)(mine ? lane : 0) * seg;
-    uint32_t row = row0, acc = 0;
+    const uint32_t fstride = t.ncol * 4u;
+    uint32_t lrow = row0 << shift, frow = row0 * fstride, acc = 0;
 
-#define RANS_O1_STEP(ACTIVE)                                                                       \
-    {                                                                                              \
+    // one symbol for the lanes in ACTIVE; the record carries the next row's offsets
+#define RANS_O1_CORE(ACTIVE)                                                                       \
         uint32_t m = R & mask;                                                                     \
-        uint32_t k = lut[(row << shift) + m];                                                      \
-        uint2 e = fb[row * ncol + k];                                                              \
+        uint32_t k = SMEM ? lds_u8(lut_a + lrow + m) : (uint32_t)lut[lrow + m];                    \
+        uint32_t e = SMEM ? lds_u32(fb_a + frow + k * 4u)                                          \
+                          : *reinterpret_cast<const uint32_t *>(fbb + frow + k * 4u);              \
         if (ACTIVE) {                                                                              \
-            R = (e.x & 0xffffu) * (R >> shift) + m - (e.x >> 16);                                  \
-            acc = (acc >> 8) | (e.y << 24);                                                        \
-            row = k;                                                                               \
-        }                                                                                          \
-        renorm(R, ACTIVE, ring, wr, ipos, in_len);                                                 \
-    }
+            uint32_t q = R >> shift;                                                               \
+            R = (e >> 20) * q + q + m - ((e >> 8) & 0xfffu);                                       \
+            acc = __funnelshift_l(acc, e, 24);                                                     \
+            lrow = k << shift;                                                                     \
+            frow = k * fstride;                                                                    \
+        }
 
     uint32_t s = 0;
     // head: the first word of a segment may be shared with the previous segment -> byte stores
     for (; s < 4 && s < seg; s++) {
         ring_ensure(ring, wr, ipos, 64);
-        RANS_O1_STEP(mine)
+        { RANS_O1_CORE(mine) }
+        renorm_safe(R, mine, ring, wr, ipos, in_len);
         if (mine) op[s] = (uint8_t)(acc >> 24);
     }
     if (s == 4) {
         // phase: at unrolled position j the lane's address ends a 4-byte word iff (op+s+j)&3 == 3
         const uint32_t ph = (uint32_t)(reinterpret_cast<uintptr_t>(op) + 4u) & 3u;
         const bool p0 = mine && ph == 3u, p1 = mine && ph == 2u, p2 = mine && ph == 1u, p3 = mine && ph == 0u;
-        for (; s + 4 <= seg; s += 4) {
-            ring_ensure(ring, wr, ipos, 256);
-            RANS_O1_STEP(mine)
-            if (p0) *reinterpret_cast<uint32_t *>(op + s - 3) = acc;
-            RANS_O1_STEP(mine)
-            if (p1) *reinterpret_cast<uint32_t *>(op + s - 2) = acc;
-            RANS_O1_STEP(mine)
-            if (p2) *reinterpret_cast<uint32_t *>(op + s - 1) = acc;
-            RANS_O1_STEP(mine)
-            if (p3) *reinterpret_cast<uint32_t *>(op + s) = acc;
+        uint8_t *wp = op + s;                                        // running pointer of the unrolled loop
+        uint32_t rel = ipos - wr.ipos0;
+        while (s + 4 <= seg && wr.ipos0 + rel + 256u <= in_len) {
+            ring_ensure(ring, wr, wr.ipos0 + rel, 256);
+            { RANS_O1_CORE(mine) renorm_fast_s(R, mine, ring_a, rel); }
+            if (p0) *reinterpret_cast<uint32_t *>(wp - 3) = acc;
+            { RANS_O1_CORE(mine) renorm_fast_s(R, mine, ring_a, rel); }
+            if (p1) *reinterpret_cast<uint32_t *>(wp - 2) = acc;
+            { RANS_O1_CORE(mine) renorm_fast_s(R, mine, ring_a, rel); }
+            if (p2) *reinterpret_cast<uint32_t *>(wp - 1) = acc;
+            { RANS_O1_CORE(mine) renorm_fast_s(R, mine, ring_a, rel); }
+            if (p3) *reinterpret_cast<uint32_t *>(wp) = acc;
+            wp += 4;
+            s += 4;
         }
+        ipos = wr.ipos0 + rel;
         // the last (up to 3) bytes produced by the unrolled loop may not have completed a word
         if (mine) {
             op[s - 1] = (uint8_t)(acc >> 24);
@@ -313,7 +366,8 @@ __device__ void loop_order1(uint8_t *smem, const Table &t, const uint8_t *in, ui
         }
         for (; s < seg; s++) {
             ring_ensure(ring, wr, ipos, 64);
-            RANS_O1_STEP(mine)
+            { RANS_O1_CORE(mine) }
+            renorm_safe(R, mine, ring, wr, ipos, in_len);
             if (mine) op[s] = (uint8_t)(acc >> 24);
         }
     }
@@ -321,10 +375,11 @@ __device__ void loop_order1(uint8_t *smem, const Table &t, const uint8_t *in, ui
     const bool last = lane == N - 1;
     for (uint32_t s2 = seg * N; s2 < U; s2++) {
         ring_ensure(ring, wr, ipos, 64);
-        RANS_O1_STEP(last)
+        { RANS_O1_CORE(last) }
+        renorm_safe(R, last, ring, wr, ipos, in_len);
         if (last) out[s2] = (uint8_t)(acc >> 24);
     }
-#undef RANS_O1_STEP
+#undef RANS_O1_CORE
 }
 
 // Read the N initial states (RansDecInit, rANS_word.h:123) — lane z takes state z.
@@ -343,13 +398,13 @@ __device__ int load_states(const uint8_t *p, const uint8_t *end, uint32_t N, uin
 __device__ Table place_table(uint8_t *smem, const WarpScratch &ws, uint32_t rows, uint32_t ncol, uint32_t shift)
 {
     Table t;
-    uint32_t lut_bytes = ((rows << shift) + 7u) & ~7u;
-    uint32_t need = lut_bytes + rows * ncol * 8u;
+    uint32_t lut_bytes = ((rows << shift) + 15u) & ~15u;
+    uint32_t need = lut_bytes + rows * ncol * 4u;
     if (need > ws.smem_tab_bytes && ws.pass == 0) ws.defer = true;      // caller bails out
     uint8_t *base = need <= ws.smem_tab_bytes ? smem + SM_TAB : ws.gtab;
     t.in_smem = need <= ws.smem_tab_bytes;
     t.lut = base;
-    t.fb = reinterpret_cast<uint2 *>(base + lut_bytes);
+    t.fb = reinterpret_cast<uint32_t *>(base + lut_bytes);
     t.ncol = ncol;
     t.shift = shift;
     return t;
@@ -508,8 +563,10 @@ __device__ int dec_order1(uint8_t *smem, const WarpScratch &ws, const uint8_t *i
     uint32_t R;
     if (load_states(p, end, N, R)) return -1;
     uint32_t ipos = (uint32_t)(p - in) + 4 * N;
-    if (t.in_smem) loop_order1<true>(smem, t, in, in_len, ipos, out, U, N, R, 0);
-    else           loop_order1<false>(smem, t, in, in_len, ipos, out, U, N, R, 0);
+    if (t.in_smem) {
+        if (N == 32) loop_order1<true, true>(smem, t, in, in_len, ipos, out, U, N, R, 0);
+        else         loop_order1<true, false>(smem, t, in, in_len, ipos, out, U, N, R, 0);
+    } else           loop_order1<false, false>(smem, t, in, in_len, ipos, out, U, N, R, 0);
     __syncwarp();
     return 0;
 }
@@ -795,6 +852,18 @@ rans_nx16_decode_kernel(const uint8_t *__restrict__ in, const uint64_t *__restri
 }
 
 } // namespace
+
+// streams the fast pass keeps resident at once (persistent grid size): callers that can choose
+// their batch size should use a multiple of it.
+extern "C" uint32_t hgpu_rans_nx16_wave_size(hgpu_ctx *ctx)
+{
+    if (!ctx) return 0;
+    int per_sm0 = 0;
+    const uint32_t smem0 = SM_TAB + 6656;
+    cudaFuncSetAttribute(rans_nx16_decode_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem0);
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm0, rans_nx16_decode_kernel<0>, 32, smem0) != cudaSuccess) return 0;
+    return (uint32_t)ctx->sm_count * (uint32_t)(per_sm0 < 1 ? 1 : per_sm0);
+}
 
 int hgpu_launch_rans_nx16(hgpu_ctx *ctx, const uint8_t *d_in, const uint64_t *d_in_off,
                           const uint32_t *d_in_len, uint32_t n, uint8_t *d_out,

@@ -109,6 +109,10 @@ int hgpu_rans_nx16_decode_batch_dev(hgpu_ctx *ctx,
         uint8_t *d_out, const uint64_t *d_out_off, const uint32_t *d_out_len,
         uint32_t *d_got_len, int32_t *d_status, uint32_t max_out_len, void *stream);
 
+/* Number of streams the decoder keeps resident at once (its persistent grid); batch sizes that
+ * are multiples of it avoid a partly filled last wave. */
+uint32_t hgpu_rans_nx16_wave_size(hgpu_ctx *ctx);
+
 int hgpu_rans_nx16_decode_batch_host(hgpu_ctx *ctx,
         const uint8_t *in, const uint64_t *in_off, const uint32_t *in_len, uint32_t n,
         uint8_t *out, const uint64_t *out_off, const uint32_t *out_len,

@@ -222,9 +222,9 @@ static int dec_order1(const uint8_t *in, uint32_t in_size, uint8_t *out, uint32_
     if (!store) goto done;
     /* Contexts that are absent, or present with no frequencies, are never entered by a valid
      * stream; the reference reads whatever its TLS scratch held (rANS_static4x16pr.c:589-591
-     * "continue").  The oracle pins that undefined case to a fixed row: symbol 0, f 0, b = slot
+     * "continue").  The oracle pins that undefined case to a fixed row: symbol 0, f 1, b = slot
      * index, which is also what the CUDA decoder produces. */
-    for (i = 0; i < (1 << shift); i++) store[i].b = (uint16_t)i;
+    for (i = 0; i < (1 << shift); i++) { store[i].b = (uint16_t)i; store[i].f = 1; }
     for (i = 0; i < 256; i++) lut[i] = store;
     nctx = 1;
     for (i = 0; i < 256; i++) {
