@@ -44,6 +44,7 @@ def lib():
     L.hgpu_bgzf_scan.argtypes = [vp, u64, vp, vp, vp, C.c_long]
     L.hgpu_bgzf_inflate_file_host.argtypes = [vp, vp, u64, vp, u64, C.POINTER(u64), C.POINTER(C.c_long)]
     L.hgpu_bgzf_inflate_blocks_host.argtypes = [vp, vp, vp, vp, u32, vp, vp, vp, vp, vp]
+    L.hgpu_bgzf_compress_batch_dev.argtypes = [vp, vp, vp, vp, u32, C.c_int, vp, vp, vp, vp, vp]
     L.hgpu_shard_range.argtypes = [u64, vp, C.c_int, C.c_int, C.POINTER(u64), C.POINTER(u64), C.POINTER(u64)]
     L.hgpu_crc32.restype = u32
     L.hgpu_crc32.argtypes = [vp, u32, vp, C.c_size_t]
@@ -57,6 +58,8 @@ def lib():
     L.hgpu_bam_index_records_dev.argtypes = [vp, vp, u64, vp, u64, vp, u64, vp, vp]
     L.hgpu_bam_layout_dev.argtypes = [vp, vp, u64, vp, u64, vp, vp, vp]
     L.hgpu_bam_unpack_dev.argtypes = [vp, vp, u64, vp, u64, vp, vp, vp, vp, vp, vp, vp, vp]
+    L.hgpu_bam_pack_dev.argtypes = [vp, vp, vp, vp, u64, vp, vp, vp, vp]
+    L.bgzf_compress.argtypes = [vp, C.POINTER(C.c_size_t), vp, C.c_size_t, C.c_int]
     L.rans_uncompress_to_4x16.restype = vp
     L.rans_uncompress_to_4x16.argtypes = [vp, C.c_uint, vp, C.POINTER(C.c_uint)]
     L.rans_uncompress_4x16.restype = vp
@@ -108,6 +111,28 @@ class Context:
                                                     d_out.data_ptr(), d_out_off.data_ptr(), d_out_len.data_ptr(),
                                                     d_got.data_ptr(), d_status.data_ptr(), int(max_out_len), stream),
               "rans_nx16_decode_batch_dev")
+
+    def bgzf_compress(self, payloads, level=6, stream=0):
+        """Compress a list of payloads (each <= 65280 bytes) into BGZF blocks on the device."""
+        import numpy as np
+        import torch
+        n = len(payloads)
+        dev = torch.device("cuda", torch.cuda.current_device())
+        in_len = np.array([len(p) for p in payloads], dtype=np.uint32)
+        in_off = np.concatenate([[0], np.cumsum(in_len.astype(np.int64))[:-1]]).astype(np.int64)
+        blob = np.frombuffer(b"".join(payloads) + b"\0" * 8, dtype=np.uint8).copy()
+        d_in = torch.from_numpy(blob).to(dev)
+        d_out = torch.zeros(n * 65536 + 64, dtype=torch.uint8, device=dev)
+        out_off = np.arange(n, dtype=np.int64) * 65536
+        t = lambda a: torch.from_numpy(a).to(dev)
+        d_io, d_il, d_oo = t(in_off), t(in_len.view(np.int32)), t(out_off)
+        d_ol = torch.zeros(n, dtype=torch.int32, device=dev); d_st = torch.zeros(n, dtype=torch.int32, device=dev)
+        check(lib().hgpu_bgzf_compress_batch_dev(self.h, d_in.data_ptr(), d_io.data_ptr(), d_il.data_ptr(), n, level,
+                                                 d_out.data_ptr(), d_oo.data_ptr(), d_ol.data_ptr(), d_st.data_ptr(), stream),
+              "bgzf_compress_batch_dev")
+        torch.cuda.synchronize()
+        out = d_out.cpu().numpy(); ol = d_ol.cpu().numpy(); st = d_st.cpu().numpy()
+        return [out[i * 65536:i * 65536 + int(ol[i])].tobytes() if st[i] == 0 else None for i in range(n)]
 
     def rans_nx16_encode(self, raws, orders, stream=0):
         """Encode a list of byte strings on the device (hgpu_rans_nx16_encode_batch_dev).  Returns
@@ -165,6 +190,20 @@ class Context:
                                     data_off.data_ptr(), seq.data_ptr() if want_text else None, qual.data_ptr() if want_text else None,
                                     seq_off.data_ptr(), status.data_ptr(), stream), "bam_unpack")
         return dict(n=n, rec_off=rec_off, core=core, data=data, data_off=data_off, seq=seq, qual=qual, seq_off=seq_off, status=status)
+
+    def bam_pack_dev(self, core, data, data_off, n, stream=0):
+        """bam_write1 data movement on the device: returns (out uint8 tensor, out_off int64[n+1], status)."""
+        import torch
+        dev = core.device
+        out_off = torch.empty(n + 1, dtype=torch.int64, device=dev)
+        status = torch.zeros(max(1, n), dtype=torch.int32, device=dev)
+        L = lib()
+        check(L.hgpu_bam_pack_dev(self.h, core.data_ptr(), data.data_ptr(), data_off.data_ptr(), n, None, out_off.data_ptr(), None, stream), "bam_pack(layout)")
+        torch.cuda.synchronize()
+        total = int(out_off[n].item())
+        out = torch.empty(max(1, total), dtype=torch.uint8, device=dev)
+        check(L.hgpu_bam_pack_dev(self.h, core.data_ptr(), data.data_ptr(), data_off.data_ptr(), n, out.data_ptr(), out_off.data_ptr(), status.data_ptr(), stream), "bam_pack")
+        return out[:total], out_off, status
 
     # ---- host-pointer entry points; buffers are numpy uint8 arrays (or pinned torch tensors' .numpy()) ----
     def bgzf_inflate_file_host(self, file_np, out_np):

@@ -365,3 +365,99 @@ extern "C" int hgpu_bam_unpack_dev(hgpu_ctx *ctx, const uint8_t *d_stream, uint6
     hgpu_count_launch();
     return hgpu_check(cudaGetLastError(), "bam unpack launch");
 }
+
+// =============================================================================================
+// BAM record PACK — the inverse data movement, bam_write1 (sam.c:862-928): bam1_core_t + data ->
+// block_size, 32-byte little-endian core, qname without the padding NULs, the rest verbatim.
+// Records with more than 65535 CIGAR operations need the CG-tag rewrite (:899-925): they are
+// flagged (status 1) and given zero bytes; qname > 254 / positions beyond INT_MAX -> status -1.
+// =============================================================================================
+namespace {
+
+__global__ void bam_pack_sizes_kernel(const hgpu_bam1_core *core, const uint64_t *data_off, uint64_t n,
+                                      uint64_t *out_sz, uint64_t *dummy)
+{
+    uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i > n) return;
+    uint64_t sz = 0;
+    if (i < n) {
+        hgpu_bam1_core c = core[i];
+        uint32_t l_data = (uint32_t)(data_off[i + 1] - data_off[i]);
+        bool bad = (uint32_t)c.l_qname - c.l_extranul > 255u || c.n_cigar > 0xffffu || c.pos > 0x7fffffffLL ||
+                   c.mpos > 0x7fffffffLL || c.isize < -0x80000000LL || c.isize > 0x7fffffffLL;
+        sz = bad ? 0 : 4ull + l_data - c.l_extranul + 32;
+    }
+    out_sz[i] = sz;
+    dummy[i] = 0;
+}
+
+__global__ void __launch_bounds__(256)
+bam_pack_kernel(const hgpu_bam1_core *core, const uint8_t *data, const uint64_t *data_off, uint64_t n,
+                uint8_t *out, const uint64_t *out_off, int32_t *status)
+{
+    const uint32_t lane = threadIdx.x & 31;
+    uint64_t r = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (r >= n) return;
+    hgpu_bam1_core c = core[r];
+    const uint8_t *d = data + data_off[r];
+    const uint32_t l_data = (uint32_t)(data_off[r + 1] - data_off[r]);
+    const uint32_t qn = (uint32_t)c.l_qname - c.l_extranul;
+    int st = 0;
+    if (qn > 255u || c.pos > 0x7fffffffLL || c.mpos > 0x7fffffffLL || c.isize < -0x80000000LL || c.isize > 0x7fffffffLL) st = -1;
+    else if (c.n_cigar > 0xffffu) st = 1;
+    if (lane == 0 && status) status[r] = st;
+    if (st) return;
+    uint8_t *o = out + out_off[r];
+    const uint32_t block_len = l_data - c.l_extranul + 32;
+    if (lane < 9) {
+        uint32_t v;
+        switch (lane) {
+        case 0: v = block_len; break;
+        case 1: v = (uint32_t)c.tid; break;
+        case 2: v = (uint32_t)c.pos; break;
+        case 3: v = (uint32_t)c.bin << 16 | (uint32_t)c.qual << 8 | qn; break;
+        case 4: v = (uint32_t)c.flag << 16 | (c.n_cigar & 0xffffu); break;
+        case 5: v = (uint32_t)c.l_qseq; break;
+        case 6: v = (uint32_t)c.mtid; break;
+        case 7: v = (uint32_t)c.mpos; break;
+        default: v = (uint32_t)c.isize; break;
+        }
+        uint8_t *p = o + 4 * lane;
+        p[0] = (uint8_t)v; p[1] = (uint8_t)(v >> 8); p[2] = (uint8_t)(v >> 16); p[3] = (uint8_t)(v >> 24);
+    }
+    for (uint32_t i = lane; i < qn; i += 32) o[36 + i] = d[i];
+    const uint32_t rest = l_data - c.l_qname;
+    const uint8_t *from = d + c.l_qname;
+    uint8_t *to = o + 36 + qn;
+    for (uint32_t i = lane; i < rest; i += 32) to[i] = from[i];
+}
+
+} // namespace
+
+// d_out_off: n+1 entries, filled here (exclusive prefix sums of the record sizes); pass d_out = NULL
+// to only compute the layout.
+extern "C" int hgpu_bam_pack_dev(hgpu_ctx *ctx, const hgpu_bam1_core *d_core, const uint8_t *d_data,
+                                 const uint64_t *d_data_off, uint64_t n, uint8_t *d_out, uint64_t *d_out_off,
+                                 int32_t *d_status, void *stream)
+{
+    if (!ctx || !d_core || !d_data_off || !d_out_off) { hgpu_set_error("bad argument"); return HGPU_ERR_ARG; }
+    cudaStream_t st = stream ? (cudaStream_t)stream : ctx->stream;
+    if (!d_out) {
+        uint64_t m = n + 1, nt = (m + TILE - 1) / TILE;
+        int rc = hgpu_ensure_bam(ctx, (nt * 2 + m) * sizeof(uint64_t) + 64);
+        if (rc) return rc;
+        uint64_t *ta = (uint64_t *)ctx->d_bam, *tb = ta + nt, *dummy = tb + nt;
+        bam_pack_sizes_kernel<<<(unsigned)((m + 255) / 256), 256, 0, st>>>(d_core, d_data_off, n, d_out_off, dummy);
+        scan_tiles_reduce<<<(unsigned)nt, 256, 0, st>>>(d_out_off, dummy, m, ta, tb);
+        scan_tile_sums<<<1, 1024, 0, st>>>(ta, tb, nt);
+        scan_tiles_apply<<<(unsigned)nt, 256, 0, st>>>(d_out_off, dummy, m, ta, tb);
+        hgpu_count_launch(4);
+        return hgpu_check(cudaGetLastError(), "bam pack layout launch");
+    }
+    if (n == 0) return HGPU_OK;
+    if (!d_data) { hgpu_set_error("bad argument"); return HGPU_ERR_ARG; }
+    uint64_t blocks = (n * 32 + 255) / 256;
+    bam_pack_kernel<<<(unsigned)blocks, 256, 0, st>>>(d_core, d_data, d_data_off, n, d_out, d_out_off, d_status);
+    hgpu_count_launch();
+    return hgpu_check(cudaGetLastError(), "bam pack launch");
+}

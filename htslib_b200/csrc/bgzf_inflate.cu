@@ -857,6 +857,217 @@ int ensure_crc_tables(hgpu_ctx *ctx, cudaStream_t st)
     return HGPU_OK;
 }
 
+
+// =============================================================================================
+// BGZF block COMPRESS — stands where bgzf_compress / deflate_block / bgzf_encode_func stand
+// (bgzf.c:624-683, :709, :1330): one warp per <= 0xff00-byte payload, output = a complete BGZF
+// block (18-byte header, raw DEFLATE, CRC32, ISIZE).  Compressed bytes need not match zlib's
+// (SURVEY.md §8c); what is pinned is that zlib / the reference reader inflate them back to the
+// input and that the size stays within a stated ratio (tests/test_gpu_bgzf_compress.py).
+//
+// level 0  : stored block, exactly what htslib writes at level 0 (bgzf.c:573-580).
+// level >=1: lane-parallel LZ77 + fixed-Huffman codes (BTYPE=1).  Every lane hashes the 4 bytes at
+//            its own position (12-bit hash, 16-bit positions in shared memory), verifies and
+//            extends its candidate (plus the distance-1 candidate, which catches the runs that
+//            dominate quality strings), a greedy in-order selection keeps non-overlapping
+//            matches (ballot + ffs skip over literal stretches), tokens go to a per-warp list;
+//            a second pass turns 32 tokens at a time into <= 31-bit codes, prefix-sums their
+//            bit lengths and ORs them into the output words.  Falls back to a stored block when
+//            that would be smaller (zlib arm does the same, bgzf.c:653-667).
+// =============================================================================================
+constexpr uint32_t DEFL_HASH_BITS = 12;
+constexpr uint32_t DEFL_MAX_IN = 0xff00 + 256;      // htslib never exceeds 0xff00; allow the full 64 KiB - 280
+constexpr uint32_t DEFL_TOK_CAP = 65536;
+
+struct DeflateSmem {
+    uint16_t htab[1u << DEFL_HASH_BITS];
+};
+
+__device__ __forceinline__ uint32_t fixed_lit_code(uint32_t sym, uint32_t &nbits)
+{
+    // RFC 1951 3.2.6, codes are sent MSB first -> bit-reverse for the LSB-first stream
+    uint32_t code;
+    if (sym < 144) { code = 0x30 + sym; nbits = 8; }
+    else if (sym < 256) { code = 0x190 + (sym - 144); nbits = 9; }
+    else if (sym < 280) { code = sym - 256; nbits = 7; }
+    else { code = 0xc0 + (sym - 280); nbits = 8; }
+    return __brev(code) >> (32 - nbits);
+}
+
+// token -> (bits, nbits), fixed Huffman
+__device__ __forceinline__ uint32_t token_bits(uint32_t tok, uint32_t &nbits)
+{
+    if (!(tok >> 31)) return fixed_lit_code(tok & 0xff, nbits);
+    uint32_t len = (tok & 0xff) + 3, dist = ((tok >> 8) & 0x7fff) + 1;
+    // length symbol
+    uint32_t ls = 28;
+    while (ls > 0 && c_len_base[ls] > len) ls--;
+    uint32_t lx = c_len_xtra[ls], n1;
+    uint32_t bits = fixed_lit_code(257 + ls, n1);
+    bits |= (len - c_len_base[ls]) << n1; n1 += lx;
+    // distance symbol: 5-bit fixed code, MSB first
+    uint32_t ds = 29;
+    while (ds > 0 && c_dst_base[ds] > dist) ds--;
+    uint32_t dx = c_dst_xtra[ds];
+    bits |= (__brev(ds) >> 27) << n1; n1 += 5;
+    bits |= (dist - c_dst_base[ds]) << n1; n1 += dx;
+    nbits = n1;
+    return bits;
+}
+
+__device__ __forceinline__ uint32_t ld4(const uint8_t *p) { return p[0] | (uint32_t)p[1] << 8 | (uint32_t)p[2] << 16 | (uint32_t)p[3] << 24; }
+
+// Returns the BGZF block length written to out (<= 65536), 0 on failure.
+__device__ uint32_t deflate_block_warp(DeflateSmem &s, const uint32_t (*crc_tab)[256], const uint8_t *in, uint32_t n,
+                                       int level, uint8_t *out, uint32_t *toks)
+{
+    const uint32_t lane = hgpu_lane();
+    if (n > 65280u) return 0;
+    const uint32_t crc = warp_crc32(crc_tab, in, n);
+    uint32_t dlen = 0;                                   // deflate payload bytes
+    bool stored = level == 0 || n < 16;
+    if (!stored) {
+        // ---- pass 1: LZ77 tokens ----
+        __syncwarp();
+        for (uint32_t i = lane; i < (1u << DEFL_HASH_BITS); i += 32) s.htab[i] = 0;
+        __syncwarp();
+        uint32_t ntok = 0, covered = 0;
+        for (uint32_t base = 0; base < n; base += 32) {
+            const uint32_t p = base + lane;
+            uint32_t mlen = 0, mdist = 0;
+            const bool can = p + 4 <= n;
+            uint32_t cand = 0, h = 0;
+            if (can) { h = (ld4(in + p) * 2654435761u) >> (32 - DEFL_HASH_BITS); cand = s.htab[h]; }
+            __syncwarp();
+            if (can) s.htab[h] = (uint16_t)(p + 1);
+            __syncwarp();
+            if (can && p >= covered) {
+                const uint32_t maxl = n - p < 258u ? n - p : 258u;
+                // candidate from the hash table
+                if (cand && p + 1 - cand <= 32768u) {
+                    const uint8_t *a = in + (cand - 1), *b = in + p;
+                    uint32_t l = 0;
+                    while (l < maxl && a[l] == b[l]) l++;
+                    if (l >= 4) { mlen = l; mdist = p + 1 - cand; }
+                }
+                // distance-1 candidate (runs)
+                if (p >= 1) {
+                    const uint8_t *b = in + p, *a1 = in + p - 1;
+                    uint32_t l = 0;
+                    while (l < maxl && a1[l] == b[l]) l++;
+                    if (l >= 3 && l > mlen) { mlen = l; mdist = 1; }
+                }
+            }
+            // greedy in-order selection inside the chunk
+            uint32_t cur = covered > base ? covered : base;
+            const uint32_t cend = base + 32 < n ? base + 32 : n;
+            uint32_t has = __ballot_sync(0xffffffffu, mlen != 0);
+            while (cur < cend) {
+                uint32_t rel = cur - base;
+                uint32_t later = has & ~((1u << rel) - 1u);
+                uint32_t nm = later ? (uint32_t)(__ffs(later) - 1) : 32u;       // first match at/after cur
+                uint32_t lit_end = base + nm < cend ? base + nm : cend;
+                // literals [cur, lit_end)
+                uint32_t nl = lit_end - cur;
+                if (nl) {
+                    if (p >= cur && p < lit_end && ntok + (p - cur) < DEFL_TOK_CAP) toks[ntok + (p - cur)] = in[p];
+                    ntok += nl;
+                    cur = lit_end;
+                }
+                if (nm < 32 && base + nm < cend) {
+                    uint32_t ml = __shfl_sync(0xffffffffu, mlen, nm), md = __shfl_sync(0xffffffffu, mdist, nm);
+                    if (lane == 0 && ntok < DEFL_TOK_CAP) toks[ntok] = 0x80000000u | (ml - 3) | ((md - 1) << 8);
+                    ntok++;
+                    cur = base + nm + ml;
+                }
+            }
+            covered = cur;
+        }
+        __syncwarp();
+        __threadfence_block();
+        // ---- pass 2: bits ----
+        // zero the slot's deflate area first (bits are ORed in)
+        uint32_t *ow = reinterpret_cast<uint32_t *>(out);          // out slots are 64 KiB aligned by contract (>= 4)
+        for (uint32_t i = lane; i < 65536 / 4; i += 32) ow[i] = 0;
+        __syncwarp();
+        __threadfence_block();
+        uint64_t bitpos = 18 * 8;
+        if (lane == 0) atomicOr(&ow[bitpos >> 5], 3u << (bitpos & 31));     // BFINAL=1, BTYPE=01
+        bitpos += 3;
+        bool overflow = ntok > DEFL_TOK_CAP;
+        const uint64_t limit = (uint64_t)(65536 - 8 - 4) * 8;       // keep room for EOB + footer
+        for (uint32_t t0 = 0; t0 < ntok && !overflow; t0 += 32) {
+            uint32_t t = t0 + lane, nb = 0, bits = 0;
+            if (t < ntok) bits = token_bits(toks[t], nb);
+            uint32_t inc = nb;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) { uint32_t v = __shfl_up_sync(0xffffffffu, inc, d); if (lane >= (uint32_t)d) inc += v; }
+            uint32_t tot = __shfl_sync(0xffffffffu, inc, 31);
+            if (bitpos + tot > limit) { overflow = true; break; }
+            if (nb) {
+                uint64_t bp = bitpos + inc - nb;
+                uint32_t w = (uint32_t)(bp >> 5), sh = (uint32_t)(bp & 31);
+                atomicOr(&ow[w], bits << sh);
+                if (sh + nb > 32) atomicOr(&ow[w + 1], bits >> (32 - sh));
+            }
+            bitpos += tot;
+        }
+        if (!overflow) {
+            bitpos += 7;                                            // end-of-block: seven zero bits
+            dlen = (uint32_t)((bitpos + 7) / 8) - 18;
+            if (dlen >= n + 5) overflow = true;                    // stored would be smaller
+        }
+        __syncwarp();
+        __threadfence_block();
+        stored = overflow;
+    }
+    if (stored) {
+        dlen = n + 5;
+        __syncwarp();
+        if (lane == 0) {
+            out[18] = 1;                                            // BFINAL=1, BTYPE=00
+            out[19] = (uint8_t)n; out[20] = (uint8_t)(n >> 8);
+            out[21] = (uint8_t)~n; out[22] = (uint8_t)(~n >> 8);
+        }
+        for (uint32_t i = lane; i < n; i += 32) out[23 + i] = in[i];
+    }
+    const uint32_t total = 18 + dlen + 8;
+    __syncwarp();
+    if (lane == 0) {
+        const uint8_t hdr[16] = {0x1f, 0x8b, 8, 4, 0, 0, 0, 0, 0, 0xff, 6, 0, 'B', 'C', 2, 0};
+        for (int i = 0; i < 16; i++) out[i] = hdr[i];
+        out[16] = (uint8_t)(total - 1); out[17] = (uint8_t)((total - 1) >> 8);
+        uint8_t *f = out + 18 + dlen;
+        f[0] = (uint8_t)crc; f[1] = (uint8_t)(crc >> 8); f[2] = (uint8_t)(crc >> 16); f[3] = (uint8_t)(crc >> 24);
+        f[4] = (uint8_t)n; f[5] = (uint8_t)(n >> 8); f[6] = 0; f[7] = 0;
+    }
+    __syncwarp();
+    return total;
+}
+
+__global__ void __launch_bounds__(128)
+bgzf_deflate_kernel(const uint8_t *__restrict__ in, const uint64_t *__restrict__ in_off,
+                    const uint32_t *__restrict__ in_len, uint32_t n, int level, uint8_t *out,
+                    const uint64_t *__restrict__ out_off, uint32_t *out_len, int32_t *status,
+                    uint32_t *toks_all, uint32_t *counter)
+{
+    __shared__ DeflateSmem smem_all[4];
+    __shared__ uint32_t crc_tab[4][256];
+    for (int i = threadIdx.x; i < 1024; i += blockDim.x) (&crc_tab[0][0])[i] = (&g_crc_tab[0][0])[i];
+    __syncthreads();
+    const uint32_t w = threadIdx.x >> 5;
+    uint32_t *toks = toks_all + ((size_t)blockIdx.x * 4 + w) * DEFL_TOK_CAP;
+    for (;;) {
+        uint32_t job = 0;
+        if (hgpu_lane() == 0) job = atomicAdd(counter, 1u);
+        job = __shfl_sync(0xffffffffu, job, 0);
+        if (job >= n) break;
+        uint32_t got = deflate_block_warp(smem_all[w], crc_tab, in + in_off[job], in_len[job], level, out + out_off[job], toks);
+        __syncwarp();
+        if (hgpu_lane() == 0) { out_len[job] = got; status[job] = got ? HGPU_OK : HGPU_BGZF_ERR_ZLIB; }
+    }
+}
+
 } // namespace
 
 int hgpu_launch_bgzf_inflate(hgpu_ctx *ctx, const uint8_t *d_in, const uint64_t *d_in_off,
@@ -922,4 +1133,30 @@ int hgpu_launch_crc32(hgpu_ctx *ctx, const uint8_t *d_buf, size_t len, uint32_t 
     crc32_chunks_kernel<<<(unsigned)nchunk, 32, 0, st>>>(d_buf, len, chunk, d_partial);
     hgpu_count_launch();
     return hgpu_check(cudaGetLastError(), "crc launch");
+}
+
+// Batch BGZF compress, device pointers.  Every out slot must be 65536 bytes and 4-byte aligned.
+extern "C" int hgpu_bgzf_compress_batch_dev(hgpu_ctx *ctx, const uint8_t *d_in, const uint64_t *d_in_off,
+        const uint32_t *d_in_len, uint32_t n, int level, uint8_t *d_out, const uint64_t *d_out_off,
+        uint32_t *d_out_len, int32_t *d_status, void *stream)
+{
+    if (!ctx) { hgpu_set_error("null context"); return HGPU_ERR_ARG; }
+    if (n == 0) return HGPU_OK;
+    cudaStream_t st = stream ? (cudaStream_t)stream : ctx->stream;
+    int rc = ensure_crc_tables(ctx, st);
+    if (rc) return rc;
+    int per_sm = 0;
+    if (hgpu_check(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, bgzf_deflate_kernel, 128, 0), "deflate occupancy"))
+        return HGPU_ERR_CUDA;
+    if (per_sm < 1) per_sm = 1;
+    uint32_t full = (uint32_t)ctx->sm_count * (uint32_t)per_sm, grid = full;
+    if (grid > (n + 3) / 4) grid = (n + 3) / 4;
+    rc = hgpu_ensure_mrec(ctx, (size_t)full * 4 * DEFL_TOK_CAP * sizeof(uint32_t));
+    if (rc) return rc;
+    uint32_t *counter = hgpu_take_counter(ctx, st);
+    if (!counter) return HGPU_ERR_CUDA;
+    bgzf_deflate_kernel<<<grid, 128, 0, st>>>(d_in, d_in_off, d_in_len, n, level, d_out, d_out_off, d_out_len, d_status,
+                                              reinterpret_cast<uint32_t *>(ctx->d_mrec), counter);
+    hgpu_count_launch();
+    return hgpu_check(cudaGetLastError(), "deflate launch");
 }

@@ -441,3 +441,46 @@ extern "C" uint32_t hts_crc32(uint32_t crc, const void *buf, size_t len)
     if (!ctx) { fprintf(stderr, "htsgpu: hts_crc32 without a CUDA device: %s\n", hgpu_last_error()); abort(); }
     return hgpu_crc32(ctx, crc, buf, len);
 }
+
+extern "C" int hgpu_bgzf_compress_batch_dev(hgpu_ctx *ctx, const uint8_t *d_in, const uint64_t *d_in_off,
+        const uint32_t *d_in_len, uint32_t n, int level, uint8_t *d_out, const uint64_t *d_out_off,
+        uint32_t *d_out_len, int32_t *d_status, void *stream);
+
+// bgzf_compress (bgzf.c:624-683): one block, host pointers
+extern "C" int bgzf_compress(void *dst, size_t *dlen, const void *src, size_t slen, int level)
+{
+    static const uint8_t eof_block[28] = {0x1f, 0x8b, 8, 4, 0, 0, 0, 0, 0, 0xff, 6, 0, 'B', 'C', 2, 0, 0x1b, 0, 3, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+    if (!dst || !dlen || (slen && !src)) return -1;
+    if (slen == 0) {                                  // bgzf.c:566: the EOF marker
+        if (*dlen < 28) return -1;
+        memcpy(dst, eof_block, 28);
+        *dlen = 28;
+        return 0;
+    }
+    if (slen > 65280) return -1;
+    std::lock_guard<std::mutex> lock(g_shim_mu);
+    hgpu_ctx *ctx = shim_ctx();
+    if (!ctx) return -1;
+    if (cudaSetDevice(ctx->device) != cudaSuccess) return -1;
+    size_t in_bytes = (slen + 4 + 255) & ~(size_t)255;
+    if (hgpu_ensure_stage(ctx, in_bytes + 65536 + 256)) return -1;
+    uint8_t *d_in = ctx->d_stage, *d_out = d_in + in_bytes;
+    uint64_t *d_off = (uint64_t *)(d_out + 65536);      // {in_off, out_off}
+    uint32_t *d_len = (uint32_t *)(d_off + 2), *d_ol = d_len + 1;
+    int32_t *d_st = (int32_t *)(d_ol + 1);
+    uint64_t offs[2] = {0, 0};
+    uint32_t len32 = (uint32_t)slen, got = 0;
+    int32_t st = 0;
+    cudaStream_t s = ctx->stream;
+    if (cudaMemcpyAsync(d_in, src, slen, cudaMemcpyHostToDevice, s) != cudaSuccess) return -1;
+    if (cudaMemcpyAsync(d_off, offs, 16, cudaMemcpyHostToDevice, s) != cudaSuccess) return -1;
+    if (cudaMemcpyAsync(d_len, &len32, 4, cudaMemcpyHostToDevice, s) != cudaSuccess) return -1;
+    if (hgpu_bgzf_compress_batch_dev(ctx, d_in, d_off, d_len, 1, level < 0 ? 6 : level, d_out, d_off + 1, d_ol, d_st, s)) return -1;
+    if (cudaMemcpyAsync(&got, d_ol, 4, cudaMemcpyDeviceToHost, s) != cudaSuccess) return -1;
+    if (cudaMemcpyAsync(&st, d_st, 4, cudaMemcpyDeviceToHost, s) != cudaSuccess) return -1;
+    if (cudaStreamSynchronize(s) != cudaSuccess) return -1;
+    if (st != HGPU_OK || got == 0 || got > *dlen) return -1;
+    if (cudaMemcpy(dst, d_out, got, cudaMemcpyDeviceToHost) != cudaSuccess) return -1;
+    *dlen = got;
+    return 0;
+}

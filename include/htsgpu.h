@@ -70,6 +70,16 @@ int hgpu_bgzf_inflate_blocks_host(hgpu_ctx *ctx,
         uint8_t *out, const uint64_t *out_off, const uint32_t *out_cap,
         uint32_t *out_len, int32_t *status);
 
+/* BGZF COMPRESS — replaces bgzf_compress / deflate_block as run per job by bgzf_encode_func
+ * (bgzf.c:624-683, :709, :1330) for a batch of payloads (each <= 65280 bytes; htslib uses
+ * BGZF_BLOCK_SIZE 0xff00), one warp per payload.  Every out slot is 65536 bytes, 4-byte aligned;
+ * out_len[i] receives the BGZF block length.  level 0 = stored block (bgzf.c:573-580), level >= 1 =
+ * LZ77 + fixed-Huffman DEFLATE with stored fallback.  Output inflates to the input with any
+ * RFC 1951 inflater; bytes differ from zlib's (stated ratio in tests/test_gpu_bgzf_compress.py). */
+int hgpu_bgzf_compress_batch_dev(hgpu_ctx *ctx,
+        const uint8_t *d_in, const uint64_t *d_in_off, const uint32_t *d_in_len, uint32_t n, int level,
+        uint8_t *d_out, const uint64_t *d_out_off, uint32_t *d_out_len, int32_t *d_status, void *stream);
+
 /* Multi-GPU sharding rule: rank r of `world` owns the contiguous unit range
  * [first, first+count) and, if unit_out_len is given, writes at byte out_base of the global
  * decompressed stream.  Blocks / slices are independent (bgzf.c:775, cram_decode.c:2140), so there
@@ -181,6 +191,16 @@ int hgpu_bam_unpack_dev(hgpu_ctx *ctx, const uint8_t *d_stream, uint64_t len,
                         uint8_t *d_seq, uint8_t *d_qual, const uint64_t *d_seq_off,
                         int32_t *d_status, void *stream);
 
+/* BAM record PACK — the data movement of bam_write1 (sam.c:862-928): core[i] + data -> BAM bytes
+ * (block_size, 32-byte LE core, qname without its padding NULs, the rest verbatim).  Two calls:
+ * with d_out == NULL it fills d_out_off[0..n] (exclusive prefix sums of the record sizes; the total
+ * is the last entry), with d_out it writes the records.  status[i]: 0; -1 for bam_write1's error
+ * conditions (:867-877); 1 when n_cigar > 65535 (CG-tag rewrite :899-925 left to the host; the
+ * record gets zero bytes). */
+int hgpu_bam_pack_dev(hgpu_ctx *ctx, const hgpu_bam1_core *d_core, const uint8_t *d_data,
+                      const uint64_t *d_data_off, uint64_t n, uint8_t *d_out, uint64_t *d_out_off,
+                      int32_t *d_status, void *stream);
+
 /* Sizes pass for step 2: fills d_data_off[0..n] and d_seq_off[0..n] (exclusive prefix sums of
  * l_data and l_qseq) so the caller can allocate; totals are the last entries. */
 int hgpu_bam_layout_dev(hgpu_ctx *ctx, const uint8_t *d_stream, uint64_t len,
@@ -198,6 +218,10 @@ unsigned char *rans_uncompress_to_4x16(unsigned char *in, unsigned int in_size,
 unsigned char *rans_uncompress_4x16(unsigned char *in, unsigned int in_size, unsigned int *out_size);
 /* hts_crc32 (htslib.map:657) */
 uint32_t hts_crc32(uint32_t crc, const void *buf, size_t len);
+/* bgzf_compress (htslib/bgzf.h:392, htslib.map:312): one BGZF block from slen <= 65280 bytes;
+ * *dlen is capacity in / block length out; slen == 0 writes the 28-byte EOF block (bgzf.c:566);
+ * returns 0 or -1.  Host pointers. */
+int bgzf_compress(void *dst, size_t *dlen, const void *src, size_t slen, int level);
 
 #ifdef __cplusplus
 }

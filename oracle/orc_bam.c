@@ -148,3 +148,26 @@ int orc_bam_unpack1(const uint8_t *rec, orc_bam1_core *c, uint8_t *data, uint8_t
     }
     return status;
 }
+
+/*
+ * bam_write1 (sam.c:862-928) for one record: core + data -> BAM bytes (block_size included).
+ * Returns bytes written; -1 for the reference's error conditions (qname > 254 chars, positions
+ * beyond INT_MAX); -2 when n_cigar > 0xffff (the CG-tag rewrite, :899-925, is left to the host).
+ */
+long orc_bam_pack1(const orc_bam1_core *c, const uint8_t *data, uint32_t l_data, uint8_t *out)
+{
+    uint32_t x[8], block_len = l_data - c->l_extranul + 32, qn = c->l_qname - c->l_extranul;
+    int i;
+    if (qn > 255) return -1;
+    if (c->n_cigar > 0xffff) return -2;
+    if (c->pos > 0x7fffffffLL || c->mpos > 0x7fffffffLL || c->isize < -0x80000000LL || c->isize > 0x7fffffffLL) return -1;
+    x[0] = (uint32_t)c->tid; x[1] = (uint32_t)c->pos;
+    x[2] = (uint32_t)c->bin << 16 | (uint32_t)c->qual << 8 | qn;
+    x[3] = (uint32_t)c->flag << 16 | (c->n_cigar & 0xffff);
+    x[4] = (uint32_t)c->l_qseq; x[5] = (uint32_t)c->mtid; x[6] = (uint32_t)c->mpos; x[7] = (uint32_t)c->isize;
+    out[0] = block_len; out[1] = block_len >> 8; out[2] = block_len >> 16; out[3] = block_len >> 24;
+    for (i = 0; i < 8; i++) { out[4 + 4 * i] = x[i]; out[5 + 4 * i] = x[i] >> 8; out[6 + 4 * i] = x[i] >> 16; out[7 + 4 * i] = x[i] >> 24; }
+    memcpy(out + 36, data, qn);
+    memcpy(out + 36 + qn, data + c->l_qname, l_data - c->l_qname);
+    return 4 + (long)block_len;
+}
