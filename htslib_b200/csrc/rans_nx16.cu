@@ -851,6 +851,182 @@ rans_nx16_decode_kernel(const uint8_t *__restrict__ in, const uint64_t *__restri
     }
 }
 
+
+// =============================================================================================
+// rANS 4x8 (CRAM 3.0 block method 4, "RANS") — replaces rans_uncompress / rans_uncompress_O0/_O1
+// (htscodecs rANS_static.c:840-850, :221-384, :599-827).  One warp per stream, the four states on
+// lanes 0-3; renormalisation is byte-wise (L = 2^23, 0-2 bytes per state and step, taken in state
+// order: lane z starts at the prefix sum of the lower lanes' byte counts, rANS_byte.h:512-554).
+// Tables live in the per-CTA global scratch (a 3.0-era format: correctness first).
+// =============================================================================================
+constexpr uint32_t L8 = 1u << 23;
+
+__device__ __forceinline__ void renorm8(uint32_t &R, bool active, const uint8_t *in, uint32_t &ipos, uint32_t in_len)
+{
+    const uint32_t lane = hgpu_lane();
+    uint32_t c = !active || R >= L8 ? 0u : (R < (1u << 15) ? 2u : 1u);
+    uint32_t b1 = __ballot_sync(0xffffffffu, c >= 1), b2 = __ballot_sync(0xffffffffu, c == 2);
+    if (!b1) return;
+    uint32_t lt = hgpu_lanemask_lt();
+    uint32_t off = __popc(b1 & lt) + __popc(b2 & lt), tot = __popc(b1) + __popc(b2);
+    uint32_t avail = in_len - ipos;                                  // ipos <= in_len always
+    uint32_t start = off < avail ? off : avail;
+    uint32_t n = c < avail - start ? c : avail - start;
+    if (n >= 1) R = (R << 8) | in[ipos + start];
+    if (n == 2) R = (R << 8) | in[ipos + start + 1];
+    ipos += tot < avail ? tot : avail;
+    (void)lane;
+}
+
+// returns 0 ok / -1 error; out_size = decoded length
+__device__ int dec_4x8(uint8_t *gtab, const uint8_t *in, uint32_t in_size, uint8_t *out, uint32_t out_cap, uint32_t &out_size)
+{
+    const uint32_t lane = hgpu_lane();
+    if (in_size < 26) return -1;
+    const uint32_t order = in[0];
+    if (order > 1) return -1;
+    const uint32_t in_sz = in[1] | in[2] << 8 | in[3] << 16 | (uint32_t)in[4] << 24;
+    const uint32_t out_sz = in[5] | in[6] << 8 | in[7] << 16 | (uint32_t)in[8] << 24;
+    if (in_sz != in_size - 9 || out_sz > out_cap) return -1;
+    if (order && in_size < 27) return -1;
+    uint8_t *lut = gtab;                                             // [rows][4096]
+    uint32_t *fs = reinterpret_cast<uint32_t *>(gtab + 256u * 4096u); // [rows][256]  f | start<<16
+    const uint8_t *cp = in + 9, *end = in + in_size;
+    uint32_t R = L8;
+    if (!order) {
+        int j = *cp++, rle = 0;
+        uint32_t x = 0, lastF = 0, lastj = 0;
+        do {
+            if (cp > end - 16) return -1;
+            uint32_t F = *cp++;
+            if (F >= 128) F = ((F & 127) << 8) | *cp++;
+            if (x + F > 4096) return -1;
+            for (uint32_t y = lane; y < F; y += 32) lut[x + y] = (uint8_t)j;
+            if (lane == 0) fs[j] = F | (x << 16);
+            lastF = F; lastj = (uint32_t)j;
+            x += F;
+            if (!rle && j + 1 == *cp) { j = *cp++; rle = *cp++; }
+            else if (rle) { rle--; if (++j > 255) return -1; }
+            else j = *cp++;
+        } while (j);
+        if (x < 4095 || x > 4096) return -1;
+        // slot 4095 of a 4095-sum table repeats the last symbol with bias+1 (:299-305): give that
+        // symbol one more slot by widening its frequency entry
+        if (x != 4096 && lane == 0) lut[4095] = (uint8_t)lastj;      // bias = m - start comes out as sbase[4094]+1
+        (void)lastF;
+        const bool short_tab = x != 4096;
+        if (cp > end - 16) return -1;
+        if (lane < 4) { const uint8_t *q = cp + 4 * lane; R = q[0] | q[1] << 8 | q[2] << 16 | (uint32_t)q[3] << 24; }
+        if (__any_sync(0xffffffffu, R < L8)) return -1;
+        uint32_t ipos = (uint32_t)(cp - in) + 16;
+        __syncwarp();
+        __threadfence_block();
+        const bool mine = lane < 4;
+        uint32_t i = 0;
+        for (; i + 4 <= out_sz; i += 4) {
+            uint32_t m = R & 4095u, sym = lut[m], e = fs[sym];
+            if (mine) {
+                uint32_t f = e & 0xffffu, st = e >> 16;
+                // reference: sfreq[m]*(R>>12) + sbase[m]; for the patched slot sbase = last bias + 1 = m - start
+                (void)short_tab;
+                R = f * (R >> 12) + m - st;
+                out[i + lane] = (uint8_t)sym;
+            }
+            renorm8(R, mine, in, ipos, in_size);
+        }
+        if (mine && i + lane < out_sz) out[i + lane] = lut[R & 4095u];
+    } else {
+        // context rows are numbered in order of first appearance as context or symbol (:636-652)
+        uint16_t *map = reinterpret_cast<uint16_t *>(gtab + 256u * 4096u + 256u * 256u * 4u);   // 512 bytes after the tables
+        __syncwarp();
+        for (uint32_t k = lane; k < 256; k += 32) map[k] = 0xffff;
+        for (uint32_t k = lane; k < 256u * 256u; k += 32) fs[k] = 0;
+        __syncwarp();
+        __threadfence_block();
+        uint32_t mi = 0;
+        int ci = *cp++, rle_i = 0;
+        do {
+            if (map[ci] == 0xffff) { __syncwarp(); if (lane == 0) map[ci] = (uint16_t)mi; mi++; __syncwarp(); __threadfence_block(); }
+            const uint32_t row = map[ci];
+            uint32_t x = 0;
+            int j = *cp++, rle_j = 0;
+            do {
+                if (map[j] == 0xffff) { __syncwarp(); if (lane == 0) map[j] = (uint16_t)mi; mi++; __syncwarp(); __threadfence_block(); }
+                if (cp > end - 16) return -1;
+                uint32_t F = *cp++;
+                if (F >= 128) F = ((F & 127) << 8) | *cp++;
+                if (!F) F = 4096;
+                if (x + F > 4096) return -1;
+                for (uint32_t y = lane; y < F; y += 32) lut[row * 4096u + x + y] = (uint8_t)j;
+                if (lane == 0) fs[row * 256u + j] = (F & 0xffffu) | (x << 16);
+                x += F;
+                if (!rle_j && j + 1 == *cp) { j = *cp++; rle_j = *cp++; }
+                else if (rle_j) { rle_j--; if (++j > 255) return -1; }
+                else j = *cp++;
+            } while (j);
+            if (x < 4095 || x > 4096) return -1;
+            if (x != 4096 && lane == 0) lut[row * 4096u + 4095u] = 0;   // calloc'd slot in the reference
+            if (!rle_i && ci + 1 == *cp) { ci = *cp++; rle_i = *cp++; }
+            else if (rle_i) { rle_i--; if (++ci > 255) return -1; }
+            else ci = *cp++;
+        } while (ci);
+        __syncwarp();
+        __threadfence_block();
+        if (cp > end - 16) return -1;
+        if (lane < 4) { const uint8_t *q = cp + 4 * lane; R = q[0] | q[1] << 8 | q[2] << 16 | (uint32_t)q[3] << 24; }
+        if (__any_sync(0xffffffffu, R < L8)) return -1;
+        uint32_t ipos = (uint32_t)(cp - in) + 16;
+        const bool mine = lane < 4;
+        const uint32_t q4 = out_sz >> 2;
+        uint32_t l = map[0] == 0xffff ? 0u : map[0];
+        uint8_t *op = out + (size_t)(mine ? lane : 0) * q4;
+        for (uint32_t i = 0; i < q4; i++) {
+            uint32_t m = R & 4095u, c = lut[l * 4096u + m], e = fs[l * 256u + c];
+            if (mine) {
+                uint32_t f = e & 0xffffu;
+                R = f * (R >> 12) + m - (e >> 16);
+                op[i] = (uint8_t)c;
+            }
+            renorm8(R, mine, in, ipos, in_size);
+            uint16_t ml = map[c];
+            if (mine) l = ml == 0xffff ? 0u : ml;
+        }
+        const bool last = lane == 3;
+        for (uint32_t p = 4 * q4; p < out_sz; p++) {
+            uint32_t m = R & 4095u, c = lut[l * 4096u + m], e = fs[l * 256u + c];
+            if (last) {
+                uint32_t f = e & 0xffffu;
+                R = f * (R >> 12) + m - (e >> 16);
+                out[p] = (uint8_t)c;
+            }
+            renorm8(R, last, in, ipos, in_size);
+            uint16_t ml = map[c];
+            if (last) l = ml == 0xffff ? 0u : ml;
+        }
+    }
+    out_size = out_sz;
+    return 0;
+}
+
+__global__ void __launch_bounds__(32)
+rans_4x8_decode_kernel(const uint8_t *__restrict__ in, const uint64_t *__restrict__ in_off,
+                       const uint32_t *__restrict__ in_len, uint32_t n, uint8_t *out,
+                       const uint64_t *__restrict__ out_off, const uint32_t *__restrict__ out_len,
+                       uint32_t *got_len, int32_t *status, uint8_t *scratch, size_t per_cta, uint32_t *counter)
+{
+    uint8_t *gtab = scratch + (size_t)blockIdx.x * per_cta;
+    for (;;) {
+        uint32_t job = 0;
+        if (hgpu_lane() == 0) job = atomicAdd(counter, 1u);
+        job = __shfl_sync(0xffffffffu, job, 0);
+        if (job >= n) break;
+        uint32_t got = 0;
+        int rc = dec_4x8(gtab, in + in_off[job], in_len[job], out + out_off[job], out_len[job], got);
+        __syncwarp();
+        if (hgpu_lane() == 0) { status[job] = rc ? HGPU_RANS_ERR : HGPU_OK; got_len[job] = rc ? 0 : got; }
+    }
+}
+
 } // namespace
 
 // streams the fast pass keeps resident at once (persistent grid size): callers that can choose
@@ -912,4 +1088,25 @@ int hgpu_launch_rans_nx16(hgpu_ctx *ctx, const uint8_t *d_in, const uint64_t *d_
                                                          max_out_len, smem_tab1, c1);
     hgpu_count_launch(2);
     return hgpu_check(cudaGetLastError(), "rans launch");
+}
+
+// rANS 4x8 batch decode, device pointers (CRAM 3.0 method 4; cram_io.c:1666-1682)
+extern "C" int hgpu_rans4x8_decode_batch_dev(hgpu_ctx *ctx, const uint8_t *d_in, const uint64_t *d_in_off,
+        const uint32_t *d_in_len, uint32_t n, uint8_t *d_out, const uint64_t *d_out_off, const uint32_t *d_out_len,
+        uint32_t *d_got_len, int32_t *d_status, void *stream)
+{
+    if (!ctx) { hgpu_set_error("null context"); return HGPU_ERR_ARG; }
+    if (n == 0) return HGPU_OK;
+    cudaStream_t st = stream ? (cudaStream_t)stream : ctx->stream;
+    uint32_t grid = (uint32_t)ctx->sm_count * 16u;
+    if (grid > n) grid = n;
+    size_t per_cta = (GTAB_BYTES + 1024 + 255) & ~(size_t)255;
+    int rc = hgpu_ensure_scratch(ctx, per_cta * grid);
+    if (rc) return rc;
+    uint32_t *counter = hgpu_take_counter(ctx, st);
+    if (!counter) return HGPU_ERR_CUDA;
+    rans_4x8_decode_kernel<<<grid, 32, 0, st>>>(d_in, d_in_off, d_in_len, n, d_out, d_out_off, d_out_len, d_got_len,
+                                                d_status, ctx->d_scratch, per_cta, counter);
+    hgpu_count_launch();
+    return hgpu_check(cudaGetLastError(), "rans4x8 launch");
 }

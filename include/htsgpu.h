@@ -128,6 +128,14 @@ int hgpu_rans_nx16_decode_batch_host(hgpu_ctx *ctx,
         uint8_t *out, const uint64_t *out_off, const uint32_t *out_len,
         uint32_t *got_len, int32_t *status);
 
+/* rANS 4x8 (CRAM 3.0 block method 4, "RANS") — replaces rans_uncompress (rANS_static.c:840-850) as
+ * called from cram_uncompress_block (cram_io.c:1666-1682) for a batch of streams.  The 9-byte stream
+ * header carries both sizes; out_len[i] is the slot capacity. */
+int hgpu_rans4x8_decode_batch_dev(hgpu_ctx *ctx,
+        const uint8_t *d_in, const uint64_t *d_in_off, const uint32_t *d_in_len, uint32_t n,
+        uint8_t *d_out, const uint64_t *d_out_off, const uint32_t *d_out_len,
+        uint32_t *d_got_len, int32_t *d_status, void *stream);
+
 /* CRAM 3.x framing on the host: walks containers and blocks (cram_read_container
  * cram/cram_io.c:3760, cram_read_block :1414-1483) of a file image and lists every block so the
  * payloads of all entropy-coded blocks can go to the batch decoders in one launch.  method: 0 RAW,

@@ -275,3 +275,28 @@ def orc_bam_unpack_all(stream):
         st = o.orc_bam_unpack1(p, C.byref(core), data, seq, qual)
         res.append((st, core.astuple(), bytes(data[: ld.value]), bytes(seq[: lq.value]), bytes(qual[: lq.value])))
     return res, [offs[i] for i in range(n)]
+
+
+def orc_rans_4x8_decode(data, cap):
+    o = orc()
+    out = (C.c_uint8 * max(1, cap))()
+    n = C.c_uint32(cap)
+    rc = o.orc_rans_4x8_decode(buf(data), C.c_uint32(len(data)), out, C.byref(n))
+    return None if rc else bytes(out[: n.value])
+
+
+def ref_rans_4x8(data=None, order=None, comp=None):
+    """reference rans_compress / rans_uncompress (rANS_static.c:829-850)."""
+    r = ref()
+    r.rans_compress.restype = C.c_void_p; r.rans_uncompress.restype = C.c_void_p
+    libc = C.CDLL(None); libc.free.argtypes = [C.c_void_p]
+    n = C.c_uint(0)
+    if comp is None:
+        p = r.rans_compress(buf(data), C.c_uint(len(data)), C.byref(n), C.c_int(order))
+    else:
+        p = r.rans_uncompress(buf(comp), C.c_uint(len(comp)), C.byref(n))
+    if not p:
+        return None
+    res = C.string_at(p, n.value)
+    libc.free(p)
+    return res
