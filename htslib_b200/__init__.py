@@ -51,6 +51,7 @@ def lib():
     L.hgpu_rans_nx16_decode_batch_dev.argtypes = [vp, vp, vp, vp, u32, vp, vp, vp, vp, vp, u32, vp]
     L.hgpu_rans_nx16_decode_batch_host.argtypes = [vp, vp, vp, vp, u32, vp, vp, vp, vp, vp]
     L.hgpu_rans4x8_decode_batch_dev.argtypes = [vp, vp, vp, vp, u32, vp, vp, vp, vp, vp, vp]
+    L.hgpu_arith_decode_batch_dev.argtypes = [vp, vp, vp, vp, u32, vp, vp, vp, vp, vp, u32, vp]
     L.hgpu_rans_nx16_wave_size.restype = u32
     L.hgpu_rans_nx16_wave_size.argtypes = [vp]
     L.hgpu_rans_nx16_compress_bound.restype = u32
@@ -112,6 +113,36 @@ class Context:
                                                     d_out.data_ptr(), d_out_off.data_ptr(), d_out_len.data_ptr(),
                                                     d_got.data_ptr(), d_status.data_ptr(), int(max_out_len), stream),
               "rans_nx16_decode_batch_dev")
+
+    def arith_decode(self, comps, caps, stream=0):
+        """Decode a list of arith_dynamic streams on the device; returns list of (status, bytes)."""
+        return self._decode_list(lib().hgpu_arith_decode_batch_dev, comps, caps, stream, True)
+
+    def _decode_list(self, fn, comps, caps, stream, with_max):
+        import numpy as np
+        import torch
+        n = len(comps)
+        dev = torch.device("cuda", torch.cuda.current_device())
+        in_len = np.array([len(c) for c in comps], dtype=np.uint32)
+        in_off = np.concatenate([[0], np.cumsum(in_len.astype(np.int64) + 3)[:-1]]).astype(np.int64)
+        blob = np.zeros(int(in_off[-1]) + int(in_len[-1]) + 8, dtype=np.uint8)
+        for o, c in zip(in_off, comps):
+            blob[int(o):int(o) + len(c)] = np.frombuffer(c, dtype=np.uint8)
+        out_len = np.array(caps, dtype=np.uint32)
+        out_off = np.concatenate([[0], np.cumsum(out_len.astype(np.int64) + 1)[:-1]]).astype(np.int64)
+        t = lambda a: torch.from_numpy(a).to(dev)
+        d_in = t(blob); d_out = torch.zeros(int(out_off[-1]) + int(out_len[-1]) + 8, dtype=torch.uint8, device=dev)
+        d_io, d_il, d_oo, d_ol = t(in_off), t(in_len.view(np.int32)), t(out_off), t(out_len.view(np.int32))
+        d_got = torch.zeros(n, dtype=torch.int32, device=dev); d_st = torch.zeros(n, dtype=torch.int32, device=dev)
+        args = [self.h, d_in.data_ptr(), d_io.data_ptr(), d_il.data_ptr(), n, d_out.data_ptr(), d_oo.data_ptr(),
+                d_ol.data_ptr(), d_got.data_ptr(), d_st.data_ptr()]
+        if with_max:
+            args.append(int(out_len.max()) if n else 0)
+        args.append(stream)
+        check(fn(*args), "decode batch")
+        torch.cuda.synchronize()
+        out = d_out.cpu().numpy(); got = d_got.cpu().numpy(); st = d_st.cpu().numpy()
+        return [(int(st[i]), out[int(out_off[i]):int(out_off[i]) + int(got[i])].tobytes()) for i in range(n)]
 
     def rans4x8_decode(self, comps, caps, stream=0):
         """Decode a list of rANS 4x8 streams on the device; returns list of (status, bytes)."""

@@ -136,6 +136,15 @@ int hgpu_rans4x8_decode_batch_dev(hgpu_ctx *ctx,
         uint8_t *d_out, const uint64_t *d_out_off, const uint32_t *d_out_len,
         uint32_t *d_got_len, int32_t *d_status, void *stream);
 
+/* Adaptive arithmetic coder (CRAM 3.1 block method 6, "ARITH_PR") — replaces arith_uncompress_to
+ * (arith_dynamic.c:1033-1278) as called from cram_uncompress_block (cram_io.c:1716-1733) for a
+ * batch of streams, one THREAD per stream (the coder is strictly sequential).  Same argument
+ * meaning as the rANS batch decoder.  X_EXT (bzip2) payloads are rejected. */
+int hgpu_arith_decode_batch_dev(hgpu_ctx *ctx,
+        const uint8_t *d_in, const uint64_t *d_in_off, const uint32_t *d_in_len, uint32_t n,
+        uint8_t *d_out, const uint64_t *d_out_off, const uint32_t *d_out_len,
+        uint32_t *d_got_len, int32_t *d_status, uint32_t max_out_len, void *stream);
+
 /* CRAM 3.x framing on the host: walks containers and blocks (cram_read_container
  * cram/cram_io.c:3760, cram_read_block :1414-1483) of a file image and lists every block so the
  * payloads of all entropy-coded blocks can go to the batch decoders in one launch.  method: 0 RAW,

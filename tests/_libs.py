@@ -76,6 +76,8 @@ def ref_rans_nx16_encode(data, order):
 def golden_raw(name):
     """The raw input the htscodecs tests feed: first column, newlines removed (rans4x16.test:12)."""
     path = os.path.join(GOLD, "htscodecs", "dat", name)
+    if not name.startswith("q"):              # u32 is used verbatim (arith.test:11-18)
+        return open(path, "rb").read()
     out = bytearray()
     with open(path, "rb") as f:
         for line in f:
@@ -300,3 +302,19 @@ def ref_rans_4x8(data=None, order=None, comp=None):
     res = C.string_at(p, n.value)
     libc.free(p)
     return res
+
+
+def ref_arith(data=None, order=None, comp=None, cap=None):
+    """reference arith_compress_to / arith_uncompress_to (arith_dynamic.c:730, :1033)."""
+    r = ref()
+    r.arith_compress_to.restype = C.c_void_p; r.arith_uncompress_to.restype = C.c_void_p
+    r.arith_compress_bound.restype = C.c_uint
+    if comp is None:
+        capc = r.arith_compress_bound(C.c_uint(len(data)), C.c_int(order))
+        out = (C.c_uint8 * max(1, capc))(); n = C.c_uint(capc)
+        p = r.arith_compress_to(buf(data), C.c_uint(len(data)), out, C.byref(n), C.c_int(order))
+        assert p
+        return bytes(out[: n.value])
+    out = (C.c_uint8 * max(1, cap))(); n = C.c_uint(cap)
+    p = r.arith_uncompress_to(buf(comp), C.c_uint(len(comp)), out, C.byref(n))
+    return bytes(out[: n.value]) if p else None
