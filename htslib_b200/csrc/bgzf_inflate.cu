@@ -326,7 +326,10 @@ __device__ uint32_t warp_crc32(const uint32_t (*tab)[256], const uint8_t *out, u
 //
 // piece = { dst:16 | plen:6<<16 ,  src }      (offsets into the member's output)
 // ---------------------------------------------------------------------------------------------
-constexpr int GRP = 16;
+#ifndef GRP_N
+#define GRP_N 4
+#endif
+constexpr int GRP = GRP_N;
 
 __device__ __forceinline__ uint32_t low_mask(uint32_t n) { return n >= 32u ? 0xffffffffu : (1u << n) - 1u; }
 
@@ -785,7 +788,10 @@ __device__ int check_header(const uint8_t *h)
 
 constexpr int INFLATE_WARPS = 4;      // warps per CTA; they share only the CRC tables
 
-__global__ void __launch_bounds__(32 * INFLATE_WARPS, 3)
+#ifndef INFL_LB
+#define INFL_LB 5
+#endif
+__global__ void __launch_bounds__(32 * INFLATE_WARPS, INFL_LB)
 bgzf_inflate_kernel(const uint8_t *__restrict__ in, const uint64_t *__restrict__ in_off,
                     const uint32_t *__restrict__ in_len, uint32_t n, uint8_t *out,
                     const uint64_t *__restrict__ out_off, const uint32_t *__restrict__ out_cap,
