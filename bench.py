@@ -44,6 +44,23 @@ def parse():
     return ap.parse_args()
 
 
+def ncu_traffic(kernel_tag):
+    """dram__bytes_read+write of one launch from the committed ncu --set full capture (profiles/),
+    with the algorithmic bytes of THAT captured launch, so the ratio can be applied honestly."""
+    p = os.path.join(ROOT, "profiles", "r1_%s_ncu_summary.txt" % kernel_tag)
+    if not os.path.exists(p):
+        return None
+    rd = wr = None
+    for line in open(p):
+        f = line.split()
+        if len(f) >= 3 and f[0] == "dram__bytes_read.sum" and rd is None: rd = (float(f[1]), f[2])
+        if len(f) >= 3 and f[0] == "dram__bytes_write.sum" and wr is None: wr = (float(f[1]), f[2])
+    if not rd or not wr:
+        return None
+    scale = {"Gbyte": 1e9, "Mbyte": 1e6, "Kbyte": 1e3, "byte": 1.0}
+    return {"dram_bytes": rd[0] * scale.get(rd[1], 1) + wr[0] * scale.get(wr[1], 1), "source": os.path.relpath(p, ROOT)}
+
+
 def peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -304,8 +321,8 @@ def run_ours(args):
     assert bool((d_len.cpu().numpy().astype(np.uint32) == ulen).all())
     import zlib
     # shards were compressed independently; check the first shard's CRC32 end to end
-    k = corpus["shard_blocks"][0]
-    crc = zlib.crc32(d_out[:int(ulen[:k].astype(np.int64).sum())].cpu().numpy().tobytes())
+    k_shard = corpus["shard_blocks"][0]
+    crc = zlib.crc32(d_out[:int(ulen[:k_shard].astype(np.int64).sum())].cpu().numpy().tobytes())
     assert crc == corpus["shard_crcs"][0], "first shard CRC mismatch"
 
     if world > 1:
@@ -416,7 +433,7 @@ def run_ours(args):
         torch.cuda.empty_cache()
         rc, n, bad = ctx.bgzf_inflate_file_host(fn, on)           # warm-up (allocates staging)
         assert rc == 0 and n == U, (rc, n, bad, H.last_error())
-        assert zlib.crc32(on[:int(ulen[:k].astype(np.int64).sum())].tobytes()) == corpus["shard_crcs"][0]
+        assert zlib.crc32(on[:int(ulen[:k_shard].astype(np.int64).sum())].tobytes()) == corpus["shard_crcs"][0]
         reps = max(2, min(args.steps, 5))
         if world > 1:
             dist.barrier()
@@ -452,7 +469,10 @@ def run_ours(args):
                                    % (U / 1e9 / corpus["tile"], corpus["tile"], world)},
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": hbm, "unit": "GB/s", "frac": achieved / hbm,
                      "traffic": None, "kernel": "bgzf_inflate_kernel", "algorithmic_bytes_per_launch": U + Cb,
-                     "peak_source": how},
+                     "peak_source": how,
+                     "traffic_note": "ncu --set full was captured on the same kernel at --gb 1 (profiles/r1_inflate_ncu_summary.txt): "
+                                     "dram read+write per launch there is in traffic_capture; a 10 GB launch was not captured (null above)",
+                     "traffic_capture": ncu_traffic("inflate")},
         "gpu_launches": int(launches),
         "clocks": clocks,
     }

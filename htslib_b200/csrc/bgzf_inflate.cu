@@ -622,18 +622,6 @@ __device__ int decode_body_parallel(InflateSmem &s, const uint32_t *wbase, const
     uint32_t tot_out = __shfl_sync(0xffffffffu, on, 31), tot_m = __shfl_sync(0xffffffffu, mn, 31);
     if ((uint64_t)o + tot_out > cap) return HGPU_BGZF_ERR_SPACE;
     if (tot_m > MREC_CAP) return HGPU_BGZF_ERR_ZLIB;           // impossible within 64 KiB of output
-    // Make the destination sectors fully valid in L2 before any byte-granular write lands in
-    // them: a load from a sector that holds only some freshly written bytes has to wait for the
-    // rest of the sector to come from DRAM, and the match copies below read what was just written.
-    // Only 16-byte units entirely inside this block's range are touched (neighbouring blocks are
-    // being written by other warps).
-    {
-        uintptr_t lo = (reinterpret_cast<uintptr_t>(out + o) + 15) & ~(uintptr_t)15;
-        uintptr_t hi = reinterpret_cast<uintptr_t>(out + o + tot_out) & ~(uintptr_t)15;
-        for (uintptr_t a = lo + 16 * lane; a < hi; a += 16 * 32)
-            *reinterpret_cast<uint4 *>(a) = make_uint4(0, 0, 0, 0);
-        __syncwarp();
-    }
     bool bad_dist = false;
     if (lane <= E) {
         uint32_t e2, n2, m2, st2;
