@@ -318,3 +318,43 @@ def ref_arith(data=None, order=None, comp=None, cap=None):
     out = (C.c_uint8 * max(1, cap))(); n = C.c_uint(cap)
     p = r.arith_uncompress_to(buf(comp), C.c_uint(len(comp)), out, C.byref(n))
     return bytes(out[: n.value]) if p else None
+
+
+def ref_tok3_encode(names, level=3, use_arith=0):
+    """reference tok3_encode_names (tokenise_name3.c:1456): names is the NUL- or LF-separated blob."""
+    r = ref()
+    r.tok3_encode_names.restype = C.c_void_p
+    n = C.c_int(0); last = C.c_int(0)
+    src = C.create_string_buffer(bytes(names), len(names) + 1)
+    p = r.tok3_encode_names(src, C.c_int(len(names)), C.c_int(level), C.c_int(use_arith), C.byref(n), C.byref(last))
+    assert p, "reference tok3 encoder failed"
+    res = C.string_at(p, n.value)
+    C.CDLL(None).free(C.c_void_p(p))
+    return res
+
+
+def ref_tok3_decode(comp):
+    r = ref()
+    r.tok3_decode_names.restype = C.c_void_p
+    n = C.c_uint(0)
+    p = r.tok3_decode_names(buf(comp), C.c_uint(len(comp)), C.byref(n))
+    if not p:
+        return None
+    res = C.string_at(p, n.value)
+    C.CDLL(None).free(C.c_void_p(p))
+    return res
+
+
+def orc_tok3_decode(comp):
+    """oracle tok3 decode; the adaptive arithmetic sub-coder is oracle/_ref's arith_uncompress_to."""
+    o = orc()
+    o.orc_tok3_decode.restype = C.c_void_p
+    r = ref()
+    fn = C.cast(r.arith_uncompress_to, C.c_void_p) if r is not None else C.c_void_p(0)
+    n = C.c_uint32(0)
+    p = o.orc_tok3_decode(buf(comp), C.c_uint32(len(comp)), C.byref(n), fn)
+    if not p:
+        return None
+    res = C.string_at(p, n.value)
+    o.orc_free(C.c_void_p(p))
+    return res
