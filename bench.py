@@ -38,6 +38,7 @@ def parse():
     ap.add_argument("--level", type=int, default=6)
     ap.add_argument("--quals", default="novaseq")
     ap.add_argument("--rans-slices", type=int, default=-2, help="CRAM slices for the rANS leg (0 = skip)")
+    ap.add_argument("--tok3-blocks", type=int, default=1184, help="read-name blocks for the tok3 leg (0 = skip)")
     ap.add_argument("--cpu-sample-gb", type=float, default=4.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
@@ -491,7 +492,72 @@ def run_ours(args):
                 out.setdefault("extra", {})["rans_nx16_decode"] = rl
         except Exception as ex:                                   # the headline line must still print
             out.setdefault("extra", {})["rans_nx16_decode"] = {"error": repr(ex)}
+        try:
+            tl = tok3_leg(args, ctx)
+            if tl:
+                out.setdefault("extra", {})["tok3_decode"] = tl
+        except Exception as ex:
+            out.setdefault("extra", {})["tok3_decode"] = {"error": repr(ex)}
     print(json.dumps(out), flush=True)
+
+
+def tok3_leg(args, ctx):
+    """CRAM 3.1 read-name (tok3) blocks, 10 000 names per slice, through the host-buffer API
+    (hgpu_tok3_decode_batch_host: framing walk on the host, rANS token streams + name rebuild on the
+    device).  Inputs are fixtures written once by the reference encoder (tests/golden/make_tok3_slices.py)."""
+    import gzip
+    import htslib_b200 as H
+    if args.tok3_blocks <= 0:
+        return None
+    d = os.path.join(ROOT, "tests", "golden", "tok3_slices")
+    uniq = [open(os.path.join(d, "slice%d.tok3" % k), "rb").read() for k in range(8)]
+    want = [gzip.open(os.path.join(d, "slice%d.names.gz" % k), "rb").read() for k in range(8)]
+    Lh = H.lib()
+    n = args.tok3_blocks
+    comps = [uniq[k % 8] for k in range(n)]
+    in_len = np.array([len(c) for c in comps], dtype=np.uint32)
+    in_off = np.concatenate([[0], np.cumsum(in_len.astype(np.uint64))[:-1]]).astype(np.uint64)
+    blob = np.frombuffer(b"".join(comps) + b"\0" * 8, dtype=np.uint8)
+    caps = np.array([Lh.hgpu_tok3_out_bound(c, len(c)) for c in comps], dtype=np.uint32)
+    out_off = np.concatenate([[0], np.cumsum(caps.astype(np.uint64))[:-1]]).astype(np.uint64)
+    out = np.zeros(int(caps.astype(np.uint64).sum()) + 8, dtype=np.uint8)
+    got = np.zeros(n, dtype=np.uint32); st = np.zeros(n, dtype=np.int32)
+    p = lambda a: a.ctypes.data_as(C.c_void_p)
+    Lh.hgpu_tok3_last_ms.argtypes = [C.c_void_p]
+    wall, dev_ms = [], []
+    for it in range(1 + 3):
+        t0 = time.perf_counter()
+        rc = Lh.hgpu_tok3_decode_batch_host(ctx.h, p(blob), p(in_off), p(in_len), n, p(out), p(out_off), p(caps), p(got), p(st))
+        t1 = time.perf_counter()
+        assert rc == 0, H.last_error()
+        ms2 = (C.c_float * 2)()
+        Lh.hgpu_tok3_last_ms(ms2)
+        if it >= 1:
+            wall.append(t1 - t0); dev_ms.append((ms2[0], ms2[1]))
+    assert int(np.abs(st).sum()) == 0, "tok3 decode reported errors"
+    for k in range(8):
+        assert out[int(out_off[k]):int(out_off[k]) + int(got[k])].tobytes() == want[k], "tok3 output differs from the names the fixture was made from"
+    U = int(got.astype(np.int64).sum()); Cb = int(in_len.astype(np.int64).sum())
+    ent = float(np.mean([a for a, b in dev_ms])); nam = float(np.mean([b for a, b in dev_ms]))
+    res = {"workload": "%d tok3 blocks x 10 000 Illumina names (8 unique reference-encoded fixtures tiled), host buffers" % n,
+           "blocks": n, "names": n * 10000, "uncompressed_GB": U / 1e9, "compressed_GB": Cb / 1e9,
+           "entropy_ms": ent, "rebuild_ms": nam, "device_GBps": U / (ent + nam) / 1e6,
+           "names_per_s_device": n * 10000 / ((ent + nam) / 1e3),
+           "e2e_ms": float(np.mean(wall)) * 1e3, "e2e_GBps": U / float(np.mean(wall)) / 1e9,
+           "unit": "GB/s (uncompressed names)"}
+    r = ref_lib()
+    if r is not None:                                             # the reference's own decoder, one core, the 8 unique blocks
+        r.tok3_decode_names.restype = C.c_void_p
+        libc = C.CDLL(None)
+        t0 = time.perf_counter(); tot = 0
+        for rep in range(3):
+            for c in uniq:
+                m = C.c_uint(0)
+                q = r.tok3_decode_names(c, C.c_uint(len(c)), C.byref(m))
+                tot += m.value
+                libc.free(C.c_void_p(q))
+        res["cpu_reference_1core_GBps"] = tot / (time.perf_counter() - t0) / 1e9
+    return res
 
 
 def run_reference(args):

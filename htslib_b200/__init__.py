@@ -68,6 +68,11 @@ def lib():
     L.rans_uncompress_4x16.argtypes = [vp, C.c_uint, C.POINTER(C.c_uint)]
     L.hts_crc32.restype = u32
     L.hts_crc32.argtypes = [u32, vp, C.c_size_t]
+    L.hgpu_tok3_out_bound.restype = u32
+    L.hgpu_tok3_out_bound.argtypes = [C.c_char_p, u32]
+    L.hgpu_tok3_decode_batch_host.argtypes = [vp, vp, vp, vp, u32, vp, vp, vp, vp, vp]
+    L.tok3_decode_names.restype = vp
+    L.tok3_decode_names.argtypes = [C.c_char_p, u32, C.POINTER(u32)]
     _lib = L
     return L
 
@@ -113,6 +118,23 @@ class Context:
                                                     d_out.data_ptr(), d_out_off.data_ptr(), d_out_len.data_ptr(),
                                                     d_got.data_ptr(), d_status.data_ptr(), int(max_out_len), stream),
               "rans_nx16_decode_batch_dev")
+
+    def tok3_decode(self, comps):
+        """Decode a list of tok3 name blocks (host buffers); returns list of (status, bytes)."""
+        import numpy as np
+        L = lib()
+        n = len(comps)
+        in_len = np.array([len(c) for c in comps], dtype=np.uint32)
+        in_off = np.concatenate([[0], np.cumsum(in_len.astype(np.uint64))[:-1]]).astype(np.uint64)
+        blob = np.frombuffer(b"".join(comps) + b"\0" * 8, dtype=np.uint8)
+        caps = np.array([max(1024, L.hgpu_tok3_out_bound(bytes(c), len(c))) for c in comps], dtype=np.uint32)
+        out_off = np.concatenate([[0], np.cumsum(caps.astype(np.uint64))[:-1]]).astype(np.uint64)
+        out = np.zeros(int(caps.astype(np.uint64).sum()) + 8, dtype=np.uint8)
+        got = np.zeros(n, dtype=np.uint32); st = np.zeros(n, dtype=np.int32)
+        p = lambda a: a.ctypes.data_as(C.c_void_p)
+        check(L.hgpu_tok3_decode_batch_host(self.h, p(blob), p(in_off), p(in_len), n, p(out), p(out_off), p(caps), p(got), p(st)),
+              "tok3_decode_batch_host")
+        return [(int(st[i]), out[int(out_off[i]):int(out_off[i]) + int(got[i])].tobytes()) for i in range(n)]
 
     def arith_decode(self, comps, caps, stream=0):
         """Decode a list of arith_dynamic streams on the device; returns list of (status, bytes)."""

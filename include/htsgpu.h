@@ -38,6 +38,8 @@ extern "C" {
 #define HGPU_BGZF_ERR_SPACE  (-4)  /* output longer than the slot the caller gave it */
 /* per-stream rANS status: the reference only has "returns NULL" (rANS_static4x16pr.c:1586) */
 #define HGPU_RANS_ERR        (-1)
+#define HGPU_TOK3_ERR        (-1)  /* tok3_decode_names would have returned NULL */
+#define HGPU_TOK3_ERR_LIMIT  (-5)  /* a token stream claims more than 4 B/name + 2 B/name-byte: refused, not decoded */
 
 typedef struct hgpu_ctx hgpu_ctx;
 
@@ -160,6 +162,25 @@ typedef struct hgpu_cram_block {
 } hgpu_cram_block;
 long hgpu_cram_scan_blocks(const uint8_t *file, uint64_t len, hgpu_cram_block *blocks, long cap,
                            int *major, int *minor);
+
+/* Read-name tokeniser ("tok3", CRAM 3.1 block method 8) — replaces tok3_decode_names
+ * (htscodecs/htscodecs/tokenise_name3.c:1679-1834, tokenise_name3.h:59) as called per block from
+ * cram_uncompress_block (cram/cram_io.c:1753-1765), for a batch of name blocks with HOST buffers.
+ * The descriptor framing is walked on the host; every compressed token stream of every block goes
+ * to the rANS-Nx16 / adaptive-arithmetic batch decoders in one launch each, then one warp per block
+ * rebuilds the names (one lane per token position).  out_cap[i] must be at least
+ * hgpu_tok3_out_bound(block) = the block's own size field + 1024 (the slack the reference's decoder
+ * allocates, :1808); out_len[i] is what tok3_decode_names would report in *out_len (NUL-separated
+ * names); status[i] is HGPU_OK or HGPU_TOK3_ERR where the reference returns NULL. */
+uint32_t hgpu_tok3_out_bound(const uint8_t *in, uint32_t len);
+int hgpu_tok3_decode_batch_host(hgpu_ctx *ctx,
+        const uint8_t *in, const uint64_t *in_off, const uint32_t *in_len, uint32_t n,
+        uint8_t *out, const uint64_t *out_off, const uint32_t *out_cap,
+        uint32_t *out_len, int32_t *status);
+/* device milliseconds of the last call: ms2[0] token-stream entropy decode, ms2[1] name rebuild */
+void hgpu_tok3_last_ms(float *ms2);
+/* drop-in for the reference symbol itself: one block, malloc'd result, NULL on failure */
+uint8_t *tok3_decode_names(uint8_t *in, uint32_t sz, uint32_t *out_len);
 
 /* rANS Nx16 ENCODE — stands where rans_compress_to_4x16 stands (rANS_static4x16pr.c:1203-1579) for
  * a batch of streams, one warp per stream.  order[i]: bit 0 = order-1, bit 2 (value 4) = 32-way
