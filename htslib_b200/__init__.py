@@ -8,7 +8,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libhtsgpu.so")
+LIB_PATH = os.environ.get("HGPU_LIB") or os.path.join(_HERE, "libhtsgpu.so")   # HGPU_LIB: A/B builds when tuning
 HEADER_PATH = os.path.join(os.path.dirname(_HERE), "include", "htsgpu.h")
 
 HGPU_OK = 0
@@ -320,7 +320,7 @@ def cram_scan_blocks(file_np):
     """List the blocks of a CRAM 3.x file image: structured numpy array (hgpu_cram_block)."""
     import numpy as np
     dt = np.dtype([("data_off", "<u8"), ("comp_size", "<u4"), ("uncomp_size", "<u4"), ("content_id", "<i4"),
-                   ("method", "u1"), ("content_type", "u1"), ("pad", "<u2"), ("container", "<u4"), ("pad2", "<u4")])
+                   ("method", "u1"), ("content_type", "u1"), ("hdr_len", "<u2"), ("container", "<u4"), ("pad2", "<u4")])
     assert dt.itemsize == 32
     L = lib()
     L.hgpu_cram_scan_blocks.restype = C.c_long
@@ -343,3 +343,23 @@ def bgzf_scan(file_np):
     off = np.zeros(n, dtype=np.uint64); ln = np.zeros(n, dtype=np.uint32); isz = np.zeros(n, dtype=np.uint32)
     lib().hgpu_bgzf_scan(file_np.ctypes.data, file_np.size, off.ctypes.data, ln.ctypes.data, isz.ctypes.data, n)
     return off, ln, isz
+
+
+def cram_uncompress_blocks(ctx, file_np, blocks=None):
+    """Uncompress every block of a CRAM file image on the device (hgpu_cram_uncompress_blocks_host).
+    Returns (blocks, [(status, bytes)])."""
+    import numpy as np
+    if blocks is None:
+        blocks, _ = cram_scan_blocks(file_np)
+    n = len(blocks)
+    sizes = blocks["uncomp_size"].astype(np.uint64)
+    out_off = np.concatenate([[0], np.cumsum((sizes + 15) // 16 * 16)[:-1]]).astype(np.uint64) if n else np.zeros(0, np.uint64)
+    out = np.zeros(int(out_off[-1] + sizes[-1]) + 16 if n else 16, dtype=np.uint8)
+    got = np.zeros(n, dtype=np.uint32); st = np.zeros(n, dtype=np.int32)
+    L = lib()
+    L.hgpu_cram_uncompress_blocks_host.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p, C.c_uint32, C.c_void_p,
+                                                   C.c_void_p, C.c_void_p, C.c_void_p]
+    barr = np.ascontiguousarray(blocks)
+    check(L.hgpu_cram_uncompress_blocks_host(ctx.h, file_np.ctypes.data, file_np.size, barr.ctypes.data, n, out.ctypes.data,
+                                             out_off.ctypes.data, got.ctypes.data, st.ctypes.data), "cram_uncompress_blocks_host")
+    return blocks, [(int(st[i]), out[int(out_off[i]):int(out_off[i]) + int(got[i])].tobytes()) for i in range(n)]

@@ -838,6 +838,15 @@ __global__ void crc32_chunks_kernel(const uint8_t *buf, size_t len, size_t chunk
     if (hgpu_lane() == 0) partial[w] = crc;
 }
 
+// one warp per buffer: CRC-32 of n independent byte ranges (CRAM block header+payload, cram_io.c:1428-1433, :1585)
+__global__ void crc32_batch_kernel(const uint8_t *buf, const uint64_t *off, const uint32_t *len, uint32_t n, uint32_t *crc_out)
+{
+    const uint32_t i = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (i >= n) return;
+    uint32_t crc = warp_crc32(g_crc_tab, buf + off[i], len[i]);
+    if (hgpu_lane() == 0) crc_out[i] = crc;
+}
+
 bool g_crc_ready[64];
 
 int ensure_crc_tables(hgpu_ctx *ctx, cudaStream_t st)
@@ -1127,6 +1136,17 @@ int hgpu_launch_crc32(hgpu_ctx *ctx, const uint8_t *d_buf, size_t len, uint32_t 
     crc32_chunks_kernel<<<(unsigned)nchunk, 32, 0, st>>>(d_buf, len, chunk, d_partial);
     hgpu_count_launch();
     return hgpu_check(cudaGetLastError(), "crc launch");
+}
+
+int hgpu_launch_crc32_batch(hgpu_ctx *ctx, const uint8_t *d_buf, const uint64_t *d_off, const uint32_t *d_len, uint32_t n,
+                            uint32_t *d_crc, cudaStream_t st)
+{
+    if (n == 0) return HGPU_OK;
+    int rc = ensure_crc_tables(ctx, st);
+    if (rc) return rc;
+    crc32_batch_kernel<<<(n + 3) / 4, 128, 0, st>>>(d_buf, d_off, d_len, n, d_crc);
+    hgpu_count_launch();
+    return hgpu_check(cudaGetLastError(), "crc batch launch");
 }
 
 // Batch BGZF compress, device pointers.  Every out slot must be 65536 bytes and 4-byte aligned.

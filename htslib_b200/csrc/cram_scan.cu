@@ -67,7 +67,8 @@ extern "C" long hgpu_cram_scan_blocks(const uint8_t *file, uint64_t len, hgpu_cr
         while (p < cend) {
             if (cend - p < 2) return -1;
             hgpu_cram_block b;
-            b.method = p[0]; b.content_type = p[1]; b.pad = 0; b.container = container;
+            const uint8_t *hdr = p;
+            b.method = p[0]; b.content_type = p[1]; b.container = container;
             p += 2;
             int32_t cs, us;
             if (!(k = itf8(p, cend, &b.content_id))) return -1; p += k;
@@ -75,6 +76,7 @@ extern "C" long hgpu_cram_scan_blocks(const uint8_t *file, uint64_t len, hgpu_cr
             if (!(k = itf8(p, cend, &us))) return -1; p += k;
             if (cs < 0 || us < 0 || (uint64_t)(cend - p) < (uint64_t)cs + 4) { hgpu_set_error("block runs past its container"); return -1; }
             b.data_off = (uint64_t)(p - file);
+            b.hdr_len = (uint16_t)(p - hdr);
             b.comp_size = (uint32_t)cs; b.uncomp_size = (uint32_t)us;
             if (blocks && n < cap) blocks[n] = b;
             n++;

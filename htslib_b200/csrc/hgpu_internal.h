@@ -48,6 +48,9 @@ int hgpu_launch_bgzf_inflate(hgpu_ctx *ctx, const uint8_t *d_in, const uint64_t 
 int hgpu_launch_crc32(hgpu_ctx *ctx, const uint8_t *d_buf, size_t len, uint32_t *d_partial,
                       uint32_t *h_result, uint32_t crc0, cudaStream_t st);
 
+int hgpu_launch_crc32_batch(hgpu_ctx *ctx, const uint8_t *d_buf, const uint64_t *d_off, const uint32_t *d_len, uint32_t n,
+                            uint32_t *d_crc, cudaStream_t st);
+
 #ifdef __CUDACC__
 __device__ __forceinline__ uint32_t hgpu_lanemask_lt()
 {

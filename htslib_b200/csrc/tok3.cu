@@ -5,349 +5,19 @@
 //   host   : walks each block's descriptor framing (ttype byte, dup links, varint sizes) and turns the
 //            compressed token streams of all blocks into one job list;
 //   device : the existing rANS-Nx16 / adaptive-arithmetic batch decoders expand every token stream
-//            into an arena, then tok3_names_kernel rebuilds the names, one WARP per block with one
-//            LANE per token position (token positions own disjoint streams, so the lanes of a name
-//            are independent; names themselves are a serial chain through the name they diff against).
+//            into an arena, then tok3_names_kernel (tok3_names.cu) rebuilds the names, one warp per block.
 //
 // Layout per block in HBM: a descriptor table of max_tok*16 {offset,len,synth} entries into the stream
 // arena; a history table (nreads+1) x max_tok of {value, type|aux} so that any earlier name can be the
 // reference of a later one (decode_name :1023-1210 keeps the same per-name token history); a name
 // table {offset, ntok, history row}.  A duplicate name aliases its source's history row.
-#include "hgpu_internal.h"
+#include "tok3_internal.h"
 #include <vector>
 #include <string.h>
 #include <stdlib.h>
 #include <mutex>
 
 namespace {
-
-enum { T_TYPE = 0, T_ALPHA, T_CHAR, T_DIGITS0, T_DZLEN, T_DUP, T_DIFF, T_DIGITS, T_DDELTA,
-       T_DDELTA0, T_MATCH, T_NOP, T_END };
-constexpr int TOK_MAX = 128;                       // MAX_TOKENS, tokenise_name3.c:115
-
-struct Tok3Desc {                                  // one token stream ("descriptor", :143-148)
-    uint64_t off;                                  // byte offset in the stream arena
-    uint32_t len;                                  // buf_a
-    uint32_t synth;                                // 0: real bytes; else 0x100|type: [type, MATCH, MATCH, ...] (:1720-1729)
-};
-
-struct Tok3Block {
-    uint64_t out_off;                              // names go to d_out + out_off
-    uint64_t hist_off;                             // first uint2 of this block's history table
-    uint64_t name_off;                             // first uint4 of this block's name table
-    uint32_t out_cap;
-    uint32_t desc_base;                            // first Tok3Desc of this block
-    uint32_t max_tok;
-    uint32_t nreads;                               // header field; the context holds nreads+1 names (:189-192)
-    uint32_t ulen;                                 // header field
-    uint32_t job0, njobs;                          // entropy-decoder jobs of this block
-    int32_t  host_status;                          // framing already rejected on the host
-};
-
-__device__ __forceinline__ int desc_byte(const uint8_t *arena, const Tok3Desc &d, uint32_t pos)
-{
-    if (d.synth) return pos == 0 ? (int)(d.synth & 0xff) : T_MATCH;
-    return arena[d.off + pos];
-}
-__device__ __forceinline__ Tok3Desc load_desc(const Tok3Desc *p)
-{
-    uint4 v = __ldg(reinterpret_cast<const uint4 *>(p));
-    Tok3Desc d;
-    d.off = (uint64_t)v.x | ((uint64_t)v.y << 32);
-    d.len = v.z;
-    d.synth = v.w;
-    return d;
-}
-
-__constant__ uint32_t c_p10[10] = {1, 10, 100, 1000, 10000, 100000, 1000000, 10000000, 100000000, 1000000000};
-
-// append_uint32_var (:249-286): no leading zeros, nothing at all for 0
-__device__ __forceinline__ int var_digits(uint32_t v)
-{
-    int n = 0;
-    #pragma unroll
-    for (int k = 0; k < 10; k++) n += v >= c_p10[k] ? 1 : 0;
-    return n;                                      // v == 0 -> 0
-}
-__device__ __forceinline__ void put_var(uint8_t *o, uint32_t v, int n)
-{
-    for (int k = n - 1; k >= 0; k--) { o[k] = '0' + v % 10; v /= 10; }
-}
-// append_uint32_fixed (:233-247): w digits; the leading one is stored unreduced; w == 0 or w > 9 writes nothing
-__device__ __forceinline__ void put_fixed(uint8_t *o, uint32_t v, uint32_t w)
-{
-    if (w == 0 || w > 9) return;
-    uint32_t p = c_p10[w - 1];
-    o[0] = (uint8_t)(v / p + '0');
-    v %= p;
-    for (uint32_t k = w - 1; k >= 1; k--) { o[k] = '0' + v % 10; v /= 10; }
-}
-
-enum { W_NONE = 0, W_BYTE, W_STREAM, W_NAME, W_VAR, W_FIXED, W_NUL };
-
-// One warp per name block.  cur[] (shared) holds the read cursor of each of the block's max_tok*16 streams.
-__global__ void __launch_bounds__(32) tok3_names_kernel(const Tok3Block *blocks, const Tok3Desc *descs,
-        const uint8_t *arena, const int32_t *job_status, const uint32_t *job_got, const uint32_t *job_want,
-        uint2 *hist_all, uint4 *names_all, uint8_t *out, uint32_t *out_len, int32_t *status)
-{
-    __shared__ uint32_t cur[TOK_MAX * 16];
-    const uint32_t lane = threadIdx.x;
-    const Tok3Block B = blocks[blockIdx.x];
-    const uint32_t b = blockIdx.x;
-    if (B.host_status) { if (lane == 0) { status[b] = B.host_status; out_len[b] = 0; } return; }
-
-    // every token stream must have decoded to exactly the size its header announced (:1789-1793)
-    bool bad = false;
-    for (uint32_t j = lane; j < B.njobs; j += 32)
-        bad |= job_status[B.job0 + j] != HGPU_OK || job_got[B.job0 + j] != job_want[B.job0 + j];
-    if (__any_sync(0xffffffffu, bad)) { if (lane == 0) { status[b] = HGPU_TOK3_ERR; out_len[b] = 0; } return; }
-
-    const uint32_t ndesc = B.max_tok * 16;
-    for (uint32_t i = lane; i < ndesc; i += 32) cur[i] = 0;
-    __syncwarp();
-
-    const Tok3Desc *D = descs + B.desc_base;
-    uint2 *H = hist_all + B.hist_off;                              // [name][max_tok] {val, type<<28 | aux}
-    uint4 *NM = names_all + B.name_off;                            // {offset, ntok, history row, 0}
-    uint8_t *O = out + B.out_off;
-    const uint32_t kmax = B.max_tok < (uint32_t)TOK_MAX ? B.max_tok : (uint32_t)TOK_MAX;
-
-    int64_t room = (int64_t)B.ulen + 1024;                         // name_len of decode_name (:1810-1818)
-    if ((int64_t)B.out_cap < room) room = -1;                      // caller's slot is too small: rejected below
-    uint64_t at = 0;
-    uint32_t cnum = 0;
-    int result = 0;                                                // 0 running, 1 finished, -1 error
-    if (room < 0) result = -1;
-
-    while (result == 0) {
-        // ---- token 0: which earlier name to diff against (uniform across the warp)
-        Tok3Desc d0 = load_desc(&D[0]);
-        uint32_t c0 = cur[0];
-        int t0 = c0 < d0.len ? desc_byte(arena, d0, c0) : -1;
-        __syncwarp();
-        if (lane == 0 && t0 >= 0) cur[0] = c0 + 1;
-        __syncwarp();
-        if (cnum > B.nreads) { result = -1; break; }               // cnum >= max_names (:1028)
-        if (t0 < 0 || (uint32_t)t0 >= ndesc) { result = 1; break; }
-        Tok3Desc dd = load_desc(&D[t0]);
-        uint32_t cd = cur[t0];
-        if ((uint64_t)cd + 4 > dd.len) { result = -1; break; }
-        uint32_t dist = (uint32_t)desc_byte(arena, dd, cd) | (uint32_t)desc_byte(arena, dd, cd + 1) << 8 |
-                        (uint32_t)desc_byte(arena, dd, cd + 2) << 16 | (uint32_t)desc_byte(arena, dd, cd + 3) << 24;
-        __syncwarp();
-        if (lane == 0) cur[t0] = cd + 4;
-        __syncwarp();
-        if (dist > cnum) { result = -1; break; }
-        const uint32_t pnum = cnum - dist;
-        const uint4 P = NM[pnum];                                  // only meaningful when pnum < cnum
-        uint8_t *name = O + at;
-
-        if (t0 == T_DUP) {
-            if (pnum == cnum) { result = -1; break; }
-            // strcpy semantics: up to the first NUL of the earlier name (:1043-1045)
-            const uint8_t *src = O + P.x;
-            uint32_t l = 0;
-            bool stop = false, over = false;
-            while (!stop) {
-                uint32_t i = l + lane;
-                // the earlier name always ends in a NUL this kernel wrote, so the scan terminates
-                uint8_t ch = src[i];
-                uint32_t z = __ballot_sync(0xffffffffu, ch == 0);
-                uint32_t n = z ? (uint32_t)__ffs(z) - 1 : 32u;
-                if ((int64_t)(l + n) + 1 >= room) { over = true; break; }
-                if (lane < n) name[i] = ch;
-                l += n;
-                stop = z != 0;
-            }
-            if (over) { result = -1; break; }
-            if (lane == 0) { name[l] = 0; NM[cnum] = make_uint4((uint32_t)at, P.y, P.z, 0); }
-            at += l + 1; room -= l + 1;
-            cnum++;
-            __syncwarp();
-            continue;
-        }
-
-        const uint32_t pntok = pnum == cnum ? 0 : P.y;             // last_ntok is 0 while a name is in flight (:1071)
-        const uint2 *HP = H + (uint64_t)P.z * B.max_tok;
-        uint2 *HC = H + (uint64_t)cnum * B.max_tok;
-        uint32_t len = 0, ntok = 0;
-        bool ended = false, err = false;
-
-        for (uint32_t base = 1; base < kmax && !ended && !err; base += 32) {
-            const uint32_t k = base + lane;
-            const bool active = k < kmax;
-            const Tok3Desc *S = D + (k << 4);
-            uint32_t *C = cur + (k << 4);
-            int tok = -1;
-            Tok3Desc dt;
-            uint32_t ct = 0;
-            if (active) {
-                dt = load_desc(&S[T_TYPE]);
-                ct = C[T_TYPE];
-                if (ct < dt.len) tok = desc_byte(arena, dt, ct);
-            }
-            const bool payload = tok == T_ALPHA || tok == T_CHAR || tok == T_DIGITS0 || tok == T_DIGITS ||
-                                 tok == T_DDELTA || tok == T_DDELTA0 || tok == T_MATCH || tok == T_NOP;
-            const uint32_t endmask = __ballot_sync(0xffffffffu, active && !payload);
-            const uint32_t e = endmask ? (uint32_t)__ffs(endmask) - 1 : 32u;   // first END / dry type stream
-            const bool mine = active && lane <= e;
-
-            // what this lane contributes
-            uint32_t flen = 0, need = 0, wmode = W_NONE, v = 0, w = 0;
-            uint64_t srcoff = 0;
-            Tok3Desc ds;
-            uint32_t rtype = T_NOP, rval = 0, raux = 0;
-            bool lerr = false, alpha_open = false;
-            if (mine) {
-                if (tok >= 0) C[T_TYPE] = ct + 1;                                 // decode_token_type consumed it
-                if (lane == e) {                                                  // N_END (:1186-1204)
-                    flen = 1; need = 1; wmode = W_NUL; rtype = T_END;
-                } else {
-                    const bool hasq = k < pntok;
-                    uint2 q = hasq ? HP[k] : make_uint2(0, 0);
-                    const uint32_t qtype = q.y >> 28, qaux = q.y & 0x0fffffffu;
-                    switch (tok) {
-                    case T_CHAR: {
-                        ds = load_desc(&S[T_CHAR]);
-                        uint32_t c = C[T_CHAR];
-                        if (c >= ds.len) { lerr = true; break; }
-                        v = (uint32_t)desc_byte(arena, ds, c); C[T_CHAR] = c + 1;
-                        flen = 1; need = 1; wmode = W_BYTE;
-                        rtype = T_CHAR; rval = (uint32_t)(int32_t)(int8_t)v;      // token_int = (char) (:1078)
-                        break; }
-                    case T_ALPHA: {
-                        ds = load_desc(&S[T_ALPHA]);
-                        uint32_t c = C[T_ALPHA];
-                        if (c >= ds.len) { lerr = true; break; }
-                        uint32_t n = 0;                                           // bytes consumed incl. the NUL
-                        int ch;
-                        do { ch = desc_byte(arena, ds, c + n); n++; } while (ch && c + n < ds.len);
-                        C[T_ALPHA] = c + n;
-                        flen = n - 1;                                             // a missing NUL drops the last char (:432-437)
-                        need = n; alpha_open = true;                              // needs n <= room - len
-                        wmode = W_STREAM; srcoff = c;
-                        rtype = T_ALPHA; rval = flen;
-                        break; }
-                    case T_DIGITS0: {
-                        ds = load_desc(&S[T_DZLEN]);
-                        uint32_t c = C[T_DZLEN];
-                        if (c >= ds.len) { lerr = true; break; }
-                        w = (uint32_t)desc_byte(arena, ds, c); C[T_DZLEN] = c + 1;
-                        ds = load_desc(&S[T_DIGITS0]);
-                        c = C[T_DIGITS0];
-                        if ((uint64_t)c + 4 > ds.len) { lerr = true; break; }
-                        v = (uint32_t)desc_byte(arena, ds, c) | (uint32_t)desc_byte(arena, ds, c + 1) << 8 |
-                            (uint32_t)desc_byte(arena, ds, c + 2) << 16 | (uint32_t)desc_byte(arena, ds, c + 3) << 24;
-                        C[T_DIGITS0] = c + 4;
-                        flen = w; need = 20 + w; wmode = W_FIXED;
-                        rtype = T_DIGITS0; rval = v; raux = w;
-                        break; }
-                    case T_DDELTA0: {
-                        if (!hasq) { lerr = true; break; }
-                        ds = load_desc(&S[T_DDELTA0]);
-                        uint32_t c = C[T_DDELTA0];
-                        if (c >= ds.len) { lerr = true; break; }
-                        v = (uint32_t)desc_byte(arena, ds, c) + q.x; C[T_DDELTA0] = c + 1;
-                        w = qaux;
-                        flen = w; need = w + 1; wmode = W_FIXED;
-                        rtype = T_DIGITS0; rval = v; raux = w;
-                        break; }
-                    case T_DIGITS: {
-                        ds = load_desc(&S[T_DIGITS]);
-                        uint32_t c = C[T_DIGITS];
-                        if ((uint64_t)c + 4 > ds.len) { lerr = true; break; }
-                        v = (uint32_t)desc_byte(arena, ds, c) | (uint32_t)desc_byte(arena, ds, c + 1) << 8 |
-                            (uint32_t)desc_byte(arena, ds, c + 2) << 16 | (uint32_t)desc_byte(arena, ds, c + 3) << 24;
-                        C[T_DIGITS] = c + 4;
-                        flen = (uint32_t)var_digits(v); need = 20; wmode = W_VAR;
-                        rtype = T_DIGITS; rval = v;
-                        break; }
-                    case T_DDELTA: {
-                        if (!hasq) { lerr = true; break; }
-                        ds = load_desc(&S[T_DDELTA]);
-                        uint32_t c = C[T_DDELTA];
-                        if (c >= ds.len) { lerr = true; break; }
-                        v = (uint32_t)desc_byte(arena, ds, c) + q.x; C[T_DDELTA] = c + 1;
-                        flen = (uint32_t)var_digits(v); need = 20; wmode = W_VAR;
-                        rtype = T_DIGITS; rval = v;
-                        break; }
-                    case T_NOP:
-                        rtype = T_NOP;
-                        break;
-                    default:                                                       // T_MATCH (:1133-1183)
-                        if (!hasq) { lerr = true; break; }
-                        switch (qtype) {
-                        case T_CHAR:
-                            v = q.x & 0xff; flen = 1; need = 1; wmode = W_BYTE;
-                            rtype = T_CHAR; rval = q.x;
-                            break;
-                        case T_ALPHA:
-                            if ((int32_t)q.x < 0) { lerr = true; break; }
-                            flen = q.x; need = q.x; wmode = W_NAME; srcoff = (uint64_t)P.x + qaux;
-                            if (q.x == 0) need = 0x80000000u;                      // "len + 0 >= room" still applies: marker
-                            rtype = T_ALPHA; rval = q.x;
-                            break;
-                        case T_DIGITS:
-                            v = q.x; flen = (uint32_t)var_digits(v); need = 20; wmode = W_VAR;
-                            rtype = T_DIGITS; rval = v;
-                            break;
-                        case T_DIGITS0:
-                            v = q.x; w = qaux; flen = w; need = w; wmode = W_FIXED;
-                            if (w == 0) need = 0x80000000u;
-                            rtype = T_DIGITS0; rval = v; raux = w;
-                            break;
-                        default:
-                            lerr = true;
-                        }
-                    }
-                }
-            }
-            // exclusive prefix of the fragment lengths -> where each lane writes
-            uint32_t incl = flen;
-            #pragma unroll
-            for (int s = 1; s < 32; s <<= 1) {
-                uint32_t t = __shfl_up_sync(0xffffffffu, incl, s);
-                if (lane >= (uint32_t)s) incl += t;
-            }
-            const uint32_t off = len + incl - flen;
-            // the reference's "len + need >= name_len" guards, evaluated with this lane's own len
-            if (mine && !lerr) {
-                if (alpha_open) { if ((int64_t)need > room - (int64_t)off) lerr = true; }
-                else if (need == 0x80000000u) { if ((int64_t)off >= room) lerr = true; }
-                else if (need && (int64_t)off + (int64_t)need >= room) lerr = true;
-            }
-            if (__any_sync(0xffffffffu, lerr)) { err = true; break; }
-            if (mine) {
-                uint8_t *o = name + off;
-                switch (wmode) {
-                case W_BYTE: o[0] = (uint8_t)v; break;
-                case W_NUL: o[0] = 0; break;
-                case W_STREAM: for (uint32_t i = 0; i < flen; i++) o[i] = (uint8_t)desc_byte(arena, ds, (uint32_t)srcoff + i); break;
-                case W_NAME: { const uint8_t *s = O + srcoff; for (uint32_t i = 0; i < flen; i++) o[i] = s[i]; break; }
-                case W_VAR: put_var(o, v, (int)flen); break;
-                case W_FIXED: put_fixed(o, v, w); break;
-                default: break;
-                }
-                if (rtype == T_ALPHA) raux = off;                                  // token_str = offset in the name
-                if (raux >> 28) lerr = true;                                       // beyond the packed field (names of 256 MB)
-                HC[k] = make_uint2(rval, rtype << 28 | raux);
-            }
-            if (__any_sync(0xffffffffu, lerr)) { err = true; break; }
-            len += __shfl_sync(0xffffffffu, incl, 31);
-            if (e < 32) { ended = true; ntok = base + e; }
-        }
-        if (err || !ended) { result = -1; break; }
-        if (lane == 0) NM[cnum] = make_uint4((uint32_t)at, ntok, cnum, 0);
-        at += len; room -= len;
-        cnum++;
-        __syncwarp();                                                              // history and name bytes visible to the next name
-    }
-
-    if (lane == 0) {
-        status[b] = result == 1 ? HGPU_OK : HGPU_TOK3_ERR;
-        out_len[b] = result == 1 ? (uint32_t)at : 0;
-    }
-}
 
 // big-endian 7-bit varint, var_get_u32 (varint.h:267-299)
 int h_vget(const uint8_t *p, const uint8_t *end, uint32_t *v)
@@ -401,7 +71,7 @@ extern "C" int hgpu_tok3_decode_batch_host(hgpu_ctx *ctx, const uint8_t *in, con
     std::vector<Job> rjobs, ajobs;                 // rANS-Nx16 / adaptive arithmetic
     std::vector<uint32_t> rjob_block_first(n, 0), ajob_block_first(n, 0);
     uint64_t arena = 0, hist = 0, names = 0, in_end = 0, out_end = 0;
-    uint32_t max_stream = 0;
+    uint32_t max_stream = 0, max_ndesc = 16;
     for (uint32_t b = 0; b < n; b++) {
         Tok3Block &B = blocks[b];
         memset(&B, 0, sizeof(B));
@@ -481,6 +151,7 @@ extern "C" int hgpu_tok3_decode_batch_host(hgpu_ctx *ctx, const uint8_t *in, con
         B.host_status = HGPU_OK;
         B.desc_base = (uint32_t)desc_mark;
         B.max_tok = (uint32_t)(tnum + 1 > 1 ? tnum + 1 : 1);
+        if (B.max_tok * 16 > max_ndesc) max_ndesc = B.max_tok * 16;
         B.nreads = (uint32_t)nreads;
         B.ulen = ulen;
         B.job0 = (uint32_t)job_mark | (use_arith ? 0x80000000u : 0);          // rebased below
@@ -540,12 +211,11 @@ extern "C" int hgpu_tok3_decode_batch_host(hgpu_ctx *ctx, const uint8_t *in, con
         if (rc) return rc;
     }
     cudaEventRecord(tev[1], s);
-    tok3_names_kernel<<<n, 32, 0, s>>>((const Tok3Block *)(base + o_blocks), (const Tok3Desc *)(base + o_descs), base + o_arena,
-                                      d_jst, d_jgot, d_jol, (uint2 *)(base + o_hist), (uint4 *)(base + o_names),
-                                      base + o_out, (uint32_t *)(base + o_olen), (int32_t *)(base + o_st));
-    if (hgpu_check(cudaGetLastError(), "tok3_names_kernel")) return HGPU_ERR_CUDA;
+    rc = hgpu_launch_tok3_names(ctx, (const Tok3Block *)(base + o_blocks), n, max_ndesc, (const Tok3Desc *)(base + o_descs), base + o_arena,
+                                d_jst, d_jgot, d_jol, (uint2 *)(base + o_hist), (uint4 *)(base + o_names),
+                                base + o_out, (uint32_t *)(base + o_olen), (int32_t *)(base + o_st), s);
+    if (rc) return rc;
     cudaEventRecord(tev[2], s);
-    hgpu_count_launch();
     if (hgpu_check(cudaMemcpyAsync(out_len, base + o_olen, (size_t)n * 4, cudaMemcpyDeviceToHost, s), "D2H")) return HGPU_ERR_CUDA;
     if (hgpu_check(cudaMemcpyAsync(status, base + o_st, (size_t)n * 4, cudaMemcpyDeviceToHost, s), "D2H")) return HGPU_ERR_CUDA;
     if (hgpu_check(cudaMemcpyAsync(out, base + o_out, out_end, cudaMemcpyDeviceToHost, s), "D2H")) return HGPU_ERR_CUDA;

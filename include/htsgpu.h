@@ -157,11 +157,29 @@ typedef struct hgpu_cram_block {
     uint32_t comp_size, uncomp_size;
     int32_t  content_id;
     uint8_t  method, content_type;
-    uint16_t pad;
+    uint16_t hdr_len;        /* bytes of block header before data_off (method .. uncomp_size): the block CRC covers header + payload */
     uint32_t container;      /* index of the enclosing container */
 } hgpu_cram_block;
 long hgpu_cram_scan_blocks(const uint8_t *file, uint64_t len, hgpu_cram_block *blocks, long cap,
                            int *major, int *minor);
+
+/* cram_uncompress_block (cram/cram_io.c:1576-1754) for a whole block list at once, HOST buffers — the
+ * per-block work cram_decode_slice does before its record loop (cram/cram_decode.c:619-627).  blocks[] is
+ * what hgpu_cram_scan_blocks returned for this file image; block i's data goes to out + out_off[i], a
+ * slot of blocks[i].uncomp_size bytes.  One upload of the image, one CRC-32 launch over every block's
+ * header+payload (:1585-1592), one batch launch per codec: method 4 rANS 4x8, 5 rANS Nx16, 6 adaptive
+ * arithmetic, 8 tok3; RAW is a host copy.  status[i]: HGPU_OK; HGPU_CRAM_ERR_CRC (block CRC32 failure);
+ * HGPU_CRAM_ERR_DECODE (the reference returns -1: codec failure or size mismatch); HGPU_CRAM_ERR_SPACE
+ * (a tok3 block longer than its uncomp_size field — the reference adopts the new size, a fixed slot
+ * cannot); HGPU_CRAM_UNSUPPORTED for GZIP / BZIP2 / LZMA / FQZ blocks, which stay with the host library.
+ * got_len[i]: bytes written. */
+#define HGPU_CRAM_ERR_DECODE  (-1)
+#define HGPU_CRAM_ERR_CRC     (-2)
+#define HGPU_CRAM_ERR_SPACE   (-4)
+#define HGPU_CRAM_UNSUPPORTED (-6)
+int hgpu_cram_uncompress_blocks_host(hgpu_ctx *ctx, const uint8_t *file, uint64_t file_len,
+        const hgpu_cram_block *blocks, uint32_t n, uint8_t *out, const uint64_t *out_off,
+        uint32_t *got_len, int32_t *status);
 
 /* Read-name tokeniser ("tok3", CRAM 3.1 block method 8) — replaces tok3_decode_names
  * (htscodecs/htscodecs/tokenise_name3.c:1679-1834, tokenise_name3.h:59) as called per block from

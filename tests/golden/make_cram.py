@@ -1,9 +1,8 @@
 #!/usr/bin/env python
 """Regenerates tests/golden/htslib/ce#1000.v31.cram / .v30.cram with the compiled reference
 (oracle/_ref/libhts_ref.so): ce#1000.sam + ce.fa -> CRAM 3.1 ('normal' profile: RANS_PR blocks incl.
-32-way order-1 QS, tok3 names) and CRAM 3.0 (rANS 4x8).  Also dumps, for every block, the
-reference's own cram_uncompress_block output, as <cram>.blocks.npz, so the parity tests can run
-where /root/reference and oracle/_ref are absent.  Run from the repo root in the build container."""
+32-way order-1 QS, tok3 names), CRAM 3.0 (rANS 4x8) and a CRAM 3.1 written with use_arith (method 6
+blocks, arith-coded tok3 streams, 4 slices).  Run from the repo root in the build container."""
 import ctypes as C
 import os, sys
 import numpy as np
@@ -22,11 +21,18 @@ r.hts_set_opt.argtypes = [C.c_void_p, C.c_int, C.c_char_p]
 CRAM_OPT_VERSION, CRAM_OPT_REFERENCE = 6, 9
 
 
-def write(version, name, reps=1):
+CRAM_OPT_SEQS_PER_SLICE, CRAM_OPT_USE_ARITH, HTS_OPT_COMPRESSION_LEVEL = 3, 26, 100
+
+
+def write(version, name, reps=1, int_opts=()):
     out = os.path.join(G, name).encode()
     fo = r.hts_open(out, b"wc")
     assert fo
     assert r.hts_set_opt(fo, CRAM_OPT_VERSION, version.encode()) == 0
+    r.hts_set_opt.argtypes = [C.c_void_p, C.c_int, C.c_int]
+    for opt, val in int_opts:
+        assert r.hts_set_opt(fo, opt, val) == 0
+    r.hts_set_opt.argtypes = [C.c_void_p, C.c_int, C.c_char_p]
     assert r.hts_set_opt(fo, CRAM_OPT_REFERENCE, os.path.join(G, "ce.fa").encode()) == 0
     first = True
     for _ in range(reps):
@@ -48,3 +54,6 @@ def write(version, name, reps=1):
 if __name__ == "__main__":
     write("3.1", "ce#1000.v31.cram")
     write("3.0", "ce#1000.v30.cram")
+    # adaptive-arithmetic blocks (method 6) and arith-coded tok3 streams, several slices; level 3 keeps the
+    # bzip2-backed X_EXT methods out (oracle/_ref is built without libbz2)
+    write("3.1", "ce#1000.v31arith.cram", int_opts=[(CRAM_OPT_USE_ARITH, 1), (HTS_OPT_COMPRESSION_LEVEL, 3), (CRAM_OPT_SEQS_PER_SLICE, 300)])

@@ -49,3 +49,47 @@ def test_all_rans_blocks_decode_on_gpu():
         want = orc_rans_nx16_decode(comp, int(b["uncomp_size"]))
         assert out[int(out_off[i]):int(out_off[i]) + int(out_len[i])].tobytes() == want, i
     ctx.close()
+
+
+def _expect(img, b):
+    """What cram_uncompress_block leaves in b->data, from the per-codec checkers (None = not checked here)."""
+    import _libs as L
+    comp = img[int(b["data_off"]):int(b["data_off"]) + int(b["comp_size"])].tobytes()
+    m, us = int(b["method"]), int(b["uncomp_size"])
+    if us == 0: return b""
+    if m == 0: return comp[:us]
+    if m == 4: return L.orc_rans_4x8_decode(comp, us)
+    if m == 5: return L.orc_rans_nx16_decode(comp, us)
+    if m == 6: return L.ref_arith(comp=comp, cap=us) if L.ref() is not None else None
+    if m == 8: return L.orc_tok3_decode(comp) if (comp[8] == 0 or L.ref() is not None) else None
+    return None
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", ["ce#1000.v31.cram", "ce#1000.v30.cram", "ce#1000.v31arith.cram"])
+def test_uncompress_all_blocks_in_one_call(name):
+    img = np.fromfile(os.path.join(GOLD, "htslib", name), dtype=np.uint8)
+    ctx = H.Context(0)
+    blocks, res = H.cram_uncompress_blocks(ctx, img)
+    seen = collections.Counter()
+    for b, (st, data) in zip(blocks, res):
+        m = int(b["method"])
+        if m in (1, 2, 3, 7):
+            assert st == -6                              # HGPU_CRAM_UNSUPPORTED: stays with the host library
+            continue
+        want = _expect(img, b)
+        assert st == 0, (m, int(b["content_id"]))
+        if want is not None:
+            assert data == want, (m, int(b["content_id"]))
+            seen[m] += 1
+    if name.endswith("v31.cram"): assert seen[5] == 14 and seen[8] == 1
+    if name.endswith("v30.cram"): assert seen[4] == 9
+    if name.endswith("arith.cram") and ref() is not None: assert seen[6] == 30 and seen[8] == 4
+    # one flipped payload bit: that block fails its CRC (cram_io.c:1585-1592), every other block is unaffected
+    victim = int(np.argmax(blocks["comp_size"]))
+    bad = img.copy(); bad[int(blocks[victim]["data_off"]) + 5] ^= 0x10
+    _, res2 = H.cram_uncompress_blocks(ctx, bad, blocks)
+    for i, ((st, data), (st0, data0)) in enumerate(zip(res2, res)):
+        if i == victim: assert st == -2
+        else: assert (st, data) == (st0, data0)
+    ctx.close()
