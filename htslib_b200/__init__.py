@@ -363,3 +363,22 @@ def cram_uncompress_blocks(ctx, file_np, blocks=None):
     check(L.hgpu_cram_uncompress_blocks_host(ctx.h, file_np.ctypes.data, file_np.size, barr.ctypes.data, n, out.ctypes.data,
                                              out_off.ctypes.data, got.ctypes.data, st.ctypes.data), "cram_uncompress_blocks_host")
     return blocks, [(int(st[i]), out[int(out_off[i]):int(out_off[i]) + int(got[i])].tobytes()) for i in range(n)]
+
+
+def fqz_decode(ctx, comps, caps):
+    """Decode a list of fqzcomp quality streams (hgpu_fqz_decode_batch_host); returns [(status, bytes)]."""
+    import numpy as np
+    L = lib()
+    L.hgpu_fqz_decode_batch_host.argtypes = [C.c_void_p] * 4 + [C.c_uint32] + [C.c_void_p] * 5
+    n = len(comps)
+    in_len = np.array([len(c) for c in comps], dtype=np.uint32)
+    in_off = np.concatenate([[0], np.cumsum(in_len.astype(np.uint64))[:-1]]).astype(np.uint64)
+    blob = np.frombuffer(b"".join(comps) + b"\0" * 8, dtype=np.uint8)
+    cap = np.array(caps, dtype=np.uint32)
+    out_off = np.concatenate([[0], np.cumsum((cap.astype(np.uint64) + 15) // 16 * 16)[:-1]]).astype(np.uint64)
+    out = np.zeros(int(out_off[-1] + cap[-1]) + 16, dtype=np.uint8)
+    got = np.zeros(n, dtype=np.uint32); st = np.zeros(n, dtype=np.int32)
+    p = lambda a: a.ctypes.data_as(C.c_void_p)
+    check(L.hgpu_fqz_decode_batch_host(ctx.h, p(blob), p(in_off), p(in_len), n, p(out), p(out_off), p(cap), p(got), p(st)),
+          "fqz_decode_batch_host")
+    return [(int(st[i]), out[int(out_off[i]):int(out_off[i]) + int(got[i])].tobytes()) for i in range(n)]

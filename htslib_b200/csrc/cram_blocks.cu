@@ -5,7 +5,8 @@
 // hgpu_cram_scan_blocks goes to the device: one upload of the file image, one CRC-32 launch over every
 // block's header+payload (:1585-1592), one batch launch per entropy codec (method 4 rANS 4x8, 5 rANS
 // Nx16, 6 adaptive arithmetic, 8 tok3 names), one download of all payloads.  RAW blocks are host copies.
-// GZIP / BZIP2 / LZMA / FQZ blocks are reported HGPU_CRAM_UNSUPPORTED and stay with the host library.
+// Method 7 (fqzcomp) blocks go through hgpu_fqz_decode_batch_host.  GZIP / BZIP2 / LZMA blocks are reported
+// HGPU_CRAM_UNSUPPORTED and stay with the host library.
 #include "hgpu_internal.h"
 #include <vector>
 #include <string.h>
@@ -63,6 +64,29 @@ extern "C" int hgpu_cram_uncompress_blocks_host(hgpu_ctx *ctx, const uint8_t *fi
             t_got.resize(t_in_off.size()); t_st.resize(t_in_off.size());
             int rc = hgpu_tok3_decode_batch_host(ctx, file, t_in_off.data(), t_in_len.data(), (uint32_t)t_in_off.size(),
                                                  tok_out.data(), t_out_off.data(), t_cap.data(), t_got.data(), t_st.data());
+            if (rc) return rc;
+        }
+    }
+
+    // ---- fqzcomp quality blocks (same arrangement: own entry point, own use of the staging buffer)
+    std::vector<uint64_t> f_in_off, f_out_off;
+    std::vector<uint32_t> f_in_len, f_cap, f_got;
+    std::vector<int32_t> f_st;
+    std::vector<uint8_t> fqz_out;                                             // copied into place after the big download below
+    {
+        uint64_t acc = 0;
+        for (uint32_t i : idx[7]) {
+            const hgpu_cram_block &b = blocks[i];
+            if (b.uncomp_size == 0) continue;
+            f_in_off.push_back(b.data_off); f_in_len.push_back(b.comp_size);
+            f_out_off.push_back(acc); f_cap.push_back(b.uncomp_size);
+            acc += ((uint64_t)b.uncomp_size + 15) & ~(uint64_t)15;
+        }
+        if (!f_in_off.empty()) {
+            fqz_out.resize(acc);
+            f_got.resize(f_in_off.size()); f_st.resize(f_in_off.size());
+            int rc = hgpu_fqz_decode_batch_host(ctx, file, f_in_off.data(), f_in_len.data(), (uint32_t)f_in_off.size(),
+                                                fqz_out.data(), f_out_off.data(), f_cap.data(), f_got.data(), f_st.data());
             if (rc) return rc;
         }
     }
@@ -143,7 +167,16 @@ extern "C" int hgpu_cram_uncompress_blocks_host(hgpu_ctx *ctx, const uint8_t *fi
         memcpy(out + out_off[i], file + b.data_off, m);
         got_len[i] = m;
     }
-    for (int m : {1, 2, 3, 7}) for (uint32_t i : idx[m]) status[i] = blocks[i].uncomp_size ? HGPU_CRAM_UNSUPPORTED : HGPU_OK;
+    for (int m : {1, 2, 3}) for (uint32_t i : idx[m]) status[i] = blocks[i].uncomp_size ? HGPU_CRAM_UNSUPPORTED : HGPU_OK;
+    {
+        size_t t = 0;
+        for (uint32_t i : idx[7]) {
+            if (blocks[i].uncomp_size == 0) continue;
+            if (f_st[t] != HGPU_OK) status[i] = HGPU_CRAM_ERR_DECODE;
+            else { memcpy(out + out_off[i], fqz_out.data() + f_out_off[t], f_got[t]); got_len[i] = f_got[t]; }
+            t++;
+        }
+    }
     {
         size_t t = 0;
         for (uint32_t i : idx[8]) {

@@ -23,7 +23,7 @@ constexpr int NAME_BUF = 256;                      // bytes of each of the two p
 #define TOK3_WARPS 2
 #endif
 #ifndef TOK3_MINB
-#define TOK3_MINB 1
+#define TOK3_MINB 16                               // 64 registers: 32 warps per SM; the kernel is issue-bound, more warps win
 #endif
 constexpr int WARPS = TOK3_WARPS;                  // name blocks per CTA
 

@@ -168,10 +168,11 @@ long hgpu_cram_scan_blocks(const uint8_t *file, uint64_t len, hgpu_cram_block *b
  * what hgpu_cram_scan_blocks returned for this file image; block i's data goes to out + out_off[i], a
  * slot of blocks[i].uncomp_size bytes.  One upload of the image, one CRC-32 launch over every block's
  * header+payload (:1585-1592), one batch launch per codec: method 4 rANS 4x8, 5 rANS Nx16, 6 adaptive
- * arithmetic, 8 tok3; RAW is a host copy.  status[i]: HGPU_OK; HGPU_CRAM_ERR_CRC (block CRC32 failure);
+ * arithmetic, 7 fqzcomp, 8 tok3; RAW is a host copy.  status[i]: HGPU_OK; HGPU_CRAM_ERR_CRC (block CRC32 failure);
  * HGPU_CRAM_ERR_DECODE (the reference returns -1: codec failure or size mismatch); HGPU_CRAM_ERR_SPACE
  * (a tok3 block longer than its uncomp_size field — the reference adopts the new size, a fixed slot
- * cannot); HGPU_CRAM_UNSUPPORTED for GZIP / BZIP2 / LZMA / FQZ blocks, which stay with the host library.
+ * cannot); HGPU_CRAM_UNSUPPORTED for GZIP / BZIP2 / LZMA blocks, which stay with the host library.  Method 7
+ * (FQZ) blocks go to the fqzcomp batch decoder.
  * got_len[i]: bytes written. */
 #define HGPU_CRAM_ERR_DECODE  (-1)
 #define HGPU_CRAM_ERR_CRC     (-2)
@@ -180,6 +181,21 @@ long hgpu_cram_scan_blocks(const uint8_t *file, uint64_t len, hgpu_cram_block *b
 int hgpu_cram_uncompress_blocks_host(hgpu_ctx *ctx, const uint8_t *file, uint64_t file_len,
         const hgpu_cram_block *blocks, uint32_t n, uint8_t *out, const uint64_t *out_off,
         uint32_t *got_len, int32_t *status);
+
+/* fqzcomp quality codec ("FQZ", CRAM 3.1 block method 7) — replaces fqz_decompress
+ * (htscodecs/htscodecs/fqzcomp_qual.c:1626 -> uncompress_block_fqz2f :1456-1613) as called from
+ * cram_uncompress_block (cram/cram_io.c:1684-1695) for a batch of quality blocks, HOST buffers.  The
+ * parameter blocks are read on the host; the 65 536 adaptive models of every stream are initialised by
+ * one coalesced kernel and each stream is then decoded by one thread (the range coder is sequential).
+ * out_cap[i] is the slot size (the CRAM block's uncomp_size); the stream's own size field decides how
+ * much is produced, as in the reference.  status[i]: HGPU_OK or HGPU_FQZ_ERR where it returns NULL. */
+#define HGPU_FQZ_ERR (-1)
+int hgpu_fqz_decode_batch_host(hgpu_ctx *ctx,
+        const uint8_t *in, const uint64_t *in_off, const uint32_t *in_len, uint32_t n,
+        uint8_t *out, const uint64_t *out_off, const uint32_t *out_cap,
+        uint32_t *got_len, int32_t *status);
+/* drop-in for the reference symbol (fqzcomp_qual.h:166); lengths/nlengths are not filled */
+char *fqz_decompress(char *in, size_t comp_size, size_t *uncomp_size, int *lengths, int nlengths);
 
 /* Read-name tokeniser ("tok3", CRAM 3.1 block method 8) — replaces tok3_decode_names
  * (htscodecs/htscodecs/tokenise_name3.c:1679-1834, tokenise_name3.h:59) as called per block from

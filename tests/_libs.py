@@ -358,3 +358,35 @@ def orc_tok3_decode(comp):
     res = C.string_at(p, n.value)
     o.orc_free(C.c_void_p(p))
     return res
+
+
+class FqzSlice(C.Structure):      # fqz_slice, htscodecs/htscodecs/fqzcomp_qual.h:59-63
+    _fields_ = [("num_records", C.c_int), ("len", C.POINTER(C.c_uint32)), ("flags", C.POINTER(C.c_uint32))]
+
+
+def ref_fqz_compress(quals, lens, flags=None, strat=0, vers=4):
+    """reference fqz_compress (fqzcomp_qual.c:1615): quals = concatenated quality bytes, lens = record lengths."""
+    r = ref()
+    r.fqz_compress.restype = C.c_void_p
+    n = len(lens)
+    la = (C.c_uint32 * n)(*lens); fa = (C.c_uint32 * n)(*(flags or [0] * n))
+    sl = FqzSlice(n, la, fa)
+    src = C.create_string_buffer(bytes(quals), len(quals) + 1)
+    m = C.c_size_t(0)
+    p = r.fqz_compress(C.c_int(vers), C.byref(sl), src, C.c_size_t(len(quals)), C.byref(m), C.c_int(strat), None)
+    assert p, "reference fqz_compress failed"
+    res = C.string_at(p, m.value)
+    C.CDLL(None).free(C.c_void_p(p))
+    return res
+
+
+def ref_fqz_decompress(comp):
+    r = ref()
+    r.fqz_decompress.restype = C.c_void_p
+    m = C.c_size_t(0)
+    p = r.fqz_decompress(buf(comp), C.c_size_t(len(comp)), C.byref(m), None, C.c_int(0))
+    if not p:
+        return None
+    res = C.string_at(p, m.value)
+    C.CDLL(None).free(C.c_void_p(p))
+    return res

@@ -21,7 +21,7 @@ r.hts_set_opt.argtypes = [C.c_void_p, C.c_int, C.c_char_p]
 CRAM_OPT_VERSION, CRAM_OPT_REFERENCE = 6, 9
 
 
-CRAM_OPT_SEQS_PER_SLICE, CRAM_OPT_USE_ARITH, HTS_OPT_COMPRESSION_LEVEL = 3, 26, 100
+CRAM_OPT_SEQS_PER_SLICE, CRAM_OPT_USE_FQZ, CRAM_OPT_USE_ARITH, HTS_OPT_COMPRESSION_LEVEL = 3, 25, 26, 100
 
 
 def write(version, name, reps=1, int_opts=()):
@@ -56,4 +56,5 @@ if __name__ == "__main__":
     write("3.0", "ce#1000.v30.cram")
     # adaptive-arithmetic blocks (method 6) and arith-coded tok3 streams, several slices; level 3 keeps the
     # bzip2-backed X_EXT methods out (oracle/_ref is built without libbz2)
+    write("3.1", "ce#1000.v31fqz.cram", int_opts=[(CRAM_OPT_USE_FQZ, 1), (HTS_OPT_COMPRESSION_LEVEL, 7)])   # fqzcomp quality blocks (method 7)
     write("3.1", "ce#1000.v31arith.cram", int_opts=[(CRAM_OPT_USE_ARITH, 1), (HTS_OPT_COMPRESSION_LEVEL, 3), (CRAM_OPT_SEQS_PER_SLICE, 300)])

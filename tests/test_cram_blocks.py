@@ -61,12 +61,13 @@ def _expect(img, b):
     if m == 4: return L.orc_rans_4x8_decode(comp, us)
     if m == 5: return L.orc_rans_nx16_decode(comp, us)
     if m == 6: return L.ref_arith(comp=comp, cap=us) if L.ref() is not None else None
+    if m == 7: return L.ref_fqz_decompress(comp) if L.ref() is not None else None
     if m == 8: return L.orc_tok3_decode(comp) if (comp[8] == 0 or L.ref() is not None) else None
     return None
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("name", ["ce#1000.v31.cram", "ce#1000.v30.cram", "ce#1000.v31arith.cram"])
+@pytest.mark.parametrize("name", ["ce#1000.v31.cram", "ce#1000.v30.cram", "ce#1000.v31arith.cram", "ce#1000.v31fqz.cram"])
 def test_uncompress_all_blocks_in_one_call(name):
     img = np.fromfile(os.path.join(GOLD, "htslib", name), dtype=np.uint8)
     ctx = H.Context(0)
@@ -74,7 +75,7 @@ def test_uncompress_all_blocks_in_one_call(name):
     seen = collections.Counter()
     for b, (st, data) in zip(blocks, res):
         m = int(b["method"])
-        if m in (1, 2, 3, 7):
+        if m in (1, 2, 3):
             assert st == -6                              # HGPU_CRAM_UNSUPPORTED: stays with the host library
             continue
         want = _expect(img, b)
@@ -85,6 +86,7 @@ def test_uncompress_all_blocks_in_one_call(name):
     if name.endswith("v31.cram"): assert seen[5] == 14 and seen[8] == 1
     if name.endswith("v30.cram"): assert seen[4] == 9
     if name.endswith("arith.cram") and ref() is not None: assert seen[6] == 30 and seen[8] == 4
+    if name.endswith("fqz.cram") and ref() is not None: assert seen[7] == 1
     # one flipped payload bit: that block fails its CRC (cram_io.c:1585-1592), every other block is unaffected
     victim = int(np.argmax(blocks["comp_size"]))
     bad = img.copy(); bad[int(blocks[victim]["data_off"]) + 5] ^= 0x10
