@@ -382,3 +382,65 @@ def fqz_decode(ctx, comps, caps):
     check(L.hgpu_fqz_decode_batch_host(ctx.h, p(blob), p(in_off), p(in_len), n, p(out), p(out_off), p(cap), p(got), p(st)),
           "fqz_decode_batch_host")
     return [(int(st[i]), out[int(out_off[i]):int(out_off[i]) + int(got[i])].tobytes()) for i in range(n)]
+
+
+def arith_encode(ctx, raws, orders, stream=0):
+    """Encode byte strings with the adaptive arithmetic coder on the device (hgpu_arith_encode_batch_dev).
+    Returns the compressed byte strings (None where the kernel reported failure)."""
+    import numpy as np
+    import torch
+    L = lib()
+    L.hgpu_arith_compress_bound.restype = C.c_uint32
+    L.hgpu_arith_compress_bound.argtypes = [C.c_uint32, C.c_int]
+    L.hgpu_arith_encode_batch_dev.argtypes = [C.c_void_p] * 5 + [C.c_uint32] + [C.c_void_p] * 5 + [C.c_uint32, C.c_void_p]
+    n = len(raws)
+    dev = torch.device("cuda", torch.cuda.current_device())
+    in_len = np.array([len(r) for r in raws], dtype=np.uint32)
+    in_off = np.concatenate([[0], np.cumsum(in_len.astype(np.int64))[:-1]]).astype(np.int64)
+    cap = np.array([L.hgpu_arith_compress_bound(int(l), int(o)) for l, o in zip(in_len, orders)], dtype=np.uint32)
+    out_off = np.concatenate([[0], np.cumsum((cap.astype(np.int64) + 15) // 16 * 16)[:-1]]).astype(np.int64)
+    blob = np.frombuffer(b"".join(raws) + b"\0" * 8, dtype=np.uint8).copy()
+    d_in = torch.from_numpy(blob).to(dev)
+    d_out = torch.zeros(int(out_off[-1]) + int(cap[-1]) + 64, dtype=torch.uint8, device=dev)
+    t = lambda a: torch.from_numpy(a).to(dev)
+    d_io, d_il, d_or = t(in_off), t(in_len.view(np.int32)), t(np.array(orders, dtype=np.int32))
+    d_oo, d_oc = t(out_off), t(cap.view(np.int32))
+    d_ol = torch.zeros(n, dtype=torch.int32, device=dev); d_st = torch.zeros(n, dtype=torch.int32, device=dev)
+    check(L.hgpu_arith_encode_batch_dev(ctx.h, d_in.data_ptr(), d_io.data_ptr(), d_il.data_ptr(), d_or.data_ptr(), n,
+                                        d_out.data_ptr(), d_oo.data_ptr(), d_oc.data_ptr(), d_ol.data_ptr(),
+                                        d_st.data_ptr(), int(in_len.max()) if n else 0, stream), "arith_encode_batch_dev")
+    torch.cuda.synchronize()
+    out = d_out.cpu().numpy(); ol = d_ol.cpu().numpy(); st = d_st.cpu().numpy()
+    return [out[int(o):int(o) + int(l)].tobytes() if s == 0 else None for o, l, s in zip(out_off, ol, st)]
+
+
+def _encode_list(ctx, fn, bound, raws, orders, stream, extra=()):
+    import numpy as np
+    import torch
+    n = len(raws)
+    dev = torch.device("cuda", torch.cuda.current_device())
+    in_len = np.array([len(r) for r in raws], dtype=np.uint32)
+    in_off = np.concatenate([[0], np.cumsum(in_len.astype(np.int64))[:-1]]).astype(np.int64)
+    cap = np.array([bound(int(l), int(o)) for l, o in zip(in_len, orders)], dtype=np.uint32)
+    out_off = np.concatenate([[0], np.cumsum((cap.astype(np.int64) + 15) // 16 * 16)[:-1]]).astype(np.int64)
+    blob = np.frombuffer(b"".join(raws) + b"\0" * 8, dtype=np.uint8).copy()
+    d_in = torch.from_numpy(blob).to(dev)
+    d_out = torch.zeros(int(out_off[-1]) + int(cap[-1]) + 64, dtype=torch.uint8, device=dev)
+    t = lambda a: torch.from_numpy(a).to(dev)
+    d_io, d_il, d_or = t(in_off), t(in_len.view(np.int32)), t(np.array(orders, dtype=np.int32))
+    d_oo, d_oc = t(out_off), t(cap.view(np.int32))
+    d_ol = torch.zeros(n, dtype=torch.int32, device=dev); d_st = torch.zeros(n, dtype=torch.int32, device=dev)
+    check(fn(ctx.h, d_in.data_ptr(), d_io.data_ptr(), d_il.data_ptr(), d_or.data_ptr(), n, d_out.data_ptr(), d_oo.data_ptr(),
+             d_oc.data_ptr(), d_ol.data_ptr(), d_st.data_ptr(), *extra, stream), "encode batch")
+    torch.cuda.synchronize()
+    out = d_out.cpu().numpy(); ol = d_ol.cpu().numpy(); st = d_st.cpu().numpy()
+    return [out[int(o):int(o) + int(l)].tobytes() if s == 0 else None for o, l, s in zip(out_off, ol, st)]
+
+
+def rans4x8_encode(ctx, raws, orders, stream=0):
+    """Encode byte strings with rANS 4x8 on the device (hgpu_rans4x8_encode_batch_dev)."""
+    L = lib()
+    L.hgpu_rans4x8_compress_bound.restype = C.c_uint32
+    L.hgpu_rans4x8_compress_bound.argtypes = [C.c_uint32]
+    L.hgpu_rans4x8_encode_batch_dev.argtypes = [C.c_void_p] * 5 + [C.c_uint32] + [C.c_void_p] * 6
+    return _encode_list(ctx, L.hgpu_rans4x8_encode_batch_dev, lambda l, o: L.hgpu_rans4x8_compress_bound(l), raws, orders, stream)

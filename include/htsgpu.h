@@ -147,6 +147,29 @@ int hgpu_arith_decode_batch_dev(hgpu_ctx *ctx,
         uint8_t *d_out, const uint64_t *d_out_off, const uint32_t *d_out_len,
         uint32_t *d_got_len, int32_t *d_status, uint32_t max_out_len, void *stream);
 
+/* rANS 4x8 ENCODE (CRAM 3.0 method 4) — stands where rans_compress stands (rANS_static.c:829-838;
+ * rans_compress_O0 :75-214, rans_compress_O1 :387-597) for a batch of streams, one thread per stream.
+ * order[i] bit 0 selects order-1.  Byte-identical to the reference encoder.  out_cap[i] >=
+ * hgpu_rans4x8_compress_bound(in_len[i]) (the reference's own allocation; the payload is written
+ * backwards from the end of that slot and moved down behind the table). */
+uint32_t hgpu_rans4x8_compress_bound(uint32_t size);
+int hgpu_rans4x8_encode_batch_dev(hgpu_ctx *ctx,
+        const uint8_t *d_in, const uint64_t *d_in_off, const uint32_t *d_in_len, const uint32_t *d_order,
+        uint32_t n, uint8_t *d_out, const uint64_t *d_out_off, const uint32_t *d_out_cap,
+        uint32_t *d_out_len, int32_t *d_status, void *stream);
+
+/* ARITH_PR ENCODE — stands where arith_compress_to stands (arith_dynamic.c:730-1026) for a batch of
+ * streams, one thread per stream.  order[i]: the reference's flag byte (bit 0 order-1, 0x40 RLE, 0x80
+ * PACK, 0x20 CAT, 0x10 NOSZ).  The output is byte-identical to the reference encoder's for the same
+ * flags, CAT fallback and dropped PACK bit included.  0x08 STRIPE is cleared (coded unstriped), 0x04
+ * EXT (bzip2) is an error.  out_cap[i] >= hgpu_arith_compress_bound(in_len[i], order[i]);
+ * max_in_len >= every in_len[i]. */
+uint32_t hgpu_arith_compress_bound(uint32_t size, int order);
+int hgpu_arith_encode_batch_dev(hgpu_ctx *ctx,
+        const uint8_t *d_in, const uint64_t *d_in_off, const uint32_t *d_in_len, const uint32_t *d_order,
+        uint32_t n, uint8_t *d_out, const uint64_t *d_out_off, const uint32_t *d_out_cap,
+        uint32_t *d_out_len, int32_t *d_status, uint32_t max_in_len, void *stream);
+
 /* CRAM 3.x framing on the host: walks containers and blocks (cram_read_container
  * cram/cram_io.c:3760, cram_read_block :1414-1483) of a file image and lists every block so the
  * payloads of all entropy-coded blocks can go to the batch decoders in one launch.  method: 0 RAW,
