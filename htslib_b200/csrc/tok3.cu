@@ -174,10 +174,27 @@ extern "C" int hgpu_tok3_decode_batch_host(hgpu_ctx *ctx, const uint8_t *in, con
                    o_descs = o_blocks + up((uint64_t)n * sizeof(Tok3Block)), o_jio = o_descs + up(descs.size() * sizeof(Tok3Desc)),
                    o_joo = o_jio + up((uint64_t)nj * 8), o_jil = o_joo + up((uint64_t)nj * 8), o_jol = o_jil + up((uint64_t)nj * 4),
                    o_jgot = o_jol + up((uint64_t)nj * 4), o_jst = o_jgot + up((uint64_t)nj * 4), o_olen = o_jst + up((uint64_t)nj * 4),
-                   o_st = o_olen + up((uint64_t)n * 4), total = o_st + up((uint64_t)n * 4);
+                   o_st = o_olen + up((uint64_t)n * 4), o_order = o_st + up((uint64_t)n * 4), total = o_order + up((uint64_t)n * 4);
     int rc = hgpu_ensure_stage(ctx, total + 256);
     if (rc) return rc;
     uint8_t *base = ctx->d_stage;
+    // blocks with at most 16 token positions (every Illumina-style block) share a warp in pairs; the rest,
+    // and the blocks the framing walk already rejected (their status still has to be written), take the
+    // general kernel.  order[] = [paired blocks ..., general blocks ...]
+    std::vector<uint32_t> order(n);
+    uint32_t n16 = 0, max_ndesc_gen = 16;
+    const bool h16_ok = arena < (1ull << 36) - 4096;                 // its shared-memory descriptors hold offsets in 16-byte units
+    for (uint32_t b = 0; b < n; b++)
+        if (h16_ok && blocks[b].host_status == HGPU_OK && blocks[b].max_tok <= TOK3_H16_MAX_TOK) order[n16++] = b;
+    {
+        uint32_t g = n16;
+        for (uint32_t b = 0; b < n; b++)
+            if (!(h16_ok && blocks[b].host_status == HGPU_OK && blocks[b].max_tok <= TOK3_H16_MAX_TOK)) {
+                order[g++] = b;
+                if (blocks[b].host_status == HGPU_OK && blocks[b].max_tok * 16 > max_ndesc_gen) max_ndesc_gen = blocks[b].max_tok * 16;
+            }
+    }
+    (void)max_ndesc;
     cudaStream_t s = ctx->stream;
     std::vector<uint64_t> jio(nj), joo(nj);
     std::vector<uint32_t> jil(nj), jol(nj);
@@ -211,8 +228,14 @@ extern "C" int hgpu_tok3_decode_batch_host(hgpu_ctx *ctx, const uint8_t *in, con
         if (rc) return rc;
     }
     cudaEventRecord(tev[1], s);
-    rc = hgpu_launch_tok3_names(ctx, (const Tok3Block *)(base + o_blocks), n, max_ndesc, (const Tok3Desc *)(base + o_descs), base + o_arena,
-                                d_jst, d_jgot, d_jol, (uint2 *)(base + o_hist), (uint4 *)(base + o_names),
+    if (hgpu_check(cudaMemcpyAsync(base + o_order, order.data(), (size_t)n * 4, cudaMemcpyHostToDevice, s), "H2D")) return HGPU_ERR_CUDA;
+    const uint32_t *d_order = (const uint32_t *)(base + o_order);
+    rc = hgpu_launch_tok3_names_h16(ctx, (const Tok3Block *)(base + o_blocks), d_order, n16, (const Tok3Desc *)(base + o_descs), base + o_arena,
+                                    d_jst, d_jgot, d_jol, (uint2 *)(base + o_hist), (uint4 *)(base + o_names),
+                                    base + o_out, (uint32_t *)(base + o_olen), (int32_t *)(base + o_st), s);
+    if (rc) return rc;
+    rc = hgpu_launch_tok3_names(ctx, (const Tok3Block *)(base + o_blocks), d_order + n16, n - n16, max_ndesc_gen, (const Tok3Desc *)(base + o_descs),
+                                base + o_arena, d_jst, d_jgot, d_jol, (uint2 *)(base + o_hist), (uint4 *)(base + o_names),
                                 base + o_out, (uint32_t *)(base + o_olen), (int32_t *)(base + o_st), s);
     if (rc) return rc;
     cudaEventRecord(tev[2], s);

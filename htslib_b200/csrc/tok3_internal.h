@@ -26,8 +26,16 @@ struct Tok3Block {
     int32_t  host_status;                          // framing already rejected on the host
 };
 
-// max_ndesc: the largest max_tok*16 in the batch (sizes the per-warp shared-memory tables)
-int hgpu_launch_tok3_names(hgpu_ctx *ctx, const Tok3Block *d_blocks, uint32_t n, uint32_t max_ndesc,
+// The general kernel: one warp per block, any number of token positions.  d_order[0..n): the blocks to
+// run; max_ndesc: the largest max_tok*16 among them (sizes the per-warp shared-memory tables).
+int hgpu_launch_tok3_names(hgpu_ctx *ctx, const Tok3Block *d_blocks, const uint32_t *d_order, uint32_t n, uint32_t max_ndesc,
                            const Tok3Desc *d_descs, const uint8_t *d_arena, const int32_t *d_job_status,
                            const uint32_t *d_job_got, const uint32_t *d_job_want, uint2 *d_hist, uint4 *d_names,
                            uint8_t *d_out, uint32_t *d_out_len, int32_t *d_status, cudaStream_t st);
+// The common case, blocks with at most 16 token positions (max_tok <= 17): TWO blocks per warp, one per
+// half-warp, sharing one instruction stream (tok3_names_h16.cu).
+constexpr uint32_t TOK3_H16_MAX_TOK = 17;
+int hgpu_launch_tok3_names_h16(hgpu_ctx *ctx, const Tok3Block *d_blocks, const uint32_t *d_order, uint32_t n,
+                               const Tok3Desc *d_descs, const uint8_t *d_arena, const int32_t *d_job_status,
+                               const uint32_t *d_job_got, const uint32_t *d_job_want, uint2 *d_hist, uint4 *d_names,
+                               uint8_t *d_out, uint32_t *d_out_len, int32_t *d_status, cudaStream_t st);

@@ -57,14 +57,15 @@ __device__ __forceinline__ int window_byte(const uint8_t *arena, const Tok3Desc 
 
 __constant__ uint32_t c_p10[10] = {1, 10, 100, 1000, 10000, 100000, 1000000, 10000000, 100000000, 1000000000};
 
-__global__ void __launch_bounds__(32 * WARPS, TOK3_MINB) tok3_names_kernel(const Tok3Block *blocks, uint32_t nblocks, uint32_t max_ndesc,
-        const Tok3Desc *descs, const uint8_t *arena, const int32_t *job_status, const uint32_t *job_got,
+__global__ void __launch_bounds__(32 * WARPS, TOK3_MINB) tok3_names_kernel(const Tok3Block *blocks, const uint32_t *order, uint32_t nblocks,
+        uint32_t max_ndesc, const Tok3Desc *descs, const uint8_t *arena, const int32_t *job_status, const uint32_t *job_got,
         const uint32_t *job_want, uint2 *hist_all, uint4 *names_all, uint8_t *out, uint32_t *out_len, int32_t *status)
 {
     extern __shared__ uint4 smem4[];
     const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const uint32_t b = blockIdx.x * WARPS + warp;
-    if (b >= nblocks) return;                                      // warps never synchronise with each other
+    const uint32_t slot = blockIdx.x * WARPS + warp;
+    if (slot >= nblocks) return;                                   // warps never synchronise with each other
+    const uint32_t b = order[slot];                                // the blocks this kernel was given (those with > 16 token positions)
     uint4 *dsc = smem4 + (size_t)warp * max_ndesc;
     uint32_t *cur = reinterpret_cast<uint32_t *>(smem4 + (size_t)WARPS * max_ndesc) + (size_t)warp * max_ndesc;
     uint8_t *nbuf = reinterpret_cast<uint8_t *>(reinterpret_cast<uint32_t *>(smem4 + (size_t)WARPS * max_ndesc) + (size_t)WARPS * max_ndesc) +
@@ -382,7 +383,7 @@ __global__ void __launch_bounds__(32 * WARPS, TOK3_MINB) tok3_names_kernel(const
 
 }  // namespace
 
-int hgpu_launch_tok3_names(hgpu_ctx *ctx, const Tok3Block *d_blocks, uint32_t n, uint32_t max_ndesc,
+int hgpu_launch_tok3_names(hgpu_ctx *ctx, const Tok3Block *d_blocks, const uint32_t *d_order, uint32_t n, uint32_t max_ndesc,
                            const Tok3Desc *d_descs, const uint8_t *d_arena, const int32_t *d_job_status,
                            const uint32_t *d_job_got, const uint32_t *d_job_want, uint2 *d_hist, uint4 *d_names,
                            uint8_t *d_out, uint32_t *d_out_len, int32_t *d_status, cudaStream_t st)
@@ -397,7 +398,7 @@ int hgpu_launch_tok3_names(hgpu_ctx *ctx, const Tok3Block *d_blocks, uint32_t n,
             return HGPU_ERR_CUDA;
         smem_set = smem;
     }
-    tok3_names_kernel<<<(n + WARPS - 1) / WARPS, 32 * WARPS, smem, st>>>(d_blocks, n, max_ndesc, d_descs, d_arena, d_job_status,
+    tok3_names_kernel<<<(n + WARPS - 1) / WARPS, 32 * WARPS, smem, st>>>(d_blocks, d_order, n, max_ndesc, d_descs, d_arena, d_job_status,
                                                                         d_job_got, d_job_want, d_hist, d_names, d_out, d_out_len, d_status);
     hgpu_count_launch();
     return hgpu_check(cudaGetLastError(), "tok3_names_kernel");
