@@ -444,3 +444,24 @@ def rans4x8_encode(ctx, raws, orders, stream=0):
     L.hgpu_rans4x8_compress_bound.argtypes = [C.c_uint32]
     L.hgpu_rans4x8_encode_batch_dev.argtypes = [C.c_void_p] * 5 + [C.c_uint32] + [C.c_void_p] * 6
     return _encode_list(ctx, L.hgpu_rans4x8_encode_batch_dev, lambda l, o: L.hgpu_rans4x8_compress_bound(l), raws, orders, stream)
+
+
+def tok3_encode(ctx, blobs):
+    """Encode name blocks (each a NUL/LF separated blob) with hgpu_tok3_encode_batch_host; returns [(status, bytes)]."""
+    import numpy as np
+    L = lib()
+    L.hgpu_tok3_compress_bound.restype = C.c_uint32
+    L.hgpu_tok3_compress_bound.argtypes = [C.c_uint32]
+    L.hgpu_tok3_encode_batch_host.argtypes = [C.c_void_p] * 4 + [C.c_uint32] + [C.c_void_p] * 5
+    n = len(blobs)
+    in_len = np.array([len(c) for c in blobs], dtype=np.uint32)
+    in_off = np.concatenate([[0], np.cumsum(in_len.astype(np.uint64))[:-1]]).astype(np.uint64)
+    blob = np.frombuffer(b"".join(blobs) + b"\0" * 8, dtype=np.uint8)
+    cap = np.array([L.hgpu_tok3_compress_bound(int(l)) for l in in_len], dtype=np.uint32)
+    out_off = np.concatenate([[0], np.cumsum(cap.astype(np.uint64))[:-1]]).astype(np.uint64)
+    out = np.zeros(int(cap.astype(np.uint64).sum()) + 8, dtype=np.uint8)
+    got = np.zeros(n, dtype=np.uint32); st = np.zeros(n, dtype=np.int32)
+    p = lambda a: a.ctypes.data_as(C.c_void_p)
+    check(L.hgpu_tok3_encode_batch_host(ctx.h, p(blob), p(in_off), p(in_len), n, p(out), p(out_off), p(cap), p(got), p(st)),
+          "tok3_encode_batch_host")
+    return [(int(st[i]), out[int(out_off[i]):int(out_off[i]) + int(got[i])].tobytes()) for i in range(n)]

@@ -234,6 +234,20 @@ int hgpu_tok3_decode_batch_host(hgpu_ctx *ctx,
         const uint8_t *in, const uint64_t *in_off, const uint32_t *in_len, uint32_t n,
         uint8_t *out, const uint64_t *out_off, const uint32_t *out_cap,
         uint32_t *out_len, int32_t *status);
+/* tok3 ENCODE — stands where tok3_encode_names stands (tokenise_name3.c:1451-1665) as called from
+ * cram_compress_by_method (cram/cram_io.c:1885-1899), for a batch of name blocks with HOST buffers.
+ * Block i is in[in_off[i] .. +in_len[i]): names each ended by NUL or LF (an unterminated tail is left
+ * out, as in the reference).  The output is a complete tok3 block (use_arith = 0) that the reference's
+ * tok3_decode_names and hgpu_tok3_decode_batch_host rebuild to the NUL-separated names; its bytes are
+ * not the reference encoder's (every name is diffed against the previous one, token streams are coded
+ * by this library's rANS Nx16 encoder, order 0 / order 1 whichever is smaller).  out_cap[i] >=
+ * hgpu_tok3_compress_bound(in_len[i]).  status[i]: HGPU_OK, or HGPU_TOK3_ERR (empty block, a name
+ * with more than 126 tokens or longer than 65535 bytes, slot too small). */
+uint32_t hgpu_tok3_compress_bound(uint32_t in_len);
+int hgpu_tok3_encode_batch_host(hgpu_ctx *ctx,
+        const uint8_t *in, const uint64_t *in_off, const uint32_t *in_len, uint32_t n,
+        uint8_t *out, const uint64_t *out_off, const uint32_t *out_cap,
+        uint32_t *out_len, int32_t *status);
 /* device milliseconds of the last call: ms2[0] token-stream entropy decode, ms2[1] name rebuild */
 void hgpu_tok3_last_ms(float *ms2);
 /* drop-in for the reference symbol itself: one block, malloc'd result, NULL on failure */
