@@ -417,16 +417,15 @@ extern "C" int hgpu_fqz_decode_batch_host(hgpu_ctx *ctx, const uint8_t *in, cons
 
 // Drop-in for the reference symbol (fqzcomp_qual.h): malloc'd result or NULL.  lengths/nlengths as in the
 // reference are not filled (cram_uncompress_block passes NULL, 0).
-static std::mutex g_fqz_mu;
-static hgpu_ctx *g_fqz_ctx;
+namespace { struct ShimLock { ShimLock() { hgpu_shim_lock(); } ~ShimLock() { hgpu_shim_unlock(); } }; }
 extern "C" char *fqz_decompress(char *in, size_t comp_size, size_t *uncomp_size, int *lengths, int nlengths)
 {
     (void)lengths; (void)nlengths;
     if (!in || !uncomp_size || comp_size > 0xffffffffull) return nullptr;
     uint32_t ulen = 0;
     h_vget((const uint8_t *)in, (const uint8_t *)in + comp_size, &ulen);
-    std::lock_guard<std::mutex> lock(g_fqz_mu);
-    if (!g_fqz_ctx) g_fqz_ctx = hgpu_create(-1);
+    ShimLock lock;
+    hgpu_ctx *g_fqz_ctx = hgpu_shim_ctx();
     if (!g_fqz_ctx) return nullptr;
     uint8_t *out = (uint8_t *)malloc(ulen ? ulen : 1);
     if (!out) return nullptr;

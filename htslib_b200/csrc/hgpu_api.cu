@@ -385,6 +385,10 @@ static hgpu_ctx *shim_ctx()
     if (!g_shim_ctx) g_shim_ctx = hgpu_create(-1);
     return g_shim_ctx;
 }
+// the same process-wide context and lock for the reference-named shims that live in other files
+void hgpu_shim_lock() { g_shim_mu.lock(); }
+void hgpu_shim_unlock() { g_shim_mu.unlock(); }
+hgpu_ctx *hgpu_shim_ctx() { return shim_ctx(); }
 
 // varint as written by var_put_u32 (varint.h:206): big-endian 7-bit groups
 static int h_vget(const unsigned char *p, const unsigned char *end, unsigned int *v)

@@ -32,6 +32,10 @@ int  hgpu_ensure_stage(hgpu_ctx *ctx, size_t bytes);
 int  hgpu_ensure_mrec(hgpu_ctx *ctx, size_t bytes);
 int  hgpu_ensure_bam(hgpu_ctx *ctx, size_t bytes);
 int  hgpu_ensure_pinned(hgpu_ctx *ctx, size_t bytes);
+// process-wide context of the reference-named shims (one batch at a time); call between lock/unlock
+void hgpu_shim_lock();
+void hgpu_shim_unlock();
+hgpu_ctx *hgpu_shim_ctx();
 // a zeroed (stream-ordered) work counter; slots rotate so launches in flight on different streams never share one
 uint32_t *hgpu_take_counter(hgpu_ctx *ctx, cudaStream_t st);
 

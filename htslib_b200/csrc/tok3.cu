@@ -215,7 +215,11 @@ extern "C" int hgpu_tok3_decode_batch_host(hgpu_ctx *ctx, const uint8_t *in, con
     const uint32_t *d_jil = (const uint32_t *)(base + o_jil), *d_jol = (const uint32_t *)(base + o_jol);
     uint32_t *d_jgot = (uint32_t *)(base + o_jgot);
     int32_t *d_jst = (int32_t *)(base + o_jst);
-    cudaEvent_t tev[3];
+    struct Events {                                                  // released on every return path
+        cudaEvent_t e[3] = {nullptr, nullptr, nullptr};
+        ~Events() { for (cudaEvent_t x : e) if (x) cudaEventDestroy(x); }
+    } evs;
+    cudaEvent_t *tev = evs.e;
     for (int k = 0; k < 3; k++) if (hgpu_check(cudaEventCreate(&tev[k]), "event")) return HGPU_ERR_CUDA;
     cudaEventRecord(tev[0], s);
     if (nr) {
@@ -245,7 +249,6 @@ extern "C" int hgpu_tok3_decode_batch_host(hgpu_ctx *ctx, const uint8_t *in, con
     if (hgpu_check(cudaStreamSynchronize(s), "sync")) return HGPU_ERR_CUDA;
     cudaEventElapsedTime(&g_tok3_ms[0], tev[0], tev[1]);
     cudaEventElapsedTime(&g_tok3_ms[1], tev[1], tev[2]);
-    for (int k = 0; k < 3; k++) cudaEventDestroy(tev[k]);
     return HGPU_OK;
 }
 
@@ -253,15 +256,14 @@ extern "C" int hgpu_tok3_decode_batch_host(hgpu_ctx *ctx, const uint8_t *in, con
 extern "C" void hgpu_tok3_last_ms(float *ms2) { ms2[0] = g_tok3_ms[0]; ms2[1] = g_tok3_ms[1]; }
 
 // Drop-in for the reference symbol (tokenise_name3.h:59): one block, malloc'd result, NULL on failure.
-static std::mutex g_tok3_mu;
-static hgpu_ctx *g_tok3_ctx;
+namespace { struct ShimLock { ShimLock() { hgpu_shim_lock(); } ~ShimLock() { hgpu_shim_unlock(); } }; }
 extern "C" uint8_t *tok3_decode_names(uint8_t *in, uint32_t sz, uint32_t *out_len)
 {
     if (!in || !out_len) return nullptr;
     uint32_t cap = hgpu_tok3_out_bound(in, sz);
     if (!cap) return nullptr;
-    std::lock_guard<std::mutex> lock(g_tok3_mu);
-    if (!g_tok3_ctx) g_tok3_ctx = hgpu_create(-1);
+    ShimLock lock;
+    hgpu_ctx *g_tok3_ctx = hgpu_shim_ctx();
     if (!g_tok3_ctx) return nullptr;
     uint8_t *out = (uint8_t *)malloc(cap);
     if (!out) return nullptr;

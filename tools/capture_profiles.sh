@@ -15,3 +15,6 @@ ncu --set full --clock-control none --import-source on -k regex:rans_nx16_decode
 ncu --set full --clock-control none -k regex:bam_unpack_kernel -c 1 -o $O/${TAG}_bam \
     python bench.py --gb 1 --steps 1 --warmup 1 --no-e2e --no-cpu-baseline --rans-slices 0 > $O/${TAG}_bam_bench.log 2>&1
 ls -la $O
+# 3. the tok3 name-rebuild kernel (two blocks per warp), bench leg only
+ncu --set full --clock-control none --import-source on -k regex:tok3_names -s 1 -c 1 -o $O/${TAG}_tok3 \
+    python bench.py --gb 0.5 --steps 1 --warmup 1 --no-e2e --no-cpu-baseline --rans-slices 0 --tok3-blocks 4736 > $O/${TAG}_tok3_bench.log 2>&1
