@@ -465,3 +465,28 @@ def tok3_encode(ctx, blobs):
     check(L.hgpu_tok3_encode_batch_host(ctx.h, p(blob), p(in_off), p(in_len), n, p(out), p(out_off), p(cap), p(got), p(st)),
           "tok3_encode_batch_host")
     return [(int(st[i]), out[int(out_off[i]):int(out_off[i]) + int(got[i])].tobytes()) for i in range(n)]
+
+
+def fqz_encode(ctx, quals, rec_lens, strat=0):
+    """Encode quality blocks with fqzcomp on the device (hgpu_fqz_encode_batch_host).
+    quals[i]: concatenated qualities of block i; rec_lens[i]: its record lengths.  Returns [(status, bytes)]."""
+    import numpy as np
+    L = lib()
+    L.hgpu_fqz_compress_bound.restype = C.c_uint32
+    L.hgpu_fqz_compress_bound.argtypes = [C.c_uint32, C.c_uint32]
+    L.hgpu_fqz_encode_batch_host.argtypes = [C.c_void_p] * 7 + [C.c_uint32, C.c_int] + [C.c_void_p] * 5
+    n = len(quals)
+    in_len = np.array([len(q) for q in quals], dtype=np.uint32)
+    in_off = np.concatenate([[0], np.cumsum(in_len.astype(np.uint64))[:-1]]).astype(np.uint64)
+    blob = np.frombuffer(b"".join(quals) + b"\0" * 8, dtype=np.uint8)
+    nrec = np.array([len(r) for r in rec_lens], dtype=np.uint32)
+    rec_off = np.concatenate([[0], np.cumsum(nrec.astype(np.uint64))[:-1]]).astype(np.uint64)
+    rec = np.array([x for r in rec_lens for x in r] + [0], dtype=np.uint32)
+    cap = np.array([L.hgpu_fqz_compress_bound(int(a), int(b)) for a, b in zip(in_len, nrec)], dtype=np.uint32)
+    out_off = np.concatenate([[0], np.cumsum((cap.astype(np.uint64) + 15) // 16 * 16)[:-1]]).astype(np.uint64)
+    out = np.zeros(int(out_off[-1] + cap[-1]) + 16, dtype=np.uint8)
+    got = np.zeros(n, dtype=np.uint32); st = np.zeros(n, dtype=np.int32)
+    p = lambda a: a.ctypes.data_as(C.c_void_p)
+    check(L.hgpu_fqz_encode_batch_host(ctx.h, p(blob), p(in_off), p(in_len), p(rec), p(rec_off), p(nrec), n, strat,
+                                       p(out), p(out_off), p(cap), p(got), p(st)), "fqz_encode_batch_host")
+    return [(int(st[i]), out[int(out_off[i]):int(out_off[i]) + int(got[i])].tobytes()) for i in range(n)]

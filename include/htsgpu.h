@@ -217,6 +217,19 @@ int hgpu_fqz_decode_batch_host(hgpu_ctx *ctx,
         const uint8_t *in, const uint64_t *in_off, const uint32_t *in_len, uint32_t n,
         uint8_t *out, const uint64_t *out_off, const uint32_t *out_cap,
         uint32_t *got_len, int32_t *status);
+/* fqzcomp ENCODE — stands where fqz_compress stands (fqzcomp_qual.c:1615 -> compress_block_fqz2f
+ * :1004-1239; cram_compress_by_method cram/cram_io.c:1804-1825) for a batch of quality blocks, HOST
+ * buffers.  Block i is in[in_off[i] .. +in_len[i]) = the concatenated qualities of nrec[i] records whose
+ * lengths are rec_len[rec_off[i] ..] (they must tile the block, as fqz_slice::len does).  strat 0..3
+ * selects the reference's strategy row (strat_opts, :195-201).  The output decodes to the input with the
+ * reference's fqz_decompress and with hgpu_fqz_decode_batch_host; it is one parameter block without a
+ * selector, so its bytes are not the reference encoder's when that would split the records.
+ * out_cap[i] >= hgpu_fqz_compress_bound(in_len[i], nrec[i]). */
+uint32_t hgpu_fqz_compress_bound(uint32_t in_len, uint32_t nrec);
+int hgpu_fqz_encode_batch_host(hgpu_ctx *ctx,
+        const uint8_t *in, const uint64_t *in_off, const uint32_t *in_len,
+        const uint32_t *rec_len, const uint64_t *rec_off, const uint32_t *nrec, uint32_t n, int strat,
+        uint8_t *out, const uint64_t *out_off, const uint32_t *out_cap, uint32_t *out_len, int32_t *status);
 /* drop-in for the reference symbol (fqzcomp_qual.h:166); lengths/nlengths are not filled */
 char *fqz_decompress(char *in, size_t comp_size, size_t *uncomp_size, int *lengths, int nlengths);
 
