@@ -11,7 +11,7 @@
 // Model layout follows the reference bit for bit, because the approximate sort order of the
 // symbol array (swap-with-previous after each update, halving at 65519) is part of the format.
 // Parity: golden streams htscodecs/tests/dat/arith/* and the compiled reference (oracle/_ref) on
-// seeded inputs — there is no separate CPU restatement of this codec under oracle/.
+// seeded inputs; the CPU restatement oracle/orc_arith.c is pinned on the same fixtures.
 #include "hgpu_internal.h"
 
 namespace {

@@ -390,3 +390,27 @@ def ref_fqz_decompress(comp):
     res = C.string_at(p, m.value)
     C.CDLL(None).free(C.c_void_p(p))
     return res
+
+
+def orc_fqz_decode(comp):
+    """oracle fqzcomp decode (oracle/orc_fqz.c)."""
+    o = orc()
+    o.orc_fqz_decode.restype = C.c_void_p
+    o.orc_fqz_decode.argtypes = [C.c_void_p, C.c_size_t, C.POINTER(C.c_size_t)]
+    m = C.c_size_t(0)
+    b = buf(comp)
+    p = o.orc_fqz_decode(C.cast(b, C.c_void_p), len(comp), C.byref(m))
+    if not p:
+        return None
+    res = C.string_at(p, m.value)
+    o.orc_free(C.c_void_p(p))
+    return res
+
+
+def orc_arith_decode(comp, cap):
+    """oracle adaptive-arithmetic decode (oracle/orc_arith.c); cap as arith_uncompress_to's *out_size."""
+    o = orc()
+    out = (C.c_uint8 * max(1, cap))()
+    n = C.c_uint32(cap)
+    rc = o.orc_arith_decode(buf(comp), C.c_uint32(len(comp)), out, C.byref(n))
+    return None if rc != 0 else bytes(out[: n.value])

@@ -1,7 +1,8 @@
 """GPU parity: arith_dynamic (CRAM 3.1 method 6) decode.  Checked against the reference's golden
 streams (htscodecs/tests/dat/arith/*: the decode must equal the raw input, as arith.test does) and
 against the compiled reference on seeded inputs for every format-byte combination; the checker here
-is the unmodified reference itself (oracle/_ref) — there is no separate restatement of this codec."""
+is the unmodified reference itself (oracle/_ref); oracle/orc_arith.c is pinned on the same fixtures in
+tests/test_oracle_arith.py."""
 import glob, os, random
 import pytest
 import htslib_b200 as H

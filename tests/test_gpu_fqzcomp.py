@@ -1,9 +1,8 @@
 """GPU parity: fqzcomp quality decode (CRAM 3.1 block method 7).  Checked against the reference's golden
 streams (htscodecs/tests/dat/fqzcomp/*: the decode must equal column 1 of dat/q*, minus 33, as
 tests/fqzcomp.test does) and against the compiled reference (oracle/_ref) on seeded inputs for every
-strategy, with duplicates, reversed records, variable lengths and corrupted streams.  As for the adaptive
-arithmetic coder there is no separate CPU restatement of this codec under oracle/; the checker is the
-unmodified reference."""
+strategy, with duplicates, reversed records, variable lengths and corrupted streams; oracle/orc_fqz.c is
+pinned on the same fixtures in tests/test_oracle_fqz.py."""
 import glob
 import os
 import random
