@@ -91,6 +91,38 @@ extern "C" int hgpu_cram_uncompress_blocks_host(hgpu_ctx *ctx, const uint8_t *fi
         }
     }
 
+    // ---- GZIP blocks (method 1, zlib_mem_inflate cram_io.c:1068-1157) that fit one BGZF block: a gzip member with the
+    // plain 10-byte header is header + raw DEFLATE + CRC32 + ISIZE, and CRC32 + ISIZE is exactly the BGZF footer, so
+    // swapping the header for the 18-byte BGZF one hands it to the BGZF inflate kernel.  Larger or unusual members
+    // (FEXTRA / FNAME ..., > 64 KiB) stay HGPU_CRAM_UNSUPPORTED.
+    std::vector<uint32_t> gz_idx;
+    std::vector<uint8_t> gz_in, gz_out;
+    std::vector<uint64_t> g_in_off, g_out_off;
+    std::vector<uint32_t> g_in_len, g_cap, g_got;
+    std::vector<int32_t> g_st;
+    for (uint32_t i : idx[1]) {
+        const hgpu_cram_block &b = blocks[i];
+        const uint8_t *c = file + b.data_off;
+        if (b.uncomp_size == 0 || b.uncomp_size > 65536 || b.comp_size < 18 || (uint64_t)b.comp_size + 8 > 65536) continue;
+        if (c[0] != 0x1f || c[1] != 0x8b || c[2] != 8 || c[3] != 0) continue;
+        const uint32_t total = b.comp_size + 8;
+        static const uint8_t hdr[16] = {0x1f, 0x8b, 8, 4, 0, 0, 0, 0, 0, 0xff, 6, 0, 'B', 'C', 2, 0};
+        g_in_off.push_back(gz_in.size()); g_in_len.push_back(total);
+        g_out_off.push_back((uint64_t)gz_idx.size() * 65536); g_cap.push_back(65536);
+        gz_in.insert(gz_in.end(), hdr, hdr + 16);
+        gz_in.push_back((uint8_t)((total - 1) & 0xff)); gz_in.push_back((uint8_t)((total - 1) >> 8));
+        gz_in.insert(gz_in.end(), c + 10, c + b.comp_size);              // DEFLATE payload and the CRC32 + ISIZE trailer
+        gz_idx.push_back(i);
+    }
+    if (!gz_idx.empty()) {
+        gz_in.resize(gz_in.size() + 16);
+        gz_out.resize((size_t)gz_idx.size() * 65536);
+        g_got.resize(gz_idx.size()); g_st.resize(gz_idx.size());
+        int rc = hgpu_bgzf_inflate_blocks_host(ctx, gz_in.data(), g_in_off.data(), g_in_len.data(), (uint32_t)gz_idx.size(),
+                                               gz_out.data(), g_out_off.data(), g_cap.data(), g_got.data(), g_st.data());
+        if (rc) return rc;
+    }
+
     // ---- device staging: file image, the output span (same layout as the caller's), job arrays
     std::vector<uint32_t> order;                                              // job order: 4x8, Nx16, arith
     for (int m : {4, 5, 6}) for (uint32_t i : idx[m]) if (blocks[i].uncomp_size) order.push_back(i);
@@ -168,6 +200,11 @@ extern "C" int hgpu_cram_uncompress_blocks_host(hgpu_ctx *ctx, const uint8_t *fi
         got_len[i] = m;
     }
     for (int m : {1, 2, 3}) for (uint32_t i : idx[m]) status[i] = blocks[i].uncomp_size ? HGPU_CRAM_UNSUPPORTED : HGPU_OK;
+    for (size_t t = 0; t < gz_idx.size(); t++) {                              // the GZIP blocks that went through the BGZF kernel
+        const uint32_t i = gz_idx[t];
+        if (g_st[t] != HGPU_OK || g_got[t] != blocks[i].uncomp_size) status[i] = HGPU_CRAM_ERR_DECODE;
+        else { memcpy(out + out_off[i], gz_out.data() + g_out_off[t], g_got[t]); got_len[i] = g_got[t]; status[i] = HGPU_OK; }
+    }
     {
         size_t t = 0;
         for (uint32_t i : idx[7]) {

@@ -194,8 +194,10 @@ long hgpu_cram_scan_blocks(const uint8_t *file, uint64_t len, hgpu_cram_block *b
  * arithmetic, 7 fqzcomp, 8 tok3; RAW is a host copy.  status[i]: HGPU_OK; HGPU_CRAM_ERR_CRC (block CRC32 failure);
  * HGPU_CRAM_ERR_DECODE (the reference returns -1: codec failure or size mismatch); HGPU_CRAM_ERR_SPACE
  * (a tok3 block longer than its uncomp_size field — the reference adopts the new size, a fixed slot
- * cannot); HGPU_CRAM_UNSUPPORTED for GZIP / BZIP2 / LZMA blocks, which stay with the host library.  Method 7
- * (FQZ) blocks go to the fqzcomp batch decoder.
+ * cannot); HGPU_CRAM_UNSUPPORTED for BZIP2 / LZMA blocks and for GZIP blocks that are not one plain gzip member
+ * of at most 64 KiB, which stay with the host library (small GZIP blocks — compression headers, tiny data
+ * series — are re-framed as BGZF blocks and go through the BGZF inflate kernel).  Method 7 (FQZ) blocks go to
+ * the fqzcomp batch decoder.
  * got_len[i]: bytes written. */
 #define HGPU_CRAM_ERR_DECODE  (-1)
 #define HGPU_CRAM_ERR_CRC     (-2)
