@@ -356,6 +356,29 @@ int hgpu_bam_layout_dev(hgpu_ctx *ctx, const uint8_t *d_stream, uint64_t len,
 unsigned char *rans_uncompress_to_4x16(unsigned char *in, unsigned int in_size,
                                        unsigned char *out, unsigned int *out_size);
 unsigned char *rans_uncompress_4x16(unsigned char *in, unsigned int in_size, unsigned int *out_size);
+/* the rest of the libhtscodecs seam (shims.cu): one stream per call through the batch kernels.
+ * rANS 4x8 (rANS_static.h:40-43) — encoder byte-identical to the reference */
+unsigned char *rans_uncompress(unsigned char *in, unsigned int in_size, unsigned int *out_size);
+unsigned char *rans_compress(unsigned char *in, unsigned int in_size, unsigned int *out_size, int order);
+/* adaptive arithmetic coder (arith_dynamic.h:40-55) — encoder byte-identical except that X_STRIPE is
+ * dropped (coded unstriped) and X_EXT (bzip2) fails */
+unsigned int   arith_compress_bound(unsigned int size, int order);
+unsigned char *arith_compress_to(unsigned char *in, unsigned int in_size, unsigned char *out, unsigned int *out_size, int order);
+unsigned char *arith_compress(unsigned char *in, unsigned int in_size, unsigned int *out_size, int order);
+unsigned char *arith_uncompress_to(unsigned char *in, unsigned int in_size, unsigned char *out, unsigned int *out_size);
+unsigned char *arith_uncompress(unsigned char *in, unsigned int in_size, unsigned int *out_size);
+/* rANS Nx16 encode (rANS_static4x16.h:41-50, :64): order bit 0 (order-1) and bit 2 (32-way) are honoured,
+ * the PACK / RLE / STRIPE bits are not acted on; streams decode with any rans_uncompress_to_4x16 */
+unsigned int   rans_compress_bound_4x16(unsigned int size, int order);
+unsigned char *rans_compress_to_4x16(unsigned char *in, unsigned int in_size, unsigned char *out, unsigned int *out_size, int order);
+unsigned char *rans_compress_4x16(unsigned char *in, unsigned int in_size, unsigned int *out_size, int order);
+void           rans_set_cpu(int opts);
+/* tok3 encode (tokenise_name3.h:49-51): level and use_arith are accepted and ignored */
+uint8_t *tok3_encode_names(char *blk, int len, int level, int use_arith, int *out_len, int *last_start_p);
+/* fqzcomp encode (fqzcomp_qual.h:152-154; slice = fqz_slice *, gp = fqz_gparams *): vers >= 4 and gp == NULL
+ * only — for the CRAM 3.0 layout (vers 3, per-record reversal) and for caller-supplied parameters it returns
+ * NULL, which cram_compress_by_method treats as "this method lost" (cram_io.c:2083-2087) */
+char *fqz_compress(int vers, void *slice, char *in, size_t uncomp_size, size_t *comp_size, int strat, void *gp);
 /* hts_crc32 (htslib.map:657) */
 uint32_t hts_crc32(uint32_t crc, const void *buf, size_t len);
 /* bgzf_compress (htslib/bgzf.h:392, htslib.map:312): one BGZF block from slen <= 65280 bytes;
