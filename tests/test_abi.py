@@ -51,3 +51,69 @@ def test_host_scan_matches_oracle():
     with pytest.raises(H.HgpuError):
         H.bgzf_scan(bad)
     assert H.lib().hgpu_bgzf_scan(bad.ctypes.data, bad.size, None, None, None, 0) == orc_bgzf_scan(bad.tobytes())[0]
+
+
+def test_every_shim_declines_without_a_device():
+    """No CPU fallback anywhere on the libhtscodecs seam: with no CUDA device every reference-named entry point
+    returns NULL (decoders and encoders alike) instead of computing on the host."""
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    L = H.lib()
+    for name in ("rans_uncompress", "rans_compress", "arith_compress", "arith_uncompress", "rans_compress_4x16",
+                 "tok3_decode_names", "tok3_encode_names", "fqz_decompress", "fqz_compress"):
+        getattr(L, name).restype = C.c_void_p
+    g = os.path.join(os.path.dirname(__file__), "golden", "htscodecs")
+    n = C.c_uint(0); m = C.c_size_t(0); k = C.c_int(0)
+    raw = b"ACGT" * 100
+    r4x8 = open(os.path.join(g, "dat", "r4x8", "q4.0"), "rb").read()
+    arith = open(os.path.join(g, "dat", "arith", "q4.0"), "rb").read()
+    tok3 = open(os.path.join(g, "names", "tok3", "01.names.3"), "rb").read()
+    fqz = open(os.path.join(g, "dat", "fqzcomp", "q4.0"), "rb").read()
+    assert not L.rans_uncompress(r4x8, len(r4x8), C.byref(n))
+    assert not L.rans_compress(raw, len(raw), C.byref(n), 0)
+    assert not L.arith_uncompress(arith, len(arith), C.byref(n))
+    assert not L.arith_compress(raw, len(raw), C.byref(n), 0)
+    assert not L.rans_compress_4x16(raw, len(raw), C.byref(n), 0)
+    assert not L.tok3_decode_names(tok3, len(tok3), C.byref(n))
+    names = C.create_string_buffer(b"read1\0read2\0", 13)
+    assert not L.tok3_encode_names(names, 12, 3, 0, C.byref(k), None)
+    assert not L.fqz_decompress(fqz, C.c_size_t(len(fqz)), C.byref(m), None, 0)
+    lens = (C.c_uint32 * 1)(400); flags = (C.c_uint32 * 1)(0)
+
+    class Slice(C.Structure):
+        _fields_ = [("n", C.c_int), ("len", C.POINTER(C.c_uint32)), ("flags", C.POINTER(C.c_uint32))]
+    assert not L.fqz_compress(4, C.byref(Slice(1, lens, flags)), raw, C.c_size_t(len(raw)), C.byref(m), 0, None)
+
+
+def test_header_is_plain_c_and_the_seam_links(tmp_path):
+    """include/htsgpu.h must compile as C99, and a C program that names every reference entry point must link
+    against libhtsgpu.so the way `-lhtsgpu -lhtscodecs` would (seam B1)."""
+    import subprocess
+    src = tmp_path / "seam.c"
+    src.write_text('''
+#include <stdio.h>
+#include "htsgpu.h"
+int main(void) {
+    void *f[] = { (void *)rans_uncompress_to_4x16, (void *)rans_uncompress_4x16, (void *)rans_compress_to_4x16,
+                  (void *)rans_compress_4x16, (void *)rans_compress_bound_4x16, (void *)rans_set_cpu,
+                  (void *)rans_compress, (void *)rans_uncompress,
+                  (void *)arith_compress, (void *)arith_compress_to, (void *)arith_uncompress, (void *)arith_uncompress_to,
+                  (void *)arith_compress_bound, (void *)tok3_encode_names, (void *)tok3_decode_names,
+                  (void *)fqz_compress, (void *)fqz_decompress, (void *)hts_crc32, (void *)bgzf_compress };
+    unsigned n = 0, i;
+    for (i = 0; i < sizeof f / sizeof *f; i++) n += f[i] != 0;
+    printf("%u entry points, bound(1000,1)=%u\\n", n, arith_compress_bound(1000, 1));
+    return 0;
+}
+''')
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    libdir = os.path.join(root, "htslib_b200")
+    exe = tmp_path / "seam"
+    subprocess.check_call(["gcc", "-std=c99", "-Wall", "-Werror", "-Wno-pedantic", "-I", os.path.join(root, "include"), str(src),
+                           "-L", libdir, "-lhtsgpu", "-Wl,-rpath," + libdir, "-Wl,--unresolved-symbols=ignore-in-shared-libs",
+                           "-o", str(exe)])
+    env = dict(os.environ)
+    env["LD_LIBRARY_PATH"] = "/usr/local/cuda/lib64:" + env.get("LD_LIBRARY_PATH", "")
+    out = subprocess.check_output([str(exe)], env=env).decode()
+    assert out.startswith("19 entry points") and "bound(1000,1)=" in out
