@@ -268,12 +268,54 @@ def rans_leg(args, ctx, torch, dev):
     ms = float(np.mean(times))
     U, Cb = int(out_len.astype(np.int64).sum()), int(in_len.astype(np.int64).sum())
     hbm, how = peaks()
-    return {"workload": "CRAM3.1 rANS-Nx16 decode, %d slices x (QS 1.5MB X32-O1 + BF 15kB O1 + 5x10kB O0), NovaSeq 4-bin quals, %d unique slices tiled"
-                        % (nsl, uniq),
-            "streams": n, "resident_streams_per_wave": int(wave), "uncompressed_GB": U / 1e9, "compressed_GB": Cb / 1e9, "ms": ms,
-            "value": U / ms / 1e6, "unit": "GB/s (uncompressed)",
-            "roofline": {"bound": "hbm", "achieved": (U + Cb) / ms / 1e6, "peak": hbm, "unit": "GB/s",
-                         "frac": (U + Cb) / ms / 1e6 / hbm, "traffic": None, "peak_source": how}}
+    res = {"workload": "CRAM3.1 rANS-Nx16 decode, %d slices x (QS 1.5MB X32-O1 + BF 15kB O1 + 5x10kB O0), NovaSeq 4-bin quals, %d unique slices tiled"
+                       % (nsl, uniq),
+           "streams": n, "resident_streams_per_wave": int(wave), "uncompressed_GB": U / 1e9, "compressed_GB": Cb / 1e9, "ms": ms,
+           "value": U / ms / 1e6, "unit": "GB/s (uncompressed)",
+           "roofline": {"bound": "hbm", "achieved": (U + Cb) / ms / 1e6, "peak": hbm, "unit": "GB/s",
+                        "frac": (U + Cb) / ms / 1e6 / hbm, "traffic": None, "peak_source": how}}
+    try:                                                          # the reference's own decoder on the same streams, beside it
+        res.update(ref_rans_rate(comps, ulens))
+    except Exception as ex:
+        res["cpu_reference_error"] = repr(ex)
+    return res
+
+
+def ref_rans_rate(comps, ulens, seconds=2.0):
+    """rans_uncompress_to_4x16 of the unmodified reference (oracle/_ref) over the given streams: one core, then
+    one thread per host core (ctypes releases the GIL), each for about `seconds`."""
+    from concurrent.futures import ThreadPoolExecutor
+    r = ref_lib()
+    if r is None:
+        return {}
+    r.rans_uncompress_to_4x16.restype = C.c_void_p
+    r.rans_uncompress_to_4x16.argtypes = [C.c_char_p, C.c_uint, C.c_void_p, C.POINTER(C.c_uint)]
+    # the quality blocks carry ~97 % of the bytes; the 10-15 kB blocks would only measure Python's call overhead
+    big = [i for i in range(len(comps)) if ulens[i] >= 100000] or list(range(len(comps)))
+    comps = [comps[i] for i in big]; ulens = [ulens[i] for i in big]
+
+    def work(k, until):
+        out = (C.c_uint8 * max(1, max(ulens)))()
+        done = 0
+        i = k
+        while time.perf_counter() < until:
+            m = C.c_uint(ulens[i % len(comps)])
+            if not r.rans_uncompress_to_4x16(comps[i % len(comps)], len(comps[i % len(comps)]), out, C.byref(m)):
+                raise RuntimeError("reference decoder failed on stream %d" % (i % len(comps)))
+            done += m.value
+            i += 1
+        return done
+    t0 = time.perf_counter()
+    one = work(0, t0 + seconds) / (time.perf_counter() - t0)
+    cores = len(os.sched_getaffinity(0))
+    allc = 0.0
+    for _ in range(3):                                            # best of three: the first pass also warms the cores up
+        t0 = time.perf_counter()
+        with ThreadPoolExecutor(cores) as ex:
+            tot = sum(ex.map(lambda k: work(k, t0 + seconds), range(cores)))
+        allc = max(allc, tot / (time.perf_counter() - t0))
+    return {"cpu_reference_1core_GBps": one / 1e9, "cpu_reference_allcores_GBps": allc / 1e9, "cpu_reference_cores": cores,
+            "cpu_reference_sample": "%d quality blocks, %.0f s per arm (all-core arm: best of 3), rans_uncompress_to_4x16 of oracle/_ref" % (len(comps), seconds)}
 
 
 def run_ours(args):
