@@ -67,8 +67,11 @@ def _expect(img, b):
     return None
 
 
+FOREIGN = ["auxf#values_java.cram", "ce#5b_java.cram", "xx#large_aux_java.cram", "range.cram"]   # the reference's own test/*.cram
+
+
 @pytest.mark.gpu
-@pytest.mark.parametrize("name", ["ce#1000.v31.cram", "ce#1000.v30.cram", "ce#1000.v31arith.cram", "ce#1000.v31fqz.cram"])
+@pytest.mark.parametrize("name", ["ce#1000.v31.cram", "ce#1000.v30.cram", "ce#1000.v31arith.cram", "ce#1000.v31fqz.cram"] + FOREIGN)
 def test_uncompress_all_blocks_in_one_call(name):
     img = np.fromfile(os.path.join(GOLD, "htslib", name), dtype=np.uint8)
     ctx = H.Context(0)
@@ -96,3 +99,21 @@ def test_uncompress_all_blocks_in_one_call(name):
         if i == victim: assert st == -2
         else: assert (st, data) == (st0, data0)
     ctx.close()
+
+
+@pytest.mark.parametrize("name", FOREIGN)
+def test_scan_foreign_writer_files(name):
+    """CRAM 3.0 files written by htsjdk (and range.cram), from the reference's test/: the host scanner must walk
+    them, every block's stored CRC-32 must match header+payload, and every block must decode with the oracle to
+    its uncomp_size (they include empty RANS blocks: comp_size = uncomp_size = 0)."""
+    import zlib
+    import _libs as L
+    img = np.fromfile(os.path.join(GOLD, "htslib", name), dtype=np.uint8)
+    blocks, ver = H.cram_scan_blocks(img)
+    assert ver == (3, 0) and len(blocks) > 10
+    for b in blocks:
+        o, cs, us, hl = int(b["data_off"]), int(b["comp_size"]), int(b["uncomp_size"]), int(b["hdr_len"])
+        comp = img[o:o + cs].tobytes()
+        assert zlib.crc32(img[o - hl:o + cs].tobytes()) == int.from_bytes(img[o + cs:o + cs + 4].tobytes(), "little")
+        want = _expect(img, b)
+        assert want is not None and len(want) == us, (int(b["method"]), cs, us)
