@@ -117,3 +117,36 @@ def test_scan_foreign_writer_files(name):
         assert zlib.crc32(img[o - hl:o + cs].tobytes()) == int.from_bytes(img[o + cs:o + cs + 4].tobytes(), "little")
         want = _expect(img, b)
         assert want is not None and len(want) == us, (int(b["method"]), cs, us)
+
+
+def test_scanners_survive_corrupt_images():
+    """The host scanners read untrusted files: on 3000 corrupted / truncated images they must return a block list
+    or raise, never read out of bounds (this test dies with the interpreter if they do)."""
+    import random
+    from _libs import bgzf_file
+    rng = random.Random(99)
+    crams = [np.fromfile(os.path.join(GOLD, "htslib", n), dtype=np.uint8) for n in ["ce#1000.v31.cram", "ce#5b_java.cram", "range.cram"]]
+    for trial in range(2000):
+        img = crams[trial % 3].copy()
+        for _ in range(rng.randrange(1, 6)):
+            img[rng.randrange(0, min(len(img), 3000) if trial % 2 else len(img))] = rng.randrange(256)
+        if trial % 5 == 0:
+            img = img[: rng.randrange(1, len(img))].copy()
+        try:
+            blocks, _ = H.cram_scan_blocks(img)
+            for b in blocks:                                     # whatever is listed must lie inside the image
+                assert int(b["data_off"]) + int(b["comp_size"]) + 4 <= len(img) and int(b["data_off"]) >= int(b["hdr_len"])
+        except H.HgpuError:
+            pass
+    bg = np.frombuffer(bgzf_file(bytes(rng.randrange(256) for _ in range(100000)), 6, block=9000), dtype=np.uint8)
+    for trial in range(1000):
+        img = bg.copy()
+        for _ in range(rng.randrange(1, 4)):
+            img[rng.randrange(len(img))] = rng.randrange(256)
+        if trial % 4 == 0:
+            img = img[: rng.randrange(1, len(img))].copy()
+        try:
+            off, ln, _ = H.bgzf_scan(img)
+            assert all(int(o) + int(l) <= len(img) for o, l in zip(off, ln))
+        except H.HgpuError:
+            pass
