@@ -490,3 +490,18 @@ def fqz_encode(ctx, quals, rec_lens, strat=0):
     check(L.hgpu_fqz_encode_batch_host(ctx.h, p(blob), p(in_off), p(in_len), p(rec), p(rec_off), p(nrec), n, strat,
                                        p(out), p(out_off), p(cap), p(got), p(st)), "fqz_encode_batch_host")
     return [(int(st[i]), out[int(out_off[i]):int(out_off[i]) + int(got[i])].tobytes()) for i in range(n)]
+
+
+def cram_parse_compression_header(payload, major=3):
+    """Encoding maps of a CRAM compression-header block (uncompressed payload): (series array, description text)."""
+    import numpy as np
+    L = lib()
+    L.hgpu_cram_parse_compression_header.restype = C.c_long
+    L.hgpu_cram_parse_compression_header.argtypes = [C.c_char_p, C.c_uint32, C.c_int, C.c_void_p, C.c_long, C.c_char_p, C.c_size_t]
+    dt = np.dtype([("key", "<u4"), ("encoding", "<i4"), ("id", "<i4", (2,))])
+    arr = np.zeros(4096, dtype=dt)
+    text = C.create_string_buffer(1 << 20)
+    n = L.hgpu_cram_parse_compression_header(bytes(payload), len(payload), major, arr.ctypes.data, len(arr), text, len(text))
+    if n < 0:
+        raise HgpuError("compression header: %s" % last_error())
+    return arr[:n], text.value.decode("latin-1")

@@ -186,6 +186,19 @@ typedef struct hgpu_cram_block {
 long hgpu_cram_scan_blocks(const uint8_t *file, uint64_t len, hgpu_cram_block *blocks, long cap,
                            int *major, int *minor);
 
+/* CRAM 3.x compression header on the host: the record and tag encoding maps of a container
+ * (cram_decode_compression_header, cram/cram_decode.c:144-538, and the *_decode_init parsers of
+ * cram/cram_codecs.c) — which codec and which external block feed every data series; the table a device
+ * record decoder starts from.  hdr/len: the UNCOMPRESSED payload of the container's compression-header block
+ * (content type 1; hgpu_cram_uncompress_blocks_host delivers it).  series[i]: key = 2 ASCII chars (data
+ * series) or tag[0]<<16 | tag[1]<<8 | type (tags); encoding = the CRAM encoding id; id[0], id[1] = external
+ * block content ids (-1 if none; for BYTE_ARRAY_LEN the length codec's and the value codec's).  text, if not
+ * NULL, receives the description cram_describe_encodings prints (cram/cram_external.c:476-494).  Returns the
+ * number of series or -1. */
+typedef struct hgpu_cram_series { uint32_t key; int32_t encoding; int32_t id[2]; } hgpu_cram_series;
+long hgpu_cram_parse_compression_header(const uint8_t *hdr, uint32_t len, int major_version,
+                                        hgpu_cram_series *series, long cap, char *text, size_t text_cap);
+
 /* cram_uncompress_block (cram/cram_io.c:1576-1754) for a whole block list at once, HOST buffers — the
  * per-block work cram_decode_slice does before its record loop (cram/cram_decode.c:619-627).  blocks[] is
  * what hgpu_cram_scan_blocks returned for this file image; block i's data goes to out + out_off[i], a
