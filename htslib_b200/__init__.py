@@ -505,3 +505,41 @@ def cram_parse_compression_header(payload, major=3):
     if n < 0:
         raise HgpuError("compression header: %s" % last_error())
     return arr[:n], text.value.decode("latin-1")
+
+
+def cram_scan_containers(file_np):
+    """Container headers of a CRAM 3.x image: (structured array hgpu_cram_container, flat landmark array)."""
+    import numpy as np
+    L = lib()
+    L.hgpu_cram_scan_containers.restype = C.c_long
+    L.hgpu_cram_scan_containers.argtypes = [C.c_void_p, C.c_uint64, C.c_void_p, C.c_long, C.c_void_p, C.c_long]
+    dt = np.dtype([("offset", "<u8"), ("data_off", "<u8"), ("record_counter", "<i8"), ("bases", "<i8"), ("length", "<i4"),
+                   ("ref_id", "<i4"), ("start", "<i4"), ("span", "<i4"), ("n_records", "<i4"), ("n_blocks", "<i4"),
+                   ("n_landmarks", "<i4"), ("landmark0", "<u4"), ("first_block", "<u4"), ("crc32", "<u4")])
+    assert dt.itemsize == 72
+    n = L.hgpu_cram_scan_containers(file_np.ctypes.data, file_np.size, None, 0, None, 0)
+    if n < 0:
+        raise HgpuError("CRAM container scan failed: %s" % last_error())
+    arr = np.zeros(n, dtype=dt)
+    L.hgpu_cram_scan_containers(file_np.ctypes.data, file_np.size, arr.ctypes.data, n, None, 0)
+    nl = int(arr["n_landmarks"].sum())
+    lm = np.zeros(max(1, nl), dtype=np.int32)
+    L.hgpu_cram_scan_containers(file_np.ctypes.data, file_np.size, arr.ctypes.data, n, lm.ctypes.data, nl)
+    return arr, lm[:nl]
+
+
+def cram_parse_slice_header(payload, major=3):
+    """Slice header block payload -> (dict of fields, content id list)."""
+    import numpy as np
+    L = lib()
+    L.hgpu_cram_parse_slice_header.restype = C.c_long
+    L.hgpu_cram_parse_slice_header.argtypes = [C.c_char_p, C.c_uint32, C.c_int, C.c_void_p, C.c_void_p, C.c_long]
+    dt = np.dtype([("record_counter", "<i8"), ("ref_id", "<i4"), ("start", "<i4"), ("span", "<i4"), ("n_records", "<i4"),
+                   ("n_blocks", "<i4"), ("n_content_ids", "<i4"), ("ref_base_id", "<i4"), ("md5", "u1", (16,)), ("pad", "<u4")])
+    assert dt.itemsize == 56
+    s = np.zeros(1, dtype=dt)
+    ids = np.zeros(10000, dtype=np.int32)
+    n = L.hgpu_cram_parse_slice_header(bytes(payload), len(payload), major, s.ctypes.data, ids.ctypes.data, len(ids))
+    if n < 0:
+        raise HgpuError("slice header: %s" % last_error())
+    return s[0], ids[:n].tolist()

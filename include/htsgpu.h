@@ -199,6 +199,29 @@ typedef struct hgpu_cram_series { uint32_t key; int32_t encoding; int32_t id[2];
 long hgpu_cram_parse_compression_header(const uint8_t *hdr, uint32_t len, int major_version,
                                         hgpu_cram_series *series, long cap, char *text, size_t text_cap);
 
+/* Container and slice headers of a CRAM 3.x image (cram_read_container cram/cram_io.c:3760-3900,
+ * cram_decode_slice_header cram/cram_decode.c:959-1046): the units that shard across GPUs (contiguous slice
+ * ranges per rank, no exchange) and, per slice, the content ids of its blocks.  first_block indexes the list
+ * hgpu_cram_scan_blocks returns; landmarks (slice offsets inside the container) are written flat into
+ * `landmarks`, container i owning [landmark0, landmark0 + n_landmarks).  hgpu_cram_parse_slice_header takes the
+ * payload of a slice-header block (content type 2) and returns the number of content ids, or -1. */
+typedef struct hgpu_cram_container {
+    uint64_t offset, data_off;           /* header start / first block, in the file image */
+    int64_t  record_counter, bases;
+    int32_t  length, ref_id, start, span, n_records, n_blocks, n_landmarks;
+    uint32_t landmark0, first_block, crc32;
+} hgpu_cram_container;
+typedef struct hgpu_cram_slice {
+    int64_t  record_counter;
+    int32_t  ref_id, start, span, n_records, n_blocks, n_content_ids, ref_base_id;
+    uint8_t  md5[16];
+    uint32_t pad;
+} hgpu_cram_slice;
+long hgpu_cram_scan_containers(const uint8_t *file, uint64_t len, hgpu_cram_container *out, long cap,
+                               int32_t *landmarks, long landmark_cap);
+long hgpu_cram_parse_slice_header(const uint8_t *payload, uint32_t len, int major_version,
+                                  hgpu_cram_slice *out, int32_t *content_ids, long cap);
+
 /* cram_uncompress_block (cram/cram_io.c:1576-1754) for a whole block list at once, HOST buffers — the
  * per-block work cram_decode_slice does before its record loop (cram/cram_decode.c:619-627).  blocks[] is
  * what hgpu_cram_scan_blocks returned for this file image; block i's data goes to out + out_off[i], a

@@ -94,3 +94,80 @@ def test_rejects_garbage():
             H.cram_parse_compression_header(bytes(p))
         except H.HgpuError:
             pass
+
+
+@pytest.mark.skipif(L.ref() is None, reason="needs oracle/_ref")
+@pytest.mark.parametrize("name", FILES)
+def test_containers_and_slices_equal_reference(name):
+    """Every container header field the reference exposes (htslib/cram.h:190-216) and every slice header field
+    (:418-441) must match what the host tables report; the block list and the container table must agree."""
+    path = os.path.join(L.GOLD, "htslib", name)
+    img = np.fromfile(path, dtype=np.uint8)
+    cont, lm = H.cram_scan_containers(img)
+    blocks, ver = H.cram_scan_blocks(img)
+    assert int(cont["n_blocks"].sum()) == len(blocks)
+    for i, c in enumerate(cont):
+        mine = blocks[blocks["container"] == i]
+        assert len(mine) == int(c["n_blocks"])
+        if len(mine):
+            assert int(np.where(blocks["container"] == i)[0][0]) == int(c["first_block"])
+            assert int(mine[0]["data_off"]) - int(mine[0]["hdr_len"]) == int(c["data_off"])
+    r = L.ref()
+    r.cram_open.restype = C.c_void_p; r.cram_open.argtypes = [C.c_char_p, C.c_char_p]
+    r.cram_close.argtypes = [C.c_void_p]
+    r.cram_read_container.restype = C.c_void_p; r.cram_read_container.argtypes = [C.c_void_p]
+    r.cram_read_block.restype = C.c_void_p; r.cram_read_block.argtypes = [C.c_void_p]
+    r.cram_uncompress_block.argtypes = [C.c_void_p]
+    r.cram_block_get_content_type.argtypes = [C.c_void_p]
+    for f in ("cram_container_get_length", "cram_container_get_num_blocks", "cram_container_get_num_records"):
+        getattr(r, f).restype = C.c_int32; getattr(r, f).argtypes = [C.c_void_p]
+    r.cram_container_get_num_bases.restype = C.c_int64; r.cram_container_get_num_bases.argtypes = [C.c_void_p]
+    r.cram_container_get_landmarks.restype = C.POINTER(C.c_int32); r.cram_container_get_landmarks.argtypes = [C.c_void_p, C.POINTER(C.c_int32)]
+    r.cram_container_get_coords.argtypes = [C.c_void_p, C.POINTER(C.c_int), C.POINTER(C.c_int64), C.POINTER(C.c_int64)]
+    r.cram_decode_slice_header.restype = C.c_void_p; r.cram_decode_slice_header.argtypes = [C.c_void_p, C.c_void_p]
+    r.cram_slice_hdr_get_num_blocks.restype = C.c_int32; r.cram_slice_hdr_get_num_blocks.argtypes = [C.c_void_p]
+    r.cram_slice_hdr_get_embed_ref_id.argtypes = [C.c_void_p]
+    r.cram_slice_hdr_get_coords.argtypes = [C.c_void_p, C.POINTER(C.c_int), C.POINTER(C.c_int64), C.POINTER(C.c_int64)]
+    fd = r.cram_open(path.encode(), b"r")                             # consumes container 0, the SAM header container
+    ci, bi = 1, int(cont[0]["n_blocks"])
+    slices = 0
+    while True:
+        c = r.cram_read_container(fd)
+        if not c:
+            break
+        m = cont[ci]
+        assert r.cram_container_get_length(c) == int(m["length"])
+        assert r.cram_container_get_num_blocks(c) == int(m["n_blocks"])
+        assert r.cram_container_get_num_records(c) == int(m["n_records"])
+        assert r.cram_container_get_num_bases(c) == int(m["bases"])
+        nl = C.c_int32(0)
+        lp = r.cram_container_get_landmarks(c, C.byref(nl))
+        assert nl.value == int(m["n_landmarks"])
+        assert [lp[k] for k in range(nl.value)] == lm[int(m["landmark0"]):int(m["landmark0"]) + nl.value].tolist()
+        rid, st, sp = C.c_int(0), C.c_int64(0), C.c_int64(0)
+        r.cram_container_get_coords(c, C.byref(rid), C.byref(st), C.byref(sp))
+        assert (rid.value, st.value, sp.value) == (int(m["ref_id"]), int(m["start"]), int(m["span"]))
+        for k in range(int(m["n_blocks"])):
+            b = r.cram_read_block(fd)
+            assert b
+            if r.cram_block_get_content_type(b) == 2:                     # MAPPED_SLICE header
+                assert r.cram_uncompress_block(b) == 0
+                h = r.cram_decode_slice_header(fd, b)
+                assert h
+                x = blocks[bi]
+                comp = img[int(x["data_off"]):int(x["data_off"]) + int(x["comp_size"])].tobytes()
+                payload = comp if int(x["method"]) == 0 else zlib.decompress(comp, 31)
+                s, ids = H.cram_parse_slice_header(payload, ver[0])
+                assert r.cram_slice_hdr_get_num_blocks(h) == int(s["n_blocks"])
+                assert r.cram_slice_hdr_get_embed_ref_id(h) == int(s["ref_base_id"])
+                r.cram_slice_hdr_get_coords(h, C.byref(rid), C.byref(st), C.byref(sp))
+                assert (rid.value, st.value, sp.value) == (int(s["ref_id"]), int(s["start"]), int(s["span"]))
+                # the slice's external blocks carry exactly the content ids its header lists
+                follow = blocks[bi + 1: bi + 1 + int(s["n_blocks"])]
+                ext = follow[follow["content_type"] == 4]                  # the CORE block (type 5, id 0) is not listed
+                assert sorted(int(v) for v in ext["content_id"]) == sorted(ids)
+                slices += 1
+            bi += 1
+        ci += 1
+    r.cram_close(fd)
+    assert ci == len(cont) and slices >= 1
