@@ -117,6 +117,8 @@ def test_scan_foreign_writer_files(name):
         assert zlib.crc32(img[o - hl:o + cs].tobytes()) == int.from_bytes(img[o + cs:o + cs + 4].tobytes(), "little")
         want = _expect(img, b)
         assert want is not None and len(want) == us, (int(b["method"]), cs, us)
+        if int(b["method"]) == 4 and us and L.ref() is not None:         # the oracle agrees with the reference on foreign rANS streams
+            assert L.ref_rans_4x8(comp=comp) == want
 
 
 def test_scanners_survive_corrupt_images():
