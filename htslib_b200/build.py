@@ -5,7 +5,8 @@ import sys
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
-OUT = os.path.join(HERE, "libhtsgpu.so")
+OUT = os.path.join(HERE, os.environ.get("HGPU_OUT", "libhtsgpu.so"))      # HGPU_OUT: side-by-side tuning builds
+BUILD = os.path.join(HERE, os.environ.get("HGPU_BUILD_DIR", "build"))
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
          "-Xcompiler", "-fPIC", "--use_fast_math", "-Xptxas", "-v"]
@@ -32,9 +33,9 @@ def build(force=False, verbose=False):
         return OUT
     objs = []
     procs = []
-    os.makedirs(os.path.join(HERE, "build"), exist_ok=True)
+    os.makedirs(BUILD, exist_ok=True)
     for src in sources():
-        obj = os.path.join(HERE, "build", os.path.basename(src)[:-3] + ".o")
+        obj = os.path.join(BUILD, os.path.basename(src)[:-3] + ".o")
         objs.append(obj)
         cmd = [NVCC] + FLAGS + ["-c", src, "-o", obj]
         procs.append((src, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
@@ -45,7 +46,7 @@ def build(force=False, verbose=False):
         if p.returncode != 0:
             sys.stderr.write(out)
             raise RuntimeError("nvcc failed on %s" % src)
-    with open(os.path.join(HERE, "build", "ptxas.log"), "w") as f:
+    with open(os.path.join(BUILD, "ptxas.log"), "w") as f:
         f.write("\n".join(log))
     if verbose:
         sys.stderr.write("\n".join(log))

@@ -18,6 +18,7 @@
 // The CRC-32 of the output is computed by the same warp: 32 equal chunks, slice-by-4 per lane,
 // then a log-step combine with carry-less multiplications mod the CRC polynomial.
 #include "hgpu_internal.h"
+#include <stdlib.h>
 
 namespace {
 
@@ -30,17 +31,29 @@ enum : uint32_t { K_LIT = 0, K_LEN = 1, K_EOB = 2, K_SUB = 3, K_BAD = 4, K_DIST 
 #define ENTRY(value, xb, kind, nbits) (((uint32_t)(value) << 16) | ((uint32_t)(xb) << 8) | ((uint32_t)(kind) << 4) | (uint32_t)(nbits))
 constexpr uint32_t BAD_ENTRY = ENTRY(0, 0, K_BAD, 0);
 
+// The three areas behind the decode tables are never live at the same time (table building /
+// lane-parallel decode exchange / match execution), so they share storage.
 struct InflateSmem {
     uint32_t lit[LIT_TABLE];
     uint32_t dst[DST_TABLE];
-    uint32_t cl[CL_TABLE];
-    uint16_t code[320];      // canonical code per symbol
-    uint8_t  lens[320];
-    uint32_t count[16];
-    uint32_t next[16];
-    uint32_t sub_alloc;
-    uint2    ptab[32 * 9];   // piece table of the current match batch (a match has <= 9 pieces)
-    uint2    rbuf[32];       // match records parked by the serial decoder
+    union {
+        struct {                     // header parse + table construction
+            uint32_t cl[CL_TABLE];
+            uint16_t code[320];      // canonical code per symbol
+            uint8_t  lens[320];
+            uint32_t count[16];
+            uint32_t next[16];
+            uint32_t sub_alloc;
+        };
+        struct {                     // match execution
+            uint2 ptab[32 * 9];      // piece table of the current match batch (a match has <= 9 pieces)
+            uint2 rbuf[32];          // match records parked by the serial decoder
+        };
+        struct {                     // CTA-per-block decode: what the 128 sub-range decoders exchange
+            uint32_t x_exit[128];
+            uint32_t x_sum[2][8];
+        };
+    };
 };
 
 __constant__ uint16_t c_len_base[29] = {3,4,5,6,7,8,9,10,11,13,15,17,19,23,27,31,35,43,51,59,67,83,99,115,131,163,195,227,258};
@@ -827,6 +840,364 @@ bgzf_inflate_kernel(const uint8_t *__restrict__ in, const uint64_t *__restrict__
     }
 }
 
+
+// =============================================================================================
+// CTA-per-block inflate: the member's whole output (<= 64 KiB) lives in SHARED memory.
+//
+// Why: with the output in global memory every LZ77 dependency level costs an L2 round trip
+// (~600 cycles) and a block takes ~2 M cycles from first bit to CRC; the 16 warps/SM the old
+// kernel keeps resident cannot hide that.  With the window in shared memory a level costs a
+// shared-memory round trip, a block is done in ~100 k cycles, and three blocks per SM in flight
+// are worth more than sixteen.
+//
+//   128 threads, one BGZF block at a time, 3 CTAs/SM (75 KiB each: 64 KiB window + 16 bytes of
+//   alignment slack + the decode tables).
+//   P1  warp 0: header, code lengths, decode tables (warp-parallel build), as before
+//   P2  all 128 threads: the body's bit range cut into 128 sub-ranges, speculative decode with
+//       chained restarts until every sub-range starts where its predecessor stopped; block-wide
+//       prefix sums; literals go straight into the window, matches to a 4-byte-aligned record
+//       list in a per-CTA global slot (L2 resident: the same 170 KiB are rewritten for every block)
+//   P3  warp 0: out-of-order batched LZ77 (exec_batch) on the shared window
+//   P4  all threads: CRC-32 of the window (4 chunks, slice-by-4, combined with x^n mod P), then
+//       ONE bulk asynchronous copy (TMA, cp.async.bulk shared -> global) of the 16-byte aligned
+//       body of the payload; the window is laid out so shared and global addresses are
+//       congruent mod 16, the few head/tail bytes are stored directly.
+// =============================================================================================
+constexpr int CTA_T = 128;
+constexpr uint32_t WIN_BYTES = 65536 + 16;
+
+struct CtaCtl {              // broadcast from warp 0 / thread 0 to the CTA
+    int32_t rc;
+    uint32_t mode, final_, body, o, end_pos, job, E, bad, tot_m;
+    uint32_t crc[4];
+    long long t0;            // HGPU_PROFILE: start of the current phase
+};
+enum : uint32_t { MODE_NEXT = 0, MODE_PAR = 1 };
+
+struct CtaSmem {
+    uint8_t win[WIN_BYTES];
+    InflateSmem s;
+    CtaCtl c;
+};
+
+#ifdef HGPU_PROFILE
+#define CTA_MARK(cs, i) do { if (threadIdx.x == 0) { long long n_ = clock64(); atomicAdd(&g_prof[i], (unsigned long long)(n_ - (cs).c.t0)); (cs).c.t0 = n_; } } while (0)
+#else
+#define CTA_MARK(cs, i) do { } while (0)
+#endif
+
+// P2: all threads.  Returns a CTA-uniform status.
+__device__ int decode_body_cta(CtaSmem &cs, const uint32_t *wbase, const uint32_t *wend, uint32_t body,
+                               uint32_t total, uint8_t *out, uint32_t cap, uint2 *mrec)
+{
+    InflateSmem &s = cs.s;
+    const uint32_t t = threadIdx.x, lane = t & 31, warp = t >> 5;
+    const uint32_t S = (total - body + CTA_T - 1) / CTA_T;
+    uint32_t start = body + t * S;
+    uint32_t end = t == CTA_T - 1 ? total : min(total, body + (t + 1) * S);
+    if (start > total) start = total;
+    if (end < start) end = start;
+    uint32_t exitp = 0, n = 0, m = 0, st = ST_RUN;
+    bool need = true, dummy = false;
+    for (int round = 0; round < CTA_T + 2; round++) {
+        if (need) lane_decode<false>(s, wbase, wend, start, end, exitp, n, m, st, nullptr, 0, nullptr, 0, dummy);
+        s.x_exit[t] = exitp;
+        __syncthreads();
+        uint32_t ns = t == 0 ? start : s.x_exit[t - 1];
+        need = ns != start;
+        start = ns;
+        if (!__syncthreads_or(need)) break;
+    }
+    CTA_MARK(cs, 1);
+    // first end-of-block code, invalid codes at or before it
+    if (t == 0) { cs.c.E = 0xffffffffu; cs.c.bad = 0; }
+    __syncthreads();
+    if (st == ST_EOB) atomicMin(&cs.c.E, t);
+    __syncthreads();
+    const uint32_t E = cs.c.E;
+    if (E == 0xffffffffu) return HGPU_BGZF_ERR_ZLIB;             // input ends without an end-of-block code
+    if (st == ST_BAD && t <= E) cs.c.bad = 1;
+    if (t == E) cs.c.end_pos = exitp;
+    if (t > E) { n = 0; m = 0; }
+    // block-wide exclusive prefix sums of bytes and matches
+    uint32_t on = n, mn = m;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        uint32_t a = __shfl_up_sync(0xffffffffu, on, d), c = __shfl_up_sync(0xffffffffu, mn, d);
+        if (lane >= (uint32_t)d) { on += a; mn += c; }
+    }
+    __syncthreads();                                             // x_exit reads are over: x_sum may overlap nothing, but keep phases apart
+    if (lane == 31) { s.x_sum[0][warp] = on; s.x_sum[1][warp] = mn; }
+    __syncthreads();
+    uint32_t tot_out = 0, tot_m = 0, pre_o = 0, pre_m = 0;
+#pragma unroll
+    for (uint32_t w = 0; w < CTA_T / 32; w++) {
+        if (w < warp) { pre_o += s.x_sum[0][w]; pre_m += s.x_sum[1][w]; }
+        tot_out += s.x_sum[0][w]; tot_m += s.x_sum[1][w];
+    }
+    on += pre_o; mn += pre_m;
+    if (cs.c.bad) return HGPU_BGZF_ERR_ZLIB;
+    if (cs.c.end_pos > total) return HGPU_BGZF_ERR_ZLIB;         // the block ran past the input
+    const uint32_t o = cs.c.o;
+    if ((uint64_t)o + tot_out > cap) return HGPU_BGZF_ERR_SPACE;
+    if (tot_m > MREC_CAP) return HGPU_BGZF_ERR_ZLIB;
+    bool bad_dist = false;
+    if (t <= E) {
+        uint32_t e2, n2, m2, st2;
+        lane_decode<true>(s, wbase, wend, start, end, e2, n2, m2, st2, out, o + on - n, mrec, mn - m, bad_dist);
+    }
+    if (__syncthreads_or(bad_dist)) return HGPU_BGZF_ERR_ZLIB;   // distance too far back
+    if (t == 0) { cs.c.o = o + tot_out; cs.c.tot_m = tot_m; }
+    __threadfence_block();
+    __syncthreads();
+    CTA_MARK(cs, 2);
+    return HGPU_OK;
+}
+
+// One member: warp 0 walks the deflate block headers, the CTA decodes Huffman bodies.
+__device__ int inflate_member_cta(CtaSmem &cs, const uint8_t *src, uint32_t slen, uint8_t *out, uint32_t cap,
+                                  uint32_t &olen, uint2 *mrec)
+{
+    InflateSmem &s = cs.s;
+    const uint32_t lane = hgpu_lane(), warp = threadIdx.x >> 5;
+    Prof pf;
+    Bits b;
+    const uintptr_t a0 = reinterpret_cast<uintptr_t>(src);
+    const uint32_t mis_bits = (uint32_t)(a0 & 3) * 8;
+    const uint32_t *wbase = reinterpret_cast<const uint32_t *>(a0 - (a0 & 3));
+    const uint32_t *wend = reinterpret_cast<const uint32_t *>((a0 + slen + 3) & ~(uintptr_t)3);
+    const uint32_t total = mis_bits + slen * 8;
+    if (warp == 0) bits_init(b, src, 0, slen);
+    if (threadIdx.x == 0) cs.c.o = 0;
+    __syncthreads();
+    for (;;) {
+        if (warp == 0) {
+            // ---- P1: one deflate block header (same code path as inflate_member) ----
+            int rc = HGPU_OK;
+            uint32_t mode = MODE_NEXT, final_ = 0, body = 0;
+            uint32_t o = cs.c.o;
+            do {
+                bits_fill(b);
+                final_ = bits_get(b, 1);
+                uint32_t type = bits_get(b, 2);
+                if (type == 0) {
+                    bits_drop(b, b.cnt & 7);
+                    bits_fill(b);
+                    uint32_t len = bits_get(b, 16);
+                    bits_fill(b);
+                    uint32_t nlen = bits_get(b, 16);
+                    if (bits_overrun(b) || (len ^ 0xffffu) != nlen) { rc = HGPU_BGZF_ERR_ZLIB; break; }
+                    uint32_t pos = bits_pos(b) >> 3;
+                    if ((uint64_t)pos + len > slen) { rc = HGPU_BGZF_ERR_ZLIB; break; }
+                    if (o + len > cap) { rc = HGPU_BGZF_ERR_SPACE; break; }
+                    for (uint32_t i = lane; i < len; i += 32) out[o + i] = src[pos + i];
+                    o += len;
+                    bits_init(b, src, pos + len, slen);
+                    __syncwarp();
+                } else if (type == 1 || type == 2) {
+                    int r2;
+                    if (type == 1) {
+                        __syncwarp();
+                        for (int i = lane; i < 288; i += 32) s.lens[i] = i < 144 ? 8 : i < 256 ? 9 : i < 280 ? 7 : 8;
+                        __syncwarp();
+                        r2 = build_table<LIT_ROOT, LIT_TABLE>(s, s.lit, 288, false, lit_entry);
+                        if (r2) { rc = HGPU_BGZF_ERR_ZLIB; break; }
+                        __syncwarp();
+                        for (int i = lane; i < 32; i += 32) s.lens[i] = 5;
+                        __syncwarp();
+                        r2 = build_table<DST_ROOT, DST_TABLE>(s, s.dst, 32, false, dst_entry);
+                        if (r2) { rc = HGPU_BGZF_ERR_ZLIB; break; }
+                    } else {
+                        bits_fill(b);
+                        uint32_t hlit = bits_get(b, 5) + 257, hdist = bits_get(b, 5) + 1, hclen = bits_get(b, 4) + 4;
+                        if (hlit > 286 || hdist > 30) { rc = HGPU_BGZF_ERR_ZLIB; break; }
+                        __syncwarp();
+                        if (lane < 19) s.lens[lane] = 0;
+                        __syncwarp();
+                        for (uint32_t i = 0; i < hclen; i++) {
+                            bits_fill(b);
+                            uint32_t v = bits_get(b, 3);
+                            if (lane == 0) s.lens[c_cl_order[i]] = (uint8_t)v;
+                        }
+                        if (bits_overrun(b)) { rc = HGPU_BGZF_ERR_ZLIB; break; }
+                        __syncwarp();
+                        r2 = build_table<7, CL_TABLE>(s, s.cl, 19, false, cl_entry);
+                        if (r2) { rc = HGPU_BGZF_ERR_ZLIB; break; }
+                        uint32_t nsym = hlit + hdist, i = 0, prev = 0;
+                        bool badc = false;
+                        while (i < nsym) {
+                            bits_fill(b);
+                            uint32_t e = s.cl[bits_peek(b, 7)];
+                            if (((e >> 4) & 15) != K_LIT) { badc = true; break; }
+                            bits_drop(b, e & 15);
+                            uint32_t sym = e >> 16;
+                            if (sym < 16) {
+                                if (lane == 0) s.code[i] = (uint16_t)sym;
+                                prev = sym; i++;
+                            } else {
+                                uint32_t rep, val = 0;
+                                if (sym == 16) { if (i == 0) { badc = true; break; } val = prev; rep = 3 + bits_get(b, 2); }
+                                else if (sym == 17) rep = 3 + bits_get(b, 3);
+                                else rep = 11 + bits_get(b, 7);
+                                if (i + rep > nsym) { badc = true; break; }
+                                for (uint32_t k = lane; k < rep; k += 32) s.code[i + k] = (uint16_t)val;
+                                i += rep;
+                                prev = val;
+                            }
+                            if (bits_overrun(b)) { badc = true; break; }
+                        }
+                        if (badc) { rc = HGPU_BGZF_ERR_ZLIB; break; }
+                        __syncwarp();
+                        if (s.code[256] == 0) { rc = HGPU_BGZF_ERR_ZLIB; break; }
+                        uint32_t dl = lane < hdist ? s.code[hlit + lane] : 0;
+                        uint32_t ll[9];
+#pragma unroll
+                        for (int k = 0; k < 9; k++) { uint32_t j = lane + 32 * k; ll[k] = j < hlit ? s.code[j] : 0; }
+                        __syncwarp();
+#pragma unroll
+                        for (int k = 0; k < 9; k++) { uint32_t j = lane + 32 * k; if (j < 288) s.lens[j] = (uint8_t)ll[k]; }
+                        __syncwarp();
+                        r2 = build_table<LIT_ROOT, LIT_TABLE>(s, s.lit, (int)hlit, true, lit_entry);
+                        if (r2) { rc = HGPU_BGZF_ERR_ZLIB; break; }
+                        __syncwarp();
+                        s.lens[lane] = (uint8_t)dl;
+                        __syncwarp();
+                        r2 = build_table<DST_ROOT, DST_TABLE>(s, s.dst, (int)hdist, true, dst_entry);
+                        if (r2) { rc = HGPU_BGZF_ERR_ZLIB; break; }
+                    }
+                    __syncwarp();
+                    if (bits_overrun(b)) { rc = HGPU_BGZF_ERR_ZLIB; break; }
+                    body = mis_bits + bits_pos(b);
+                    if (total - body >= PAR_MIN_BITS) mode = MODE_PAR;
+                    else {
+                        rc = decode_body_uniform(s, b, out, cap, o);
+                        if (rc) break;
+                    }
+                } else { rc = HGPU_BGZF_ERR_ZLIB; break; }
+            } while (0);
+            __syncwarp();
+            if (lane == 0) { cs.c.rc = rc; cs.c.mode = mode; cs.c.final_ = final_; cs.c.body = body; cs.c.o = o; }
+        }
+        __threadfence_block();
+        __syncthreads();
+        CTA_MARK(cs, 0);
+        if (cs.c.rc) return cs.c.rc;
+        const uint32_t final_ = cs.c.final_;
+        if (cs.c.mode == MODE_PAR) {
+            int rc = decode_body_cta(cs, wbase, wend, cs.c.body, total, out, cap, mrec);
+            if (rc) return rc;
+            // ---- P3: LZ77 on the shared window, one warp ----
+            if (warp == 0) {
+                run_matches(s, out, mrec, cs.c.tot_m);
+                // continue the uniform reader right after the end-of-block code
+                uint32_t end_pos = cs.c.end_pos;
+                uint32_t byte = (end_pos - mis_bits) >> 3, bit = (end_pos - mis_bits) & 7;
+                bits_init(b, src, byte, slen);
+                bits_fill(b);
+                bits_drop(b, bit);
+            }
+            __threadfence_block();
+            __syncthreads();
+            CTA_MARK(cs, 3);
+        }
+        if (final_) break;
+    }
+    olen = cs.c.o;
+    (void)pf;
+    return HGPU_OK;
+}
+
+// CRC-32 of win[0..n) by the CTA (4 warps, one quarter each), result CTA-uniform.
+__device__ uint32_t cta_crc32(CtaSmem &cs, const uint8_t *p, uint32_t n)
+{
+    const uint32_t warp = threadIdx.x >> 5;
+    const uint32_t q = n / 4;
+    const uint32_t beg = warp * q, len = warp == 3 ? n - 3 * q : q;
+    uint32_t crc = warp_crc32(g_crc_tab, p + beg, len);          // tables via L1 (4 KiB, read-only)
+    if (hgpu_lane() == 0) cs.c.crc[warp] = crc;
+    __syncthreads();
+    // crc(A||B) = crc(A) * x^(8|B|) ^ crc(B)
+    uint32_t r = cs.c.crc[0];
+    if (n >= 4) {
+        uint32_t xq = xpow_bytes(q), xl = xpow_bytes(n - 3 * q);
+        r = multmodp(xq, r) ^ cs.c.crc[1];
+        r = multmodp(xq, r) ^ cs.c.crc[2];
+        r = multmodp(xl, r) ^ cs.c.crc[3];
+    } else {
+        // fewer than 4 bytes: the last warp took them all, the others saw empty ranges (crc of nothing = 0)
+        r = cs.c.crc[3];
+    }
+    __syncthreads();
+    return r;
+}
+
+__global__ void __launch_bounds__(CTA_T, 3)
+bgzf_inflate_cta_kernel(const uint8_t *__restrict__ in, const uint64_t *__restrict__ in_off,
+                        const uint32_t *__restrict__ in_len, uint32_t n, uint8_t *out,
+                        const uint64_t *__restrict__ out_off, const uint32_t *__restrict__ out_cap,
+                        uint32_t *out_len, int32_t *status, uint32_t *counter, uint2 *mrec_all)
+{
+    extern __shared__ __align__(16) uint8_t dyn_smem[];
+    CtaSmem &cs = *reinterpret_cast<CtaSmem *>(dyn_smem);
+    uint2 *mrec = mrec_all + (size_t)blockIdx.x * MREC_CAP;
+    const uint32_t t = threadIdx.x;
+    for (;;) {
+        if (t == 0) cs.c.job = atomicAdd(counter, 1u);
+        __syncthreads();
+        const uint32_t job = cs.c.job;
+        if (job >= n) break;
+#ifdef HGPU_PROFILE
+        if (t == 0) cs.c.t0 = clock64();
+#endif
+        const uint8_t *blk = in + in_off[job];
+        const uint32_t blen = in_len[job];
+        uint8_t *dst = out + out_off[job];
+        uint32_t cap = out_cap[job];
+        if (cap > 65536u) cap = 65536u;                    // BGZF_MAX_BLOCK_SIZE, bgzf.c:810
+        // shared and global addresses congruent mod 16: the payload's byte i sits at win[pad + i]
+        const uint32_t pad = (uint32_t)(reinterpret_cast<uintptr_t>(dst) & 15);
+        uint8_t *win = cs.win + pad;
+        int rc = HGPU_OK;
+        uint32_t got = 0;
+        if (blen < 26 || check_header(blk) != 0 || (uint32_t)(blk[16] | blk[17] << 8) + 1u != blen)
+            rc = HGPU_BGZF_ERR_HEADER;
+        else {
+            rc = inflate_member_cta(cs, blk + 18, blen - 18, win, cap, got, mrec);
+            if (rc == HGPU_OK) {
+                uint32_t want = blk[blen - 8] | blk[blen - 7] << 8 | blk[blen - 6] << 16 | (uint32_t)blk[blen - 5] << 24;
+                uint32_t crc = cta_crc32(cs, win, got);
+                if (crc != want) rc = HGPU_BGZF_ERR_CRC;
+                CTA_MARK(cs, 4);
+            }
+        }
+        if (rc == HGPU_OK && got) {
+            // ---- write-out: head bytes up to the first 16-byte boundary, bulk copy, tail bytes ----
+            uint32_t head = (16u - pad) & 15u;
+            if (head > got) head = got;
+            const uint32_t bulk = (got - head) & ~15u, tail = got - head - bulk;
+            if (t < head) dst[t] = win[t];
+            if (t >= 32 && t - 32 < tail) dst[head + bulk + (t - 32)] = win[head + bulk + (t - 32)];
+            if (bulk) {
+                // generic-proxy writes to the window must be visible to the async proxy
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                __syncthreads();
+                if (t == 0) {
+                    uint32_t sa = (uint32_t)__cvta_generic_to_shared(win + head);
+                    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;"
+                                 :: "l"(dst + head), "r"(sa), "r"(bulk) : "memory");
+                    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+                    asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");   // the window is reused by the next block
+                }
+            }
+        }
+        __syncthreads();
+        CTA_MARK(cs, 5);
+        if (t == 0) { status[job] = rc; out_len[job] = rc == HGPU_OK ? got : 0; }
+        __syncthreads();
+    }
+    if (t == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");   // every bulk store has landed before the CTA retires
+}
+
 __global__ void crc32_chunks_kernel(const uint8_t *buf, size_t len, size_t chunk, uint32_t *partial)
 {
     // one warp per chunk
@@ -1079,32 +1450,45 @@ int hgpu_launch_bgzf_inflate(hgpu_ctx *ctx, const uint8_t *d_in, const uint64_t 
                              uint32_t *d_out_len, int32_t *d_status, cudaStream_t st)
 {
     if (n == 0) return HGPU_OK;
+    if (hgpu_check(cudaSetDevice(ctx->device), "cudaSetDevice")) return HGPU_ERR_CUDA;
     int rc = ensure_crc_tables(ctx, st);
     if (rc) return rc;
-    int per_sm = 0;
-    const size_t dyn = 4096 + INFLATE_WARPS * sizeof(InflateSmem);
-    static bool attr_set = false;
-    if (!attr_set) {
-        if (hgpu_check(cudaFuncSetAttribute(bgzf_inflate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn), "inflate smem attr"))
+    // HGPU_INFLATE_WARP=1 selects the round-1 warp-per-block kernel (output window in global memory)
+    // for A/B measurements; the product path is the CTA-per-block kernel (window in shared memory).
+    static const bool use_warp = getenv("HGPU_INFLATE_WARP") && getenv("HGPU_INFLATE_WARP")[0] == '1';
+    static bool attr_set[64];                          // function attributes are per device
+    const int dv = ctx->device & 63;
+    const size_t dyn_w = 4096 + INFLATE_WARPS * sizeof(InflateSmem), dyn_c = sizeof(CtaSmem);
+    if (!attr_set[dv]) {
+        if (hgpu_check(cudaFuncSetAttribute(bgzf_inflate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn_w), "inflate smem attr") ||
+            hgpu_check(cudaFuncSetAttribute(bgzf_inflate_cta_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn_c), "inflate smem attr"))
             return HGPU_ERR_CUDA;
-        attr_set = true;
+        attr_set[dv] = true;
     }
-    if (hgpu_check(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, bgzf_inflate_kernel, 32 * INFLATE_WARPS, dyn), "inflate occupancy"))
+    int per_sm = 0;
+    if (use_warp) {
+        if (hgpu_check(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, bgzf_inflate_kernel, 32 * INFLATE_WARPS, dyn_w), "inflate occupancy"))
+            return HGPU_ERR_CUDA;
+    } else if (hgpu_check(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, bgzf_inflate_cta_kernel, CTA_T, dyn_c), "inflate occupancy"))
         return HGPU_ERR_CUDA;
     if (per_sm < 1) per_sm = 1;
-    uint32_t grid = (uint32_t)ctx->sm_count * (uint32_t)per_sm;
-    if (grid > (n + INFLATE_WARPS - 1) / INFLATE_WARPS) grid = (n + INFLATE_WARPS - 1) / INFLATE_WARPS;
+    const uint32_t units = use_warp ? (n + INFLATE_WARPS - 1) / INFLATE_WARPS : n;
+    uint32_t full_grid = (uint32_t)ctx->sm_count * (uint32_t)per_sm, grid = full_grid;
+    if (grid > units) grid = units;
     uint32_t *counter = hgpu_take_counter(ctx, st);
     if (!counter) return HGPU_ERR_CUDA;
-    // match-record scratch, one slot per resident warp, sized for the full grid so concurrent
+    // match-record scratch, one slot per resident warp (CTA), sized for the full grid so concurrent
     // launches on other streams (the pipelined host path) can share the same layout
-    uint32_t full_grid = (uint32_t)ctx->sm_count * (uint32_t)per_sm;
-    full_grid *= INFLATE_WARPS;                        // one record slot per resident warp
-    rc = hgpu_ensure_mrec(ctx, (size_t)full_grid * MREC_CAP * sizeof(uint2) * 3);
+    const uint32_t slots = use_warp ? full_grid * INFLATE_WARPS : full_grid;
+    rc = hgpu_ensure_mrec(ctx, (size_t)slots * MREC_CAP * sizeof(uint2) * 3);
     if (rc) return rc;
-    uint2 *mrec = reinterpret_cast<uint2 *>(ctx->d_mrec) + (size_t)(ctx->next_counter % 3) * full_grid * MREC_CAP;
-    bgzf_inflate_kernel<<<grid, 32 * INFLATE_WARPS, dyn, st>>>(d_in, d_in_off, d_in_len, n, d_out, d_out_off, d_out_cap,
-                                             d_out_len, d_status, counter, mrec);
+    uint2 *mrec = reinterpret_cast<uint2 *>(ctx->d_mrec) + (size_t)(ctx->next_counter % 3) * slots * MREC_CAP;
+    if (use_warp)
+        bgzf_inflate_kernel<<<grid, 32 * INFLATE_WARPS, dyn_w, st>>>(d_in, d_in_off, d_in_len, n, d_out, d_out_off, d_out_cap,
+                                                                     d_out_len, d_status, counter, mrec);
+    else
+        bgzf_inflate_cta_kernel<<<grid, CTA_T, dyn_c, st>>>(d_in, d_in_off, d_in_len, n, d_out, d_out_off, d_out_cap,
+                                                            d_out_len, d_status, counter, mrec);
     hgpu_count_launch();
     return hgpu_check(cudaGetLastError(), "inflate launch");
 }

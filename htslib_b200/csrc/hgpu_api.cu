@@ -9,6 +9,10 @@
 #include <stdlib.h>
 #include <string.h>
 #include <vector>
+#include <new>
+
+static std::mutex g_shim_mu;       // the process-wide context of the reference-named shims: one batch at a time
+static hgpu_ctx *shim_ctx();
 
 static thread_local char g_err[512] = "";
 static std::atomic<uint64_t> g_launches{0};
@@ -285,6 +289,68 @@ extern "C" int hgpu_bgzf_inflate_blocks_host(hgpu_ctx *ctx, const uint8_t *in, c
     return HGPU_OK;
 }
 
+// A batch of bgzf_job-shaped blocks: every block has its OWN host buffers (bgzf.c:92-101 keeps
+// comp_data / uncomp_data inside each pooled job).  Gather into pinned staging, one H2D, one
+// launch, one D2H, scatter.  ctx == NULL uses the process-wide context of the reference-named
+// shims (one batch at a time).  uncomp_len[i]: in = room in uncomp[i], out = inflated length.
+extern "C" int hgpu_bgzf_inflate_jobs_host(hgpu_ctx *ctx, uint32_t n, const uint8_t *const *comp, const uint32_t *comp_len,
+                                           uint8_t *const *uncomp, uint32_t *uncomp_len, int32_t *status)
+{
+    if (n && (!comp || !comp_len || !uncomp || !uncomp_len || !status)) { hgpu_set_error("bad argument"); return HGPU_ERR_ARG; }
+    if (n == 0) return HGPU_OK;
+    std::unique_lock<std::mutex> lock(g_shim_mu, std::defer_lock);
+    if (!ctx) {
+        lock.lock();
+        ctx = shim_ctx();
+        if (!ctx) return HGPU_ERR_CUDA;
+    }
+    if (hgpu_check(cudaSetDevice(ctx->device), "cudaSetDevice")) return HGPU_ERR_CUDA;
+    try {
+        std::vector<uint64_t> ioff(n), ooff(n);
+        std::vector<uint32_t> cap(n);
+        uint64_t in_end = 0, out_end = 0;
+        for (uint32_t i = 0; i < n; i++) {
+            ioff[i] = in_end; in_end += ((uint64_t)comp_len[i] + 15) & ~(uint64_t)15;
+            cap[i] = uncomp_len[i] > 65536u ? 65536u : uncomp_len[i];
+            ooff[i] = out_end; out_end += ((uint64_t)cap[i] + 15) & ~(uint64_t)15;
+        }
+        const size_t in_bytes = ((size_t)in_end + 4 + 255) & ~(size_t)255, out_bytes = ((size_t)out_end + 255) & ~(size_t)255;
+        const size_t meta = (size_t)n * 32;
+        int rc = hgpu_ensure_stage(ctx, in_bytes + out_bytes + meta + 1024);
+        if (rc) return rc;
+        rc = hgpu_ensure_pinned(ctx, in_bytes + out_bytes + meta + 1024);
+        if (rc) return rc;
+        uint8_t *h_in = ctx->h_pinned, *h_out = h_in + in_bytes, *h_meta = h_out + out_bytes;
+        for (uint32_t i = 0; i < n; i++) memcpy(h_in + ioff[i], comp[i], comp_len[i]);
+        uint64_t *hm_ioff = (uint64_t *)h_meta, *hm_ooff = hm_ioff + n;
+        uint32_t *hm_ilen = (uint32_t *)(hm_ooff + n), *hm_cap = hm_ilen + n, *hm_got = hm_cap + n;
+        int32_t *hm_st = (int32_t *)(hm_got + n);
+        memcpy(hm_ioff, ioff.data(), n * 8); memcpy(hm_ooff, ooff.data(), n * 8);
+        memcpy(hm_ilen, comp_len, n * 4); memcpy(hm_cap, cap.data(), n * 4);
+        uint8_t *d_in = ctx->d_stage, *d_out = d_in + in_bytes, *d_meta = d_out + out_bytes;
+        uint64_t *d_ioff = (uint64_t *)d_meta, *d_ooff = d_ioff + n;
+        uint32_t *d_ilen = (uint32_t *)(d_ooff + n), *d_cap = d_ilen + n, *d_got = d_cap + n;
+        int32_t *d_st = (int32_t *)(d_got + n);
+        cudaStream_t s = ctx->stream;
+        if (hgpu_check(cudaMemcpyAsync(d_in, h_in, in_end, cudaMemcpyHostToDevice, s), "H2D")) return HGPU_ERR_CUDA;
+        if (hgpu_check(cudaMemcpyAsync(d_meta, h_meta, (size_t)n * 24, cudaMemcpyHostToDevice, s), "H2D")) return HGPU_ERR_CUDA;
+        rc = hgpu_launch_bgzf_inflate(ctx, d_in, d_ioff, d_ilen, n, d_out, d_ooff, d_cap, d_got, d_st, s);
+        if (rc) return rc;
+        if (hgpu_check(cudaMemcpyAsync(h_out, d_out, out_end, cudaMemcpyDeviceToHost, s), "D2H")) return HGPU_ERR_CUDA;
+        if (hgpu_check(cudaMemcpyAsync(hm_got, d_got, (size_t)n * 8, cudaMemcpyDeviceToHost, s), "D2H")) return HGPU_ERR_CUDA;
+        if (hgpu_check(cudaStreamSynchronize(s), "sync")) return HGPU_ERR_CUDA;
+        for (uint32_t i = 0; i < n; i++) {
+            status[i] = hm_st[i];
+            uncomp_len[i] = hm_st[i] == HGPU_OK ? hm_got[i] : 0;
+            if (hm_st[i] == HGPU_OK) memcpy(uncomp[i], h_out + ooff[i], hm_got[i]);
+        }
+        return HGPU_OK;
+    } catch (const std::bad_alloc &) {
+        hgpu_set_error("out of host memory");
+        return HGPU_ERR_NOMEM;
+    }
+}
+
 // zlib-compatible combine on the host side of the ABI: crc(A||B) from crc(A), crc(B), |B|
 static uint32_t h_multmodp(uint32_t a, uint32_t b)
 {
@@ -377,7 +443,6 @@ extern "C" int hgpu_rans_nx16_decode_batch_host(hgpu_ctx *ctx, const uint8_t *in
 
 // ------------------------------------------------------------------------------------------ shims
 
-static std::mutex g_shim_mu;
 static hgpu_ctx *g_shim_ctx;
 
 static hgpu_ctx *shim_ctx()

@@ -22,6 +22,7 @@
 // One CTA = one warp.  CTAs pull streams from an atomic work counter (persistent grid sized to
 // the SM count), largest streams first if the caller sorted them.
 #include "hgpu_internal.h"
+#include <stdio.h>
 
 namespace {
 
@@ -42,10 +43,25 @@ struct WarpScratch {
     uint8_t *tblbuf;   // TBLBUF_BYTES  : decoded order-1 table text
     uint8_t *gtab;     // GTAB_BYTES    : table overflow
     uint32_t max_out;
-    uint32_t smem_tab_bytes;
-    int pass;                // 0: small-table fast pass (defers what it cannot hold), 1: everything else
-    mutable bool defer;      // set when pass 0 hands the stream to pass 1
+    uint8_t *tab_base;       // shared-memory area tables are placed in ...
+    uint32_t tab_cap;        // ... and its size; larger tables go to gtab, or defer the stream when gtab is null
+    int pass;                // 0: small-table passes (defer what they cannot hold), 1: everything else
+    mutable bool defer;      // set when a small-table pass hands the stream to pass 1
+    struct Hook *hook;       // non-null: top-level plain streams stop after the table build (rans_nx16_fast.cuh)
 };
+
+// What a hooked dec_order0/1 hands back instead of running its symbol loop.
+struct Hook {
+    int mode;                // HOOK_X32: only 32-way streams stop; HOOK_N4: only 4-way streams stop
+    bool taken;
+    uint32_t order, N, shift, ncol, ipos, U, R, row0, tab_bytes;
+    const uint8_t *in; uint32_t in_len;
+    uint8_t *out;
+    uint8_t *lut; uint32_t *fb;
+    uint16_t *Fcap;          // HOOK_X32: [17][16] normalised frequencies of small alphabets (row 16 = flags), shared memory
+};
+constexpr int HOOK_X32 = 1, HOOK_N4 = 2;
+constexpr int RC_HOOKED = 2;
 
 // ---------------------------------------------------------------------------------------------
 // Warp-uniform scalar helpers: every lane runs the same code on the same addresses (loads
@@ -250,8 +266,8 @@ __device__ void loop_order0(uint8_t *smem, const Table &t, const uint8_t *in, ui
 {
     const uint32_t lane = hgpu_lane();
     const uint32_t mask = (1u << t.shift) - 1, shift = t.shift;
-    const uint8_t *lut = SMEM ? smem + SM_TAB : t.lut;
-    const uint32_t *fb = SMEM ? reinterpret_cast<const uint32_t *>(smem + SM_TAB + (((1u << t.shift) + 15u) & ~15u)) : t.fb;
+    const uint8_t *lut = t.lut;
+    const uint32_t *fb = t.fb;
     uint8_t *ring = smem + SM_RING;
     WordRing wr;
     ring_init(ring, wr, in, in_len, ipos);
@@ -302,11 +318,11 @@ __device__ void loop_order1(uint8_t *smem, const Table &t, const uint8_t *in, ui
 {
     const uint32_t lane = hgpu_lane();
     const uint32_t mask = (1u << t.shift) - 1, shift = t.shift;
-    const uint32_t fb_off = ((t.ncol << t.shift) + 15u) & ~15u;
-    const uint8_t *lut = SMEM ? smem + SM_TAB : t.lut;
-    const uint8_t *fbb = SMEM ? smem + SM_TAB + fb_off : reinterpret_cast<const uint8_t *>(t.fb);
+    const uint8_t *lut = t.lut;
+    const uint8_t *fbb = reinterpret_cast<const uint8_t *>(t.fb);
     const uint32_t sm_base = (uint32_t)__cvta_generic_to_shared(smem);
-    const uint32_t lut_a = sm_base + SM_TAB, fb_a = sm_base + SM_TAB + fb_off, ring_a = sm_base + SM_RING;
+    const uint32_t lut_a = SMEM ? (uint32_t)__cvta_generic_to_shared(t.lut) : 0u;
+    const uint32_t fb_a = SMEM ? (uint32_t)__cvta_generic_to_shared(t.fb) : 0u, ring_a = sm_base + SM_RING;
     uint8_t *ring = smem + SM_RING;
     WordRing wr;
     ring_init(ring, wr, in, in_len, ipos);
@@ -400,9 +416,10 @@ __device__ Table place_table(uint8_t *smem, const WarpScratch &ws, uint32_t rows
     Table t;
     uint32_t lut_bytes = ((rows << shift) + 15u) & ~15u;
     uint32_t need = lut_bytes + rows * ncol * 4u;
-    if (need > ws.smem_tab_bytes && ws.pass == 0) ws.defer = true;      // caller bails out
-    uint8_t *base = need <= ws.smem_tab_bytes ? smem + SM_TAB : ws.gtab;
-    t.in_smem = need <= ws.smem_tab_bytes;
+    (void)smem;
+    if (need > ws.tab_cap && !ws.gtab) ws.defer = true;                 // caller bails out
+    uint8_t *base = need <= ws.tab_cap ? ws.tab_base : ws.gtab;
+    t.in_smem = need <= ws.tab_cap;
     t.lut = base;
     t.fb = reinterpret_cast<uint32_t *>(base + lut_bytes);
     t.ncol = ncol;
@@ -412,7 +429,7 @@ __device__ Table place_table(uint8_t *smem, const WarpScratch &ws, uint32_t rows
 
 // order-0 stream: table + states + words  (rans_uncompress_O0_4x16 / _32x16)
 __device__ int dec_order0(uint8_t *smem, const WarpScratch &ws, const uint8_t *in, uint32_t in_len,
-                          uint8_t *out, uint32_t U, uint32_t N)
+                          uint8_t *out, uint32_t U, uint32_t N, bool top = false)
 {
     uint32_t *F = reinterpret_cast<uint32_t *>(smem + SM_F);
     uint32_t *cum = reinterpret_cast<uint32_t *>(smem + SM_CUM);
@@ -464,6 +481,19 @@ __device__ int dec_order0(uint8_t *smem, const WarpScratch &ws, const uint8_t *i
     uint32_t R;
     if (load_states(p, end, N, R)) return -1;
     uint32_t ipos = (uint32_t)(p - in) + 4 * N;
+    if (top && ws.hook && t.in_smem && ws.hook->mode == (N == 32 ? HOOK_X32 : HOOK_N4)) {
+        Hook &h = *ws.hook;
+        if (h.Fcap && ncol <= 16) {
+            __syncwarp();
+            if (lane < 16) h.Fcap[lane] = lane < ncol ? (uint16_t)F[lane] : (uint16_t)0;
+            if (lane == 0) h.Fcap[256] = 0;
+            __syncwarp();
+        }
+        h.taken = true; h.order = 0; h.N = N; h.shift = 12; h.ncol = ncol; h.ipos = ipos; h.U = U; h.R = R; h.row0 = 0;
+        h.in = in; h.in_len = in_len; h.out = out; h.lut = t.lut; h.fb = t.fb;
+        h.tab_bytes = ((4096u + 15u) & ~15u) + ncol * 4u;
+        return RC_HOOKED;
+    }
     if (t.in_smem) loop_order0<true>(smem, t, in, in_len, ipos, out, U, N, R);
     else           loop_order0<false>(smem, t, in, in_len, ipos, out, U, N, R);
     __syncwarp();
@@ -472,7 +502,7 @@ __device__ int dec_order0(uint8_t *smem, const WarpScratch &ws, const uint8_t *i
 
 // order-1 stream (rans_uncompress_O1_4x16 / _32x16; table = decode_freq1, :468-536)
 __device__ int dec_order1(uint8_t *smem, const WarpScratch &ws, const uint8_t *in, uint32_t in_len,
-                          uint8_t *out, uint32_t U, uint32_t N)
+                          uint8_t *out, uint32_t U, uint32_t N, bool top = false)
 {
     uint32_t *F = reinterpret_cast<uint32_t *>(smem + SM_F);
     uint32_t *cum = reinterpret_cast<uint32_t *>(smem + SM_CUM);
@@ -519,6 +549,12 @@ __device__ int dec_order1(uint8_t *smem, const WarpScratch &ws, const uint8_t *i
     Table t = place_table(smem, ws, ncol, ncol, shift);
     if (ws.defer) return -1;
     const uint32_t total = 1u << shift;
+    uint16_t *Fcap = (top && ws.hook && N == 32 && ncol <= 16) ? ws.hook->Fcap : nullptr;
+    if (Fcap) {                                   // row 16 = per-row "null row" flags
+        __syncwarp();
+        for (uint32_t k = lane; k < 17 * 16; k += 32) Fcap[k] = k >= 256 ? (uint16_t)1 : (uint16_t)0;
+        __syncwarp();
+    }
     for (uint32_t r = 0; r < ncol; r++) {
         if (r == 0 && !zero_in_a0) { fill_null_row(t, 0); continue; }
         // decode_freq_d (:425-456): one varint per alphabet symbol, zero followed by a run of zeros
@@ -554,6 +590,10 @@ __device__ int dec_order1(uint8_t *smem, const WarpScratch &ws, const uint8_t *i
         if (__any_sync(0xffffffffu, bad)) return -1;
         if (warp_cumsum(F, cum, (int)ncol) != total) return -1;
         fill_row(t, r, F, cum, symof, false);
+        if (Fcap) {
+            if (lane < ncol) Fcap[r * 16 + lane] = (uint16_t)F[lane];      // F <= 4096
+            if (lane == 0) Fcap[256 + r] = 0;
+        }
         __syncwarp();
     }
     __syncwarp();
@@ -563,6 +603,13 @@ __device__ int dec_order1(uint8_t *smem, const WarpScratch &ws, const uint8_t *i
     uint32_t R;
     if (load_states(p, end, N, R)) return -1;
     uint32_t ipos = (uint32_t)(p - in) + 4 * N;
+    if (top && ws.hook && t.in_smem && ws.hook->mode == (N == 32 ? HOOK_X32 : HOOK_N4)) {
+        Hook &h = *ws.hook;
+        h.taken = true; h.order = 1; h.N = N; h.shift = shift; h.ncol = ncol; h.ipos = ipos; h.U = U; h.R = R; h.row0 = 0;
+        h.in = in; h.in_len = in_len; h.out = out; h.lut = t.lut; h.fb = t.fb;
+        h.tab_bytes = (((ncol << shift) + 15u) & ~15u) + ncol * ncol * 4u;
+        return RC_HOOKED;
+    }
     if (t.in_smem) {
         if (N == 32) loop_order1<true, true>(smem, t, in, in_len, ipos, out, U, N, R, 0);
         else         loop_order1<true, false>(smem, t, in, in_len, ipos, out, U, N, R, 0);
@@ -727,8 +774,11 @@ __device__ int decode_plain(uint8_t *smem, const WarpScratch &ws, const uint8_t 
             if (t1_size > in_size || t1_size > out_size) return -1;
             for (uint32_t i = lane; i < t1_size; i += 32) t1[i] = in[i];
         } else {
-            int rc = order ? dec_order1(smem, ws, in, in_size, t1, t1_size, N)
-                           : dec_order0(smem, ws, in, in_size, t1, t1_size, N);
+            // only a stream with no transform may hand its symbol loop to the hooks (t1 == out then)
+            const bool top = !(fmt & 0xc0) && ws.hook != nullptr;
+            int rc = order ? dec_order1(smem, ws, in, in_size, t1, t1_size, N, top)
+                           : dec_order0(smem, ws, in, in_size, t1, t1_size, N, top);
+            if (rc == RC_HOOKED) return RC_HOOKED;
             if (rc) return -1;
         }
     } else
@@ -830,9 +880,11 @@ rans_nx16_decode_kernel(const uint8_t *__restrict__ in, const uint64_t *__restri
     ws.tblbuf = base + 3 * mo + 1024;
     ws.gtab = ws.tblbuf + TBLBUF_BYTES;
     ws.max_out = max_out;
-    ws.smem_tab_bytes = smem_tab_bytes;
+    ws.tab_base = smem + SM_TAB;
+    ws.tab_cap = smem_tab_bytes;
     ws.pass = PASS;
     ws.defer = false;
+    ws.hook = nullptr;
     if (PASS == 0) { ws.tmp = ws.planes = ws.meta = ws.gtab = nullptr; ws.tblbuf = base; }
     for (;;) {
         uint32_t job = 0;
@@ -851,6 +903,8 @@ rans_nx16_decode_kernel(const uint8_t *__restrict__ in, const uint64_t *__restri
     }
 }
 
+
+#include "rans_nx16_fast.cuh"
 
 // =============================================================================================
 // rANS 4x8 (CRAM 3.0 block method 4, "RANS") — replaces rans_uncompress / rans_uncompress_O0/_O1
@@ -1029,16 +1083,44 @@ rans_4x8_decode_kernel(const uint8_t *__restrict__ in, const uint64_t *__restric
 
 } // namespace
 
-// streams the fast pass keeps resident at once (persistent grid size): callers that can choose
-// their batch size should use a multiple of it.
+// 32-way streams the fast kernel keeps resident at once (persistent grid size): callers that can
+// choose their batch size should use a multiple of it.
+static uint32_t g_f32_smem[64];        // per device: dynamic shared bytes of the fast32 kernel
+
+static uint32_t f32_smem(hgpu_ctx *ctx) { int d = ctx->device; return d >= 0 && d < 64 && g_f32_smem[d] ? g_f32_smem[d] : F32_SMEM + F32_LUT; }
+
+static int rans_attrs(hgpu_ctx *ctx)
+{
+    // function attributes are per device: set them once per device, not once per process
+    static bool done[64];
+    int dev = ctx->device;
+    if (dev >= 0 && dev < 64 && done[dev]) return 0;
+    {   // fast32 wants its LUTs 4 KiB aligned in the shared window: probe where the window starts
+        uint32_t *d_o = nullptr, base = 0;
+        if (hgpu_check(cudaMalloc(&d_o, 4), "probe alloc")) return -1;
+        rans_smem_probe_kernel<<<1, 32, 1024>>>(d_o);
+        cudaError_t e = cudaMemcpy(&base, d_o, 4, cudaMemcpyDeviceToHost);
+        cudaFree(d_o);
+        if (hgpu_check(e, "smem probe")) return -1;
+        uint32_t lut0 = (base + F32_WARPS * F32_RING + F32_LUT - 1) & ~(F32_LUT - 1);
+        if (dev >= 0 && dev < 64) g_f32_smem[dev] = lut0 + F32_WARPS * (F32_LUT + F32_FB) - base;
+    }
+    if (hgpu_check(cudaFuncSetAttribute(rans_nx16_decode_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(SM_TAB + 18 * 1024)), "rans smem attr") ||
+        hgpu_check(cudaFuncSetAttribute(rans_prep32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PREP_SMEM), "rans smem attr") ||
+        hgpu_check(cudaFuncSetAttribute(rans_tile4_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)T4_SMEM), "rans smem attr") ||
+        hgpu_check(cudaFuncSetAttribute(rans_fast32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)f32_smem(ctx)), "rans smem attr"))
+        return -1;
+    if (dev >= 0 && dev < 64) done[dev] = true;
+    return 0;
+}
+
 extern "C" uint32_t hgpu_rans_nx16_wave_size(hgpu_ctx *ctx)
 {
     if (!ctx) return 0;
-    int per_sm0 = 0;
-    const uint32_t smem0 = SM_TAB + 6656;
-    cudaFuncSetAttribute(rans_nx16_decode_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem0);
-    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm0, rans_nx16_decode_kernel<0>, 32, smem0) != cudaSuccess) return 0;
-    return (uint32_t)ctx->sm_count * (uint32_t)(per_sm0 < 1 ? 1 : per_sm0);
+    if (cudaSetDevice(ctx->device) != cudaSuccess || rans_attrs(ctx)) return 0;
+    int per_sm = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, rans_fast32_kernel, F32_WARPS * 32, f32_smem(ctx)) != cudaSuccess) return 0;
+    return (uint32_t)ctx->sm_count * (uint32_t)(per_sm < 1 ? 1 : per_sm) * F32_WARPS;
 }
 
 int hgpu_launch_rans_nx16(hgpu_ctx *ctx, const uint8_t *d_in, const uint64_t *d_in_off,
@@ -1048,45 +1130,58 @@ int hgpu_launch_rans_nx16(hgpu_ctx *ctx, const uint8_t *d_in, const uint64_t *d_
                           cudaStream_t st)
 {
     if (n == 0) return HGPU_OK;
-    // Two passes over the same job list, no host synchronisation in between.
-    //  pass 0: plain streams (no PACK/RLE/STRIPE) whose table fits 6.5 KiB of shared memory — every
-    //          order-0 table and order-1 tables of small alphabets (NovaSeq qualities) — at up to
-    //          24 single-warp CTAs per SM and 256 KiB of scratch per CTA;
-    //  pass 1: whatever pass 0 deferred, with 18 KiB of table space, the transform scratch and
-    //          the global-memory table fallback.
-    const uint32_t smem_tab0 = 6656, smem_tab1 = 18 * 1024;
-    const uint32_t smem0 = SM_TAB + smem_tab0, smem1 = SM_TAB + smem_tab1;
-    static bool attr_set = false;
-    if (!attr_set) {
-        if (hgpu_check(cudaFuncSetAttribute(rans_nx16_decode_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem0), "rans smem attr") ||
-            hgpu_check(cudaFuncSetAttribute(rans_nx16_decode_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem1), "rans smem attr"))
-            return HGPU_ERR_CUDA;
-        attr_set = true;
-    }
-    int per_sm0 = 0, per_sm1 = 0;
-    if (hgpu_check(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm0, rans_nx16_decode_kernel<0>, 32, smem0), "rans occupancy") ||
-        hgpu_check(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm1, rans_nx16_decode_kernel<1>, 32, smem1), "rans occupancy"))
+    // Five launches over one job list, no host synchronisation in between:
+    //  classify  format byte -> ordered lists of plain 32-way and plain 4-way streams; the rest is "deferred"
+    //  prep32    32-way plain streams: header + table; small alphabets become fast32 jobs (after 4 head
+    //            steps), the others are decoded there with the general loops (table <= 6.5 KiB) or deferred
+    //  tile4     4-way plain streams, eight per warp
+    //  fast32    the symbol loop of the 32-way jobs, 44 streams per SM
+    //  general   everything deferred: PACK / RLE / STRIPE / CAT, big tables (18 KiB shared, else global)
+    if (hgpu_check(cudaSetDevice(ctx->device), "cudaSetDevice") || rans_attrs(ctx)) return HGPU_ERR_CUDA;
+    const uint32_t smem1 = SM_TAB + 18 * 1024;
+    int per_prep = 0, per_t4 = 0, per_f32 = 0, per_gen = 0;
+    if (hgpu_check(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_prep, rans_prep32_kernel, 32, PREP_SMEM), "rans occupancy") ||
+        hgpu_check(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_t4, rans_tile4_kernel, 32, T4_SMEM), "rans occupancy") ||
+        hgpu_check(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_f32, rans_fast32_kernel, F32_WARPS * 32, f32_smem(ctx)), "rans occupancy") ||
+        hgpu_check(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_gen, rans_nx16_decode_kernel<1>, 32, smem1), "rans occupancy"))
         return HGPU_ERR_CUDA;
-    if (per_sm0 < 1) per_sm0 = 1;
-    if (per_sm1 < 1) per_sm1 = 1;
-    uint32_t grid0 = (uint32_t)ctx->sm_count * (uint32_t)per_sm0, grid1 = (uint32_t)ctx->sm_count * (uint32_t)per_sm1;
-    if (grid0 > n) grid0 = n;
-    if (grid1 > n) grid1 = n;
-    size_t mo = ((size_t)max_out_len + 255) & ~(size_t)255;
-    size_t per_cta0 = TBLBUF_BYTES;
-    size_t per_cta1 = (3 * mo + 1024 + TBLBUF_BYTES + GTAB_BYTES + 255) & ~(size_t)255;
-    size_t need0 = per_cta0 * grid0, need1 = per_cta1 * grid1;
-    int rc = hgpu_ensure_scratch(ctx, need0 > need1 ? need0 : need1);
+    auto grid_of = [&](int per_sm, uint32_t units) {
+        uint32_t g = (uint32_t)ctx->sm_count * (uint32_t)(per_sm < 1 ? 1 : per_sm);
+        return g > units ? (units ? units : 1u) : g;
+    };
+    const uint32_t g_prep = grid_of(per_prep, n), g_t4 = grid_of(per_t4, (n + 7) / 8 + 1);
+    const uint32_t g_f32 = grid_of(per_f32, (n + F32_WARPS - 1) / F32_WARPS), g_gen = grid_of(per_gen, n);
+    // scratch: [lists 2n u32][counts 4 u32][fast jobs n] | per-CTA areas of the pass that is running
+    const size_t lists_b = ((size_t)2 * n * 4 + 255) & ~(size_t)255;
+    const size_t jobs_b = (((size_t)n * sizeof(FastJob)) + 255) & ~(size_t)255;
+    const size_t fixed = lists_b + 256 + jobs_b;
+    const size_t mo = ((size_t)max_out_len + 255) & ~(size_t)255;
+    const size_t per_small = TBLBUF_BYTES;
+    const size_t per_gen_b = (3 * mo + 1024 + TBLBUF_BYTES + GTAB_BYTES + 255) & ~(size_t)255;
+    size_t area = per_small * g_prep;
+    if (per_small * g_t4 > area) area = per_small * g_t4;
+    if (per_gen_b * g_gen > area) area = per_gen_b * g_gen;
+    int rc = hgpu_ensure_scratch(ctx, fixed + area);
     if (rc) return rc;
-    uint32_t *c0 = hgpu_take_counter(ctx, st), *c1 = hgpu_take_counter(ctx, st);
-    if (!c0 || !c1) return HGPU_ERR_CUDA;
-    rans_nx16_decode_kernel<0><<<grid0, 32, smem0, st>>>(d_in, d_in_off, d_in_len, n, d_out, d_out_off, d_out_len,
-                                                         d_got_len, d_status, ctx->d_scratch, per_cta0,
-                                                         max_out_len, smem_tab0, c0);
-    rans_nx16_decode_kernel<1><<<grid1, 32, smem1, st>>>(d_in, d_in_off, d_in_len, n, d_out, d_out_off, d_out_len,
-                                                         d_got_len, d_status, ctx->d_scratch, per_cta1,
-                                                         max_out_len, smem_tab1, c1);
-    hgpu_count_launch(2);
+    uint8_t *sc = ctx->d_scratch;
+    uint32_t *list32 = reinterpret_cast<uint32_t *>(sc), *list4 = list32 + n;
+    uint32_t *counts = reinterpret_cast<uint32_t *>(sc + lists_b);
+    FastJob *jobs = reinterpret_cast<FastJob *>(sc + lists_b + 256);
+    uint8_t *percta = sc + fixed;
+    uint32_t *c_prep = hgpu_take_counter(ctx, st), *c_t4 = hgpu_take_counter(ctx, st), *c_f32 = hgpu_take_counter(ctx, st);
+    uint32_t *c_gen = hgpu_take_counter(ctx, st), *njobs = hgpu_take_counter(ctx, st);
+    if (!c_prep || !c_t4 || !c_f32 || !c_gen || !njobs) return HGPU_ERR_CUDA;
+    rans_classify_kernel<<<1, 1024, 0, st>>>(d_in, d_in_off, d_in_len, n, d_status, list32, list4, counts);
+    rans_prep32_kernel<<<g_prep, 32, PREP_SMEM, st>>>(d_in, d_in_off, d_in_len, list32, counts, d_out, d_out_off, d_out_len,
+                                                      d_got_len, d_status, percta, per_small, max_out_len, jobs, njobs, c_prep);
+    rans_tile4_kernel<<<g_t4, 32, T4_SMEM, st>>>(d_in, d_in_off, d_in_len, list4, counts, d_out, d_out_off, d_out_len,
+                                                 d_got_len, d_status, percta, per_small, max_out_len, c_t4);
+    rans_fast32_kernel<<<g_f32, F32_WARPS * 32, f32_smem(ctx), st>>>(jobs, njobs, d_in, d_in_off, d_in_len, d_out, d_out_off, d_out_len,
+                                                                     d_status, c_f32, f32_smem(ctx));
+    rans_nx16_decode_kernel<1><<<g_gen, 32, smem1, st>>>(d_in, d_in_off, d_in_len, n, d_out, d_out_off, d_out_len,
+                                                         d_got_len, d_status, percta, per_gen_b,
+                                                         max_out_len, 18 * 1024, c_gen);
+    hgpu_count_launch(5);
     return hgpu_check(cudaGetLastError(), "rans launch");
 }
 

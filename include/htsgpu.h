@@ -72,6 +72,14 @@ int hgpu_bgzf_inflate_blocks_host(hgpu_ctx *ctx,
         uint8_t *out, const uint64_t *out_off, const uint32_t *out_cap,
         uint32_t *out_len, int32_t *status);
 
+/* The thread-pool job seam itself (integration/htsgpu_bgzf.patch): a batch of
+ * bgzf_job (bgzf.c:92-101) — every block has its own comp_data / uncomp_data host buffers.
+ * comp[i]/comp_len[i]: one whole BGZF block; uncomp[i]: 64 KiB job buffer; uncomp_len[i]: in = room,
+ * out = inflated length; status[i]: HGPU_OK or HGPU_BGZF_ERR_* (-> j->errcode |= BGZF_ERR_ZLIB,
+ * bgzf.c:1381).  ctx == NULL: the process-wide context the reference-named shims use. */
+int hgpu_bgzf_inflate_jobs_host(hgpu_ctx *ctx, uint32_t n, const uint8_t *const *comp, const uint32_t *comp_len,
+        uint8_t *const *uncomp, uint32_t *uncomp_len, int32_t *status);
+
 /* BGZF COMPRESS — replaces bgzf_compress / deflate_block as run per job by bgzf_encode_func
  * (bgzf.c:624-683, :709, :1330) for a batch of payloads (each <= 65280 bytes; htslib uses
  * BGZF_BLOCK_SIZE 0xff00), one warp per payload.  Every out slot is 65536 bytes, 4-byte aligned;
