@@ -131,7 +131,7 @@ __device__ __forceinline__ void bits_init(Bits &b, const uint8_t *src, uint32_t 
 __device__ __forceinline__ void bits_fill(Bits &b)
 {
     if (b.cnt <= 32) {
-        uint32_t v = b.w < b.wend ? __ldg(b.w) : 0;
+        uint32_t v = b.w < b.wend ? (*b.w) : 0;
         b.w++;
         b.buf |= (uint64_t)v << b.cnt;
         b.cnt += 32;
@@ -501,8 +501,8 @@ __device__ __forceinline__ void lb_init(LaneBits &b, const uint32_t *wbase, cons
 {
     uint32_t wi = start >> 5, off = start & 31;
     const uint32_t *p = wbase + wi;
-    uint32_t w0 = p < wend ? __ldg(p) : 0;
-    b.nxt = p + 1 < wend ? __ldg(p + 1) : 0;
+    uint32_t w0 = p < wend ? p[0] : 0;
+    b.nxt = p + 1 < wend ? p[1] : 0;
     b.w = p + 2;
     b.buf = w0 >> off;
     b.cnt = 32 - (int)off;
@@ -514,7 +514,7 @@ __device__ __forceinline__ void lb_fill(LaneBits &b, const uint32_t *wend)
         b.buf |= (uint64_t)b.nxt << b.cnt;
         b.cnt += 32;
         b.lim += 32;
-        b.nxt = b.w < wend ? __ldg(b.w) : 0;
+        b.nxt = b.w < wend ? (*b.w) : 0;
         b.w++;
     }
 }
@@ -537,11 +537,14 @@ enum : uint32_t { ST_RUN = 0, ST_EOB = 1, ST_BAD = 2 };
 // Decode tokens in [start, end).  EMIT=false: count output bytes / matches.  EMIT=true: write
 // literals at out[obase..] and match records at mrec[mbase..]; sets bad_dist on a distance that
 // reaches before the start of the output.
-template <bool EMIT>
+// EMIT: 0 count only; 1 literals to out[] + {dst, len | dist<<16} records to mrec[]; 2 literals to
+// out[] + a 3-byte record {len-3, dist-1 (15 bits)} parked IN the output at the match's own
+// destination (a match owns >= 3 bytes there) + its destination in the 16-bit list dlist[].
+template <int EMIT>
 __device__ __forceinline__ void lane_decode(const InflateSmem &s, const uint32_t *wbase, const uint32_t *wend,
                                             uint32_t start, uint32_t end, uint32_t &exitp, uint32_t &nout,
                                             uint32_t &nmatch, uint32_t &st, uint8_t *out, uint32_t obase,
-                                            uint2 *mrec, uint32_t mbase, bool &bad_dist)
+                                            uint2 *mrec, uint32_t mbase, bool &bad_dist, uint16_t *dlist = nullptr)
 {
     LaneBits b;
     uint32_t n = 0, m = 0, status = ST_RUN;
@@ -564,10 +567,17 @@ __device__ __forceinline__ void lane_decode(const InflateSmem &s, const uint32_t
             uint32_t xd = (d >> 8) & 0xff;
             uint32_t dist = (d >> 16) + ((uint32_t)b.buf & ((1u << xd) - 1));
             b.buf >>= xd; b.cnt -= (int)xd;
-            if (EMIT) {
+            if (EMIT == 1) {
                 uint32_t dstpos = obase + n;
                 if (dist > dstpos) bad_dist = true;
                 mrec[mbase + m] = make_uint2(dstpos, len | (dist << 16));
+            } else if (EMIT == 2) {
+                uint32_t dstpos = obase + n;
+                if (dist > dstpos) bad_dist = true;
+                out[dstpos] = (uint8_t)(len - 3);
+                out[dstpos + 1] = (uint8_t)(dist - 1);
+                out[dstpos + 2] = (uint8_t)((dist - 1) >> 8);
+                dlist[mbase + m] = (uint16_t)dstpos;
             }
             n += len; m++;
         } else if (kind == K_EOB) { status = ST_EOB; break; }
@@ -608,7 +618,7 @@ __device__ int decode_body_parallel(InflateSmem &s, const uint32_t *wbase, const
     uint32_t exitp = 0, n = 0, m = 0, st = ST_RUN;
     bool need = true, dummy = false;
     for (int round = 0; round < 34; round++) {
-        if (need) lane_decode<false>(s, wbase, wend, start, end, exitp, n, m, st, nullptr, 0, nullptr, 0, dummy);
+        if (need) lane_decode<0>(s, wbase, wend, start, end, exitp, n, m, st, nullptr, 0, nullptr, 0, dummy);
         uint32_t prev = __shfl_up_sync(0xffffffffu, exitp, 1);
         uint32_t ns = lane == 0 ? start : prev;
         need = ns != start;
@@ -638,7 +648,7 @@ __device__ int decode_body_parallel(InflateSmem &s, const uint32_t *wbase, const
     bool bad_dist = false;
     if (lane <= E) {
         uint32_t e2, n2, m2, st2;
-        lane_decode<true>(s, wbase, wend, start, end, e2, n2, m2, st2, out, o + on - n, mrec, mn - m, bad_dist);
+        lane_decode<1>(s, wbase, wend, start, end, e2, n2, m2, st2, out, o + on - n, mrec, mn - m, bad_dist);
     }
     if (__any_sync(0xffffffffu, bad_dist)) return HGPU_BGZF_ERR_ZLIB;   // distance too far back
     __syncwarp();
@@ -863,22 +873,39 @@ bgzf_inflate_kernel(const uint8_t *__restrict__ in, const uint64_t *__restrict__
 //       body of the payload; the window is laid out so shared and global addresses are
 //       congruent mod 16, the few head/tail bytes are stored directly.
 // =============================================================================================
-constexpr int CTA_T = 128;
-constexpr uint32_t WIN_BYTES = 65536 + 16;
+constexpr int CTA_T = 256;
+constexpr uint32_t WIN_BYTES = 65536 + 32;          // 16 bytes of alignment slack in front, word reads may run 4 bytes past the end
+constexpr uint32_t STAGE_BYTES = 24 * 1024;         // compressed blocks up to this size are staged in shared memory (TMA)
+constexpr uint32_t SEG_M = 4096;                    // matches resolved per LZ77 segment
 
 struct CtaCtl {              // broadcast from warp 0 / thread 0 to the CTA
     int32_t rc;
-    uint32_t mode, final_, body, o, end_pos, job, E, bad, tot_m;
-    uint32_t crc[4];
+    uint32_t mode, final_, body, o, end_pos, job, next_job, E, bad, tot_m, phase;
+    uint32_t crc[8];
     long long t0;            // HGPU_PROFILE: start of the current phase
 };
 enum : uint32_t { MODE_NEXT = 0, MODE_PAR = 1 };
 
+struct LzSmem {              // P3: match resolution state of one segment (overlays the decode tables)
+    uint32_t deps[SEG_M];    // first | end << 16 of the earlier matches (segment-relative) this match reads from
+    uint32_t done[SEG_M / 32];
+};
+
 struct CtaSmem {
     uint8_t win[WIN_BYTES];
-    InflateSmem s;
+    uint8_t stage[STAGE_BYTES + 32];
+    union {
+        InflateSmem s;               // P1, P2: decode tables + their scratch
+        LzSmem z;                    // P3
+        uint32_t crc_tab[4][256];    // P4
+    };
+    uint16_t D[SEG_M];               // destinations of the segment's matches (written by P2 while the tables are live)
     CtaCtl c;
+    unsigned long long mbar;         // mbarrier of the staging copy
 };
+
+static_assert(sizeof(CtaSmem) <= 115712, "two CTAs per SM: 2 x (size + 1 KiB) must fit 228 KiB");
+static_assert(sizeof(LzSmem) >= sizeof(InflateSmem), "the LZ state is the largest member of the union");
 
 #ifdef HGPU_PROFILE
 #define CTA_MARK(cs, i) do { if (threadIdx.x == 0) { long long n_ = clock64(); atomicAdd(&g_prof[i], (unsigned long long)(n_ - (cs).c.t0)); (cs).c.t0 = n_; } } while (0)
@@ -886,9 +913,34 @@ struct CtaSmem {
 #define CTA_MARK(cs, i) do { } while (0)
 #endif
 
-// P2: all threads.  Returns a CTA-uniform status.
+// ---- TMA (1-D bulk copy) helpers -------------------------------------------------------------
+__device__ __forceinline__ void mbar_init(unsigned long long *mb, uint32_t count)
+{
+    uint32_t a = (uint32_t)__cvta_generic_to_shared(mb);
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(a), "r"(count) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void tma_load_1d(void *smem_dst, const void *gsrc, uint32_t bytes, unsigned long long *mb)
+{
+    uint32_t d = (uint32_t)__cvta_generic_to_shared(smem_dst), m = (uint32_t)__cvta_generic_to_shared(mb);
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(m), "r"(bytes) : "memory");
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 :: "r"(d), "l"(gsrc), "r"(bytes), "r"(m) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long *mb, uint32_t parity)
+{
+    uint32_t m = (uint32_t)__cvta_generic_to_shared(mb), ok = 0;
+    while (!ok) {
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                     : "=r"(ok) : "r"(m), "r"(parity) : "memory");
+    }
+}
+
+// P2: all threads.  Returns a CTA-uniform status.  Matches are parked in the window (lane_decode<2>)
+// with their destinations in dlist (cs.D when the block has at most SEG_M matches, else the CTA's
+// global slot).
 __device__ int decode_body_cta(CtaSmem &cs, const uint32_t *wbase, const uint32_t *wend, uint32_t body,
-                               uint32_t total, uint8_t *out, uint32_t cap, uint2 *mrec)
+                               uint32_t total, uint8_t *out, uint32_t cap, uint16_t *dglobal)
 {
     InflateSmem &s = cs.s;
     const uint32_t t = threadIdx.x, lane = t & 31, warp = t >> 5;
@@ -900,7 +952,7 @@ __device__ int decode_body_cta(CtaSmem &cs, const uint32_t *wbase, const uint32_
     uint32_t exitp = 0, n = 0, m = 0, st = ST_RUN;
     bool need = true, dummy = false;
     for (int round = 0; round < CTA_T + 2; round++) {
-        if (need) lane_decode<false>(s, wbase, wend, start, end, exitp, n, m, st, nullptr, 0, nullptr, 0, dummy);
+        if (need) lane_decode<0>(s, wbase, wend, start, end, exitp, n, m, st, nullptr, 0, nullptr, 0, dummy);
         s.x_exit[t] = exitp;
         __syncthreads();
         uint32_t ns = t == 0 ? start : s.x_exit[t - 1];
@@ -926,7 +978,7 @@ __device__ int decode_body_cta(CtaSmem &cs, const uint32_t *wbase, const uint32_
         uint32_t a = __shfl_up_sync(0xffffffffu, on, d), c = __shfl_up_sync(0xffffffffu, mn, d);
         if (lane >= (uint32_t)d) { on += a; mn += c; }
     }
-    __syncthreads();                                             // x_exit reads are over: x_sum may overlap nothing, but keep phases apart
+    __syncthreads();
     if (lane == 31) { s.x_sum[0][warp] = on; s.x_sum[1][warp] = mn; }
     __syncthreads();
     uint32_t tot_out = 0, tot_m = 0, pre_o = 0, pre_m = 0;
@@ -944,7 +996,8 @@ __device__ int decode_body_cta(CtaSmem &cs, const uint32_t *wbase, const uint32_
     bool bad_dist = false;
     if (t <= E) {
         uint32_t e2, n2, m2, st2;
-        lane_decode<true>(s, wbase, wend, start, end, e2, n2, m2, st2, out, o + on - n, mrec, mn - m, bad_dist);
+        lane_decode<2>(s, wbase, wend, start, end, e2, n2, m2, st2, out, o + on - n, nullptr, mn - m, bad_dist,
+                       tot_m <= SEG_M ? cs.D : dglobal);
     }
     if (__syncthreads_or(bad_dist)) return HGPU_BGZF_ERR_ZLIB;   // distance too far back
     if (t == 0) { cs.c.o = o + tot_out; cs.c.tot_m = tot_m; }
@@ -954,13 +1007,112 @@ __device__ int decode_body_cta(CtaSmem &cs, const uint32_t *wbase, const uint32_
     return HGPU_OK;
 }
 
+// One match, one thread: w[dst .. dst+len) = w[dst-dist ...], LZ77 semantics (the source may
+// overlap the destination).  Aligned 32-bit stores with a funnel-shifted source when that is
+// safe (a word is only read after every byte of it has been written: dist >= 8, or no overlap).
+__device__ __forceinline__ void lz_copy(uint8_t *w, uint32_t dst, uint32_t dist, uint32_t len)
+{
+    uint8_t *d = w + dst;
+    const uint8_t *s = d - dist;
+    uint32_t n = len;
+    if (dist >= 8 || dist >= len) {
+        while (n && (reinterpret_cast<uintptr_t>(d) & 3)) { *d++ = *s++; n--; }
+        if (n >= 4) {
+            const uint32_t sh = (uint32_t)(reinterpret_cast<uintptr_t>(s) & 3) * 8;
+            const volatile uint32_t *ws = reinterpret_cast<const volatile uint32_t *>(reinterpret_cast<uintptr_t>(s) & ~(uintptr_t)3);
+            volatile uint32_t *wd = reinterpret_cast<volatile uint32_t *>(d);
+            uint32_t lo = *ws++;
+            const uint32_t nw = n >> 2;
+            for (uint32_t k = 0; k < nw; k++) {
+                uint32_t hi = sh ? *ws : 0u;
+                ws++;
+                *wd++ = __funnelshift_r(lo, hi, sh);
+                lo = sh ? hi : *(ws - 1);
+            }
+            d += nw * 4; s += nw * 4; n &= 3;
+        }
+        while (n) { *d++ = *s++; n--; }
+    } else {
+        volatile uint8_t *dv = d;
+        const volatile uint8_t *sv = s;
+        for (uint32_t k = 0; k < n; k++) dv[k] = sv[k];          // in order: later bytes read earlier ones
+    }
+}
+
+// P3: LZ77 resolution of the matches parked by P2, the whole CTA.
+//
+// The matches of a deflate block form a dependency DAG about 130 levels deep with ~18 matches per
+// level on sorted BAM (a record copies from the record before it).  Thread t owns matches
+// t, t+256, ... and takes them in order; a match runs when every earlier match that writes into its
+// source range is done (a contiguous index range, two binary searches over the sorted
+// destinations, precomputed for the whole segment in parallel); one barrier per round.
+__device__ void lz_resolve_cta(CtaSmem &cs, uint8_t *w, uint32_t tot_m, const uint16_t *dglobal)
+{
+    const uint32_t t = threadIdx.x;
+    for (uint32_t seg0 = 0; seg0 < tot_m; seg0 += SEG_M) {
+        const uint32_t n = min(SEG_M, tot_m - seg0);
+        if (tot_m > SEG_M) {                                     // destinations live in the global slot
+            __syncthreads();
+            for (uint32_t i = t; i < n; i += CTA_T) cs.D[i] = dglobal[seg0 + i];
+        }
+        for (uint32_t i = t; i < SEG_M / 32; i += CTA_T) cs.z.done[i] = 0;
+        __syncthreads();
+        // dependency ranges
+        for (uint32_t i = t; i < n; i += CTA_T) {
+            const uint32_t dst = cs.D[i];
+            const uint32_t len = (uint32_t)w[dst] + 3u, dist = ((uint32_t)w[dst + 1] | (uint32_t)w[dst + 2] << 8) + 1u;
+            const uint32_t s0 = dst - dist, s1 = dist < len ? dst : s0 + len;
+            // ub = #{D <= s0}, lb = #{D < s1}, over D[0..i)
+            uint32_t lo0 = 0, hi0 = i, lo1 = 0, hi1 = i;
+            while (lo0 < hi0 || lo1 < hi1) {
+                if (lo0 < hi0) { uint32_t mid = (lo0 + hi0) >> 1; if (cs.D[mid] <= s0) lo0 = mid + 1; else hi0 = mid; }
+                if (lo1 < hi1) { uint32_t mid = (lo1 + hi1) >> 1; if (cs.D[mid] < s1) lo1 = mid + 1; else hi1 = mid; }
+            }
+            const uint32_t first = lo0 ? lo0 - 1 : 0u, end = lo1;
+            cs.z.deps[i] = first < end ? (first | end << 16) : 0u;
+        }
+        __syncthreads();
+        // rounds
+        volatile uint32_t *done = cs.z.done;
+        uint32_t i = t;
+        uint32_t dep = i < n ? cs.z.deps[i] : 0u;
+        for (;;) {
+            if (i < n) {
+                const uint32_t first = dep & 0xffffu, end = dep >> 16;
+                bool ready = true;
+                if (first < end) {
+                    const uint32_t w0 = first >> 5, w1 = (end - 1) >> 5;
+                    for (uint32_t k = w0; k <= w1 && ready; k++) {
+                        uint32_t mask = 0xffffffffu;
+                        if (k == w0) mask &= 0xffffffffu << (first & 31);
+                        if (k == w1) mask &= 0xffffffffu >> (31 - ((end - 1) & 31));
+                        ready = (done[k] & mask) == mask;
+                    }
+                }
+                if (ready) {
+                    __threadfence_block();                           // acquire: the bytes behind the done bits
+                    const uint32_t dst = cs.D[i];
+                    const uint32_t len = (uint32_t)w[dst] + 3u, dist = ((uint32_t)w[dst + 1] | (uint32_t)w[dst + 2] << 8) + 1u;
+                    lz_copy(w, dst, dist, len);
+                    __threadfence_block();                           // release
+                    atomicOr(&cs.z.done[i >> 5], 1u << (i & 31));
+                    i += CTA_T;
+                    dep = i < n ? cs.z.deps[i] : 0u;
+                }
+            }
+            if (!__syncthreads_or(i < n)) break;
+        }
+    }
+    __syncthreads();
+}
+
 // One member: warp 0 walks the deflate block headers, the CTA decodes Huffman bodies.
+// src may point into shared memory (staged block) or global memory.
 __device__ int inflate_member_cta(CtaSmem &cs, const uint8_t *src, uint32_t slen, uint8_t *out, uint32_t cap,
                                   uint32_t &olen, uint2 *mrec)
 {
     InflateSmem &s = cs.s;
     const uint32_t lane = hgpu_lane(), warp = threadIdx.x >> 5;
-    Prof pf;
     Bits b;
     const uintptr_t a0 = reinterpret_cast<uintptr_t>(src);
     const uint32_t mis_bits = (uint32_t)(a0 & 3) * 8;
@@ -1084,54 +1236,76 @@ __device__ int inflate_member_cta(CtaSmem &cs, const uint8_t *src, uint32_t slen
         if (cs.c.rc) return cs.c.rc;
         const uint32_t final_ = cs.c.final_;
         if (cs.c.mode == MODE_PAR) {
-            int rc = decode_body_cta(cs, wbase, wend, cs.c.body, total, out, cap, mrec);
+            uint16_t *dglobal = reinterpret_cast<uint16_t *>(mrec);
+            int rc = decode_body_cta(cs, wbase, wend, cs.c.body, total, out, cap, dglobal);
             if (rc) return rc;
-            // ---- P3: LZ77 on the shared window, one warp ----
-            if (warp == 0) {
-                run_matches(s, out, mrec, cs.c.tot_m);
+            const uint32_t tot_m = cs.c.tot_m, end_pos = cs.c.end_pos;
+            __syncthreads();                                         // the tables are dead from here: P3 state overlays them
+            lz_resolve_cta(cs, out, tot_m, dglobal);
+            if (warp == 0 && !final_) {
                 // continue the uniform reader right after the end-of-block code
-                uint32_t end_pos = cs.c.end_pos;
                 uint32_t byte = (end_pos - mis_bits) >> 3, bit = (end_pos - mis_bits) & 7;
                 bits_init(b, src, byte, slen);
                 bits_fill(b);
                 bits_drop(b, bit);
             }
-            __threadfence_block();
-            __syncthreads();
             CTA_MARK(cs, 3);
         }
         if (final_) break;
     }
     olen = cs.c.o;
-    (void)pf;
     return HGPU_OK;
 }
 
-// CRC-32 of win[0..n) by the CTA (4 warps, one quarter each), result CTA-uniform.
+// CRC-32 of p[0..n) by the CTA (8 warps, one eighth each; slice-by-4 tables in shared memory), CTA-uniform.
 __device__ uint32_t cta_crc32(CtaSmem &cs, const uint8_t *p, uint32_t n)
 {
     const uint32_t warp = threadIdx.x >> 5;
-    const uint32_t q = n / 4;
-    const uint32_t beg = warp * q, len = warp == 3 ? n - 3 * q : q;
-    uint32_t crc = warp_crc32(g_crc_tab, p + beg, len);          // tables via L1 (4 KiB, read-only)
+    constexpr uint32_t NW = CTA_T / 32;
+    for (uint32_t i = threadIdx.x; i < 1024; i += CTA_T) (&cs.crc_tab[0][0])[i] = (&g_crc_tab[0][0])[i];
+    __syncthreads();
+    const uint32_t q = n / NW;
+    const uint32_t beg = warp * q, len = warp == NW - 1 ? n - (NW - 1) * q : q;
+    uint32_t crc = warp_crc32(cs.crc_tab, p + beg, len);
     if (hgpu_lane() == 0) cs.c.crc[warp] = crc;
     __syncthreads();
     // crc(A||B) = crc(A) * x^(8|B|) ^ crc(B)
-    uint32_t r = cs.c.crc[0];
-    if (n >= 4) {
-        uint32_t xq = xpow_bytes(q), xl = xpow_bytes(n - 3 * q);
-        r = multmodp(xq, r) ^ cs.c.crc[1];
-        r = multmodp(xq, r) ^ cs.c.crc[2];
-        r = multmodp(xl, r) ^ cs.c.crc[3];
-    } else {
-        // fewer than 4 bytes: the last warp took them all, the others saw empty ranges (crc of nothing = 0)
-        r = cs.c.crc[3];
+    uint32_t r;
+    if (q == 0) r = cs.c.crc[NW - 1];                                // everything went to the last warp
+    else {
+        const uint32_t xq = xpow_bytes(q), xl = xpow_bytes(n - (NW - 1) * q);
+        r = cs.c.crc[0];
+#pragma unroll
+        for (uint32_t k = 1; k < NW - 1; k++) r = multmodp(xq, r) ^ cs.c.crc[k];
+        r = multmodp(xl, r) ^ cs.c.crc[NW - 1];
     }
     __syncthreads();
     return r;
 }
 
-__global__ void __launch_bounds__(CTA_T, 3)
+// stage the compressed block `blk` (blen bytes, global) at cs.stage so that shared and global
+// addresses are congruent mod 16: the 16-byte aligned interior by one bulk copy, the ragged ends
+// by plain loads.  Thread 0 issues; every thread later waits on the mbarrier (phase parity).
+__device__ __forceinline__ void stage_issue(CtaSmem &cs, const uint8_t *blk, uint32_t blen)
+{
+    const uint32_t t = threadIdx.x;
+    const uint32_t mis = (uint32_t)(reinterpret_cast<uintptr_t>(blk) & 15);
+    uint8_t *sp = cs.stage + mis;                                    // byte j of the block -> sp[j]
+    uint32_t head = (16u - mis) & 15u;
+    if (head > blen) head = blen;
+    const uint32_t bulk = (blen - head) & ~15u, tail = blen - head - bulk;
+    if (t < head) sp[t] = blk[t];
+    if (t >= 32 && t - 32 < tail) sp[head + bulk + (t - 32)] = blk[head + bulk + (t - 32)];
+    if (t == 0) {
+        if (bulk) tma_load_1d(sp + head, blk + head, bulk, &cs.mbar);
+        else {
+            uint32_t m = (uint32_t)__cvta_generic_to_shared(&cs.mbar);
+            asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" :: "r"(m) : "memory");
+        }
+    }
+}
+
+__global__ void __launch_bounds__(CTA_T, 2)
 bgzf_inflate_cta_kernel(const uint8_t *__restrict__ in, const uint64_t *__restrict__ in_off,
                         const uint32_t *__restrict__ in_len, uint32_t n, uint8_t *out,
                         const uint64_t *__restrict__ out_off, const uint32_t *__restrict__ out_cap,
@@ -1141,9 +1315,9 @@ bgzf_inflate_cta_kernel(const uint8_t *__restrict__ in, const uint64_t *__restri
     CtaSmem &cs = *reinterpret_cast<CtaSmem *>(dyn_smem);
     uint2 *mrec = mrec_all + (size_t)blockIdx.x * MREC_CAP;
     const uint32_t t = threadIdx.x;
+    if (t == 0) { mbar_init(&cs.mbar, 1); cs.c.job = atomicAdd(counter, 1u); cs.c.phase = 0; }
+    __syncthreads();
     for (;;) {
-        if (t == 0) cs.c.job = atomicAdd(counter, 1u);
-        __syncthreads();
         const uint32_t job = cs.c.job;
         if (job >= n) break;
 #ifdef HGPU_PROFILE
@@ -1157,14 +1331,26 @@ bgzf_inflate_cta_kernel(const uint8_t *__restrict__ in, const uint64_t *__restri
         // shared and global addresses congruent mod 16: the payload's byte i sits at win[pad + i]
         const uint32_t pad = (uint32_t)(reinterpret_cast<uintptr_t>(dst) & 15);
         uint8_t *win = cs.win + pad;
+        const bool staged = blen >= 26 && blen <= STAGE_BYTES;
+        const uint32_t parity = cs.c.phase;
+        if (staged) {
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");     // earlier generic reads of the staging area vs. the async write
+            stage_issue(cs, blk, blen);
+            mbar_wait(&cs.mbar, parity);
+        }
+        __syncthreads();
+        if (t == 0) { cs.c.next_job = atomicAdd(counter, 1u); if (staged) cs.c.phase = parity ^ 1u; }
+        const uint8_t *cb = staged ? cs.stage + (uint32_t)(reinterpret_cast<uintptr_t>(blk) & 15) : blk;
+        CTA_MARK(cs, 6);
         int rc = HGPU_OK;
         uint32_t got = 0;
-        if (blen < 26 || check_header(blk) != 0 || (uint32_t)(blk[16] | blk[17] << 8) + 1u != blen)
+        if (blen < 26 || check_header(cb) != 0 || (uint32_t)(cb[16] | cb[17] << 8) + 1u != blen)
             rc = HGPU_BGZF_ERR_HEADER;
         else {
-            rc = inflate_member_cta(cs, blk + 18, blen - 18, win, cap, got, mrec);
+            const uint32_t want = cb[blen - 8] | cb[blen - 7] << 8 | cb[blen - 6] << 16 | (uint32_t)cb[blen - 5] << 24;
+            rc = inflate_member_cta(cs, cb + 18, blen - 18, win, cap, got, mrec);
             if (rc == HGPU_OK) {
-                uint32_t want = blk[blen - 8] | blk[blen - 7] << 8 | blk[blen - 6] << 16 | (uint32_t)blk[blen - 5] << 24;
+                __syncthreads();
                 uint32_t crc = cta_crc32(cs, win, got);
                 if (crc != want) rc = HGPU_BGZF_ERR_CRC;
                 CTA_MARK(cs, 4);
@@ -1192,7 +1378,7 @@ bgzf_inflate_cta_kernel(const uint8_t *__restrict__ in, const uint64_t *__restri
         }
         __syncthreads();
         CTA_MARK(cs, 5);
-        if (t == 0) { status[job] = rc; out_len[job] = rc == HGPU_OK ? got : 0; }
+        if (t == 0) { status[job] = rc; out_len[job] = rc == HGPU_OK ? got : 0; cs.c.job = cs.c.next_job; }
         __syncthreads();
     }
     if (t == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");   // every bulk store has landed before the CTA retires

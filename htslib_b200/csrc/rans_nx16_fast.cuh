@@ -335,22 +335,53 @@ __device__ __forceinline__ void fast32_stream(const FastJob *fj, uint32_t lut_a,
         const uint32_t shamt = 32u - 8u * ph;
         uint32_t *wp = reinterpret_cast<uint32_t *>(op + s - ph);
         uint32_t relA = rg.a;
-        while (s + 4 <= seg && rg.pos0 + rg.v + 256u <= in_len) {
-            const uint32_t g0 = relA;
-#pragma unroll
-            for (int j = 0; j < 4; j++) {
-                F32_SYMBOL(lrow = mad_lo(k_, rowsz, lut_a); frow = mad_lo(k_, fstride, fb_a);)
-                acc = __funnelshift_r(acc, k_, 4);
-                F32_RENORM_FAST
-            }
-            uint32_t B = prmt_raw(mapLo, mapHi, acc >> 16);
-            *wp++ = __funnelshift_rc(prevB, B, shamt);
-            prevB = B;
-            s += 4;
-            rg.v += relA - g0;
-            if (relA >= rg.a + 512u) relA -= 512u;
-            ring32_fill(rg);
+        // one group = 4 steps = one aligned 32-bit word of this lane's segment
+#define F32_GROUP(WREG)                                                                            \
+        {                                                                                          \
+            const uint32_t g0 = relA;                                                              \
+            _Pragma("unroll")                                                                      \
+            for (int j = 0; j < 4; j++) {                                                          \
+                F32_SYMBOL(lrow = mad_lo(k_, rowsz, lut_a); frow = mad_lo(k_, fstride, fb_a);)     \
+                acc = __funnelshift_r(acc, k_, 4);                                                 \
+                F32_RENORM_FAST                                                                    \
+            }                                                                                      \
+            uint32_t B = prmt_raw(mapLo, mapHi, acc >> 16);                                        \
+            WREG = __funnelshift_rc(prevB, B, shamt);                                              \
+            prevB = B;                                                                             \
+            rg.v += relA - g0;                                                                     \
+            if (relA >= rg.a + 512u) relA -= 512u;                                                 \
+            ring32_fill(rg);                                                                       \
         }
+        // 16-byte stores: the lanes' segments start at arbitrary addresses, so every lane has its own
+        // phase q0 (position of its next word inside a 16-byte line).  The loop body is 4 groups;
+        // a line completes after group g for the lanes with (q0 + g) % 4 == 3, and which registers
+        // hold its four words is then fixed per g: four predicated STG.128 instead of sixteen
+        // 32-bit stores, a quarter of the store transactions (32 lines per STG otherwise).
+        if (s + 16 <= seg && rg.pos0 + rg.v + 1024u <= in_len) {
+            const uint32_t q0 = (uint32_t)(reinterpret_cast<uintptr_t>(wp) >> 2) & 3u;
+            const bool p0 = q0 == 3u, p1 = q0 == 2u, p2 = q0 == 1u, p3 = q0 == 0u;
+            uint32_t W0, W1, W2, W3;
+            F32_GROUP(W0) wp[0] = W0;
+            F32_GROUP(W1) wp[1] = W1;
+            F32_GROUP(W2) wp[2] = W2;
+            F32_GROUP(W3) wp[3] = W3;
+            wp += 4; s += 16;
+            while (s + 16 <= seg && rg.pos0 + rg.v + 1024u <= in_len) {
+                F32_GROUP(W0) if (p0) *reinterpret_cast<uint4 *>(wp - 3) = make_uint4(W1, W2, W3, W0);
+                F32_GROUP(W1) if (p1) *reinterpret_cast<uint4 *>(wp - 2) = make_uint4(W2, W3, W0, W1);
+                F32_GROUP(W2) if (p2) *reinterpret_cast<uint4 *>(wp - 1) = make_uint4(W3, W0, W1, W2);
+                F32_GROUP(W3) if (p3) *reinterpret_cast<uint4 *>(wp) = make_uint4(W0, W1, W2, W3);
+                wp += 4; s += 16;
+            }
+            wp[-3] = W1; wp[-2] = W2; wp[-1] = W3;       // words of the last body that did not complete a line
+        }
+        while (s + 4 <= seg && rg.pos0 + rg.v + 256u <= in_len) {
+            uint32_t W;
+            F32_GROUP(W)
+            *wp++ = W;
+            s += 4;
+        }
+#undef F32_GROUP
         // bytes of the last group that have not completed a word (harmless rewrite of the others)
         op[s - 1] = (uint8_t)(prevB >> 24);
         op[s - 2] = (uint8_t)(prevB >> 16);
@@ -384,7 +415,7 @@ __global__ void rans_smem_probe_kernel(uint32_t *o)
     if (threadIdx.x == 0) *o = (uint32_t)__cvta_generic_to_shared(smem);
 }
 
-__global__ void __launch_bounds__(F32_WARPS * 32, 11)
+__global__ void __launch_bounds__(F32_WARPS * 32, 10)
 rans_fast32_kernel(const FastJob *__restrict__ jobs, const uint32_t *__restrict__ njobs,
                    const uint8_t *__restrict__ in, const uint64_t *__restrict__ in_off,
                    const uint32_t *__restrict__ in_len, uint8_t *out, const uint64_t *__restrict__ out_off,
