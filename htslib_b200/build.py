@@ -23,7 +23,7 @@ def needs_build():
     if not os.path.exists(OUT):
         return True
     t = os.path.getmtime(OUT)
-    deps = sources() + [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith(".h")]
+    deps = sources() + [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".h", ".cuh"))]
     deps.append(os.path.join(HERE, "..", "include", "htsgpu.h"))
     return any(os.path.getmtime(d) > t for d in deps)
 

@@ -27,7 +27,9 @@ constexpr int LIT_TABLE = (1 << LIT_ROOT) + 856;    // zlib "enough 286 9 15" = 
 constexpr int DST_TABLE = (1 << DST_ROOT) + 512;    // 30 symbols / 8 root bits: < 4 groups x 128
 constexpr int CL_TABLE = 128;
 
-enum : uint32_t { K_LIT = 0, K_LEN = 1, K_EOB = 2, K_SUB = 3, K_BAD = 4, K_DIST = 5 };
+// entry kinds: one bit each for literal / length / distance / end-of-block (so a symbol loop can test them without
+// compares); a sub-table link has the literal and length bits both set; no bit set = invalid code
+enum : uint32_t { K_BAD = 0, K_LIT = 1, K_LEN = 2, K_SUB = 3, K_DIST = 4, K_EOB = 8 };
 #define ENTRY(value, xb, kind, nbits) (((uint32_t)(value) << 16) | ((uint32_t)(xb) << 8) | ((uint32_t)(kind) << 4) | (uint32_t)(nbits))
 constexpr uint32_t BAD_ENTRY = ENTRY(0, 0, K_BAD, 0);
 
@@ -49,8 +51,8 @@ struct InflateSmem {
             uint2 ptab[32 * 9];      // piece table of the current match batch (a match has <= 9 pieces)
             uint2 rbuf[32];          // match records parked by the serial decoder
         };
-        struct {                     // CTA-per-block decode: what the 128 sub-range decoders exchange
-            uint32_t x_exit[128];
+        struct {                     // CTA-per-block decode: what the 256 sub-range decoders exchange
+            uint32_t x_exit[256];
             uint32_t x_sum[2][8];
         };
     };
@@ -851,538 +853,7 @@ bgzf_inflate_kernel(const uint8_t *__restrict__ in, const uint64_t *__restrict__
 }
 
 
-// =============================================================================================
-// CTA-per-block inflate: the member's whole output (<= 64 KiB) lives in SHARED memory.
-//
-// Why: with the output in global memory every LZ77 dependency level costs an L2 round trip
-// (~600 cycles) and a block takes ~2 M cycles from first bit to CRC; the 16 warps/SM the old
-// kernel keeps resident cannot hide that.  With the window in shared memory a level costs a
-// shared-memory round trip, a block is done in ~100 k cycles, and three blocks per SM in flight
-// are worth more than sixteen.
-//
-//   128 threads, one BGZF block at a time, 3 CTAs/SM (75 KiB each: 64 KiB window + 16 bytes of
-//   alignment slack + the decode tables).
-//   P1  warp 0: header, code lengths, decode tables (warp-parallel build), as before
-//   P2  all 128 threads: the body's bit range cut into 128 sub-ranges, speculative decode with
-//       chained restarts until every sub-range starts where its predecessor stopped; block-wide
-//       prefix sums; literals go straight into the window, matches to a 4-byte-aligned record
-//       list in a per-CTA global slot (L2 resident: the same 170 KiB are rewritten for every block)
-//   P3  warp 0: out-of-order batched LZ77 (exec_batch) on the shared window
-//   P4  all threads: CRC-32 of the window (4 chunks, slice-by-4, combined with x^n mod P), then
-//       ONE bulk asynchronous copy (TMA, cp.async.bulk shared -> global) of the 16-byte aligned
-//       body of the payload; the window is laid out so shared and global addresses are
-//       congruent mod 16, the few head/tail bytes are stored directly.
-// =============================================================================================
-constexpr int CTA_T = 256;
-constexpr uint32_t WIN_BYTES = 65536 + 32;          // 16 bytes of alignment slack in front, word reads may run 4 bytes past the end
-constexpr uint32_t STAGE_BYTES = 24 * 1024;         // compressed blocks up to this size are staged in shared memory (TMA)
-constexpr uint32_t SEG_M = 4096;                    // matches resolved per LZ77 segment
-
-struct CtaCtl {              // broadcast from warp 0 / thread 0 to the CTA
-    int32_t rc;
-    uint32_t mode, final_, body, o, end_pos, job, next_job, E, bad, tot_m, phase;
-    uint32_t crc[8];
-    long long t0;            // HGPU_PROFILE: start of the current phase
-};
-enum : uint32_t { MODE_NEXT = 0, MODE_PAR = 1 };
-
-struct LzSmem {              // P3: match resolution state of one segment (overlays the decode tables)
-    uint32_t deps[SEG_M];    // first | end << 16 of the earlier matches (segment-relative) this match reads from
-    uint32_t done[SEG_M / 32];
-};
-
-struct CtaSmem {
-    uint8_t win[WIN_BYTES];
-    uint8_t stage[STAGE_BYTES + 32];
-    union {
-        InflateSmem s;               // P1, P2: decode tables + their scratch
-        LzSmem z;                    // P3
-        uint32_t crc_tab[4][256];    // P4
-    };
-    uint16_t D[SEG_M];               // destinations of the segment's matches (written by P2 while the tables are live)
-    CtaCtl c;
-    unsigned long long mbar;         // mbarrier of the staging copy
-};
-
-static_assert(sizeof(CtaSmem) <= 115712, "two CTAs per SM: 2 x (size + 1 KiB) must fit 228 KiB");
-static_assert(sizeof(LzSmem) >= sizeof(InflateSmem), "the LZ state is the largest member of the union");
-
-#ifdef HGPU_PROFILE
-#define CTA_MARK(cs, i) do { if (threadIdx.x == 0) { long long n_ = clock64(); atomicAdd(&g_prof[i], (unsigned long long)(n_ - (cs).c.t0)); (cs).c.t0 = n_; } } while (0)
-#else
-#define CTA_MARK(cs, i) do { } while (0)
-#endif
-
-// ---- TMA (1-D bulk copy) helpers -------------------------------------------------------------
-__device__ __forceinline__ void mbar_init(unsigned long long *mb, uint32_t count)
-{
-    uint32_t a = (uint32_t)__cvta_generic_to_shared(mb);
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(a), "r"(count) : "memory");
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-}
-__device__ __forceinline__ void tma_load_1d(void *smem_dst, const void *gsrc, uint32_t bytes, unsigned long long *mb)
-{
-    uint32_t d = (uint32_t)__cvta_generic_to_shared(smem_dst), m = (uint32_t)__cvta_generic_to_shared(mb);
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(m), "r"(bytes) : "memory");
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                 :: "r"(d), "l"(gsrc), "r"(bytes), "r"(m) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(unsigned long long *mb, uint32_t parity)
-{
-    uint32_t m = (uint32_t)__cvta_generic_to_shared(mb), ok = 0;
-    while (!ok) {
-        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
-                     : "=r"(ok) : "r"(m), "r"(parity) : "memory");
-    }
-}
-
-// P2: all threads.  Returns a CTA-uniform status.  Matches are parked in the window (lane_decode<2>)
-// with their destinations in dlist (cs.D when the block has at most SEG_M matches, else the CTA's
-// global slot).
-__device__ int decode_body_cta(CtaSmem &cs, const uint32_t *wbase, const uint32_t *wend, uint32_t body,
-                               uint32_t total, uint8_t *out, uint32_t cap, uint16_t *dglobal)
-{
-    InflateSmem &s = cs.s;
-    const uint32_t t = threadIdx.x, lane = t & 31, warp = t >> 5;
-    const uint32_t S = (total - body + CTA_T - 1) / CTA_T;
-    uint32_t start = body + t * S;
-    uint32_t end = t == CTA_T - 1 ? total : min(total, body + (t + 1) * S);
-    if (start > total) start = total;
-    if (end < start) end = start;
-    uint32_t exitp = 0, n = 0, m = 0, st = ST_RUN;
-    bool need = true, dummy = false;
-    for (int round = 0; round < CTA_T + 2; round++) {
-        if (need) lane_decode<0>(s, wbase, wend, start, end, exitp, n, m, st, nullptr, 0, nullptr, 0, dummy);
-        s.x_exit[t] = exitp;
-        __syncthreads();
-        uint32_t ns = t == 0 ? start : s.x_exit[t - 1];
-        need = ns != start;
-        start = ns;
-        if (!__syncthreads_or(need)) break;
-    }
-    CTA_MARK(cs, 1);
-    // first end-of-block code, invalid codes at or before it
-    if (t == 0) { cs.c.E = 0xffffffffu; cs.c.bad = 0; }
-    __syncthreads();
-    if (st == ST_EOB) atomicMin(&cs.c.E, t);
-    __syncthreads();
-    const uint32_t E = cs.c.E;
-    if (E == 0xffffffffu) return HGPU_BGZF_ERR_ZLIB;             // input ends without an end-of-block code
-    if (st == ST_BAD && t <= E) cs.c.bad = 1;
-    if (t == E) cs.c.end_pos = exitp;
-    if (t > E) { n = 0; m = 0; }
-    // block-wide exclusive prefix sums of bytes and matches
-    uint32_t on = n, mn = m;
-#pragma unroll
-    for (int d = 1; d < 32; d <<= 1) {
-        uint32_t a = __shfl_up_sync(0xffffffffu, on, d), c = __shfl_up_sync(0xffffffffu, mn, d);
-        if (lane >= (uint32_t)d) { on += a; mn += c; }
-    }
-    __syncthreads();
-    if (lane == 31) { s.x_sum[0][warp] = on; s.x_sum[1][warp] = mn; }
-    __syncthreads();
-    uint32_t tot_out = 0, tot_m = 0, pre_o = 0, pre_m = 0;
-#pragma unroll
-    for (uint32_t w = 0; w < CTA_T / 32; w++) {
-        if (w < warp) { pre_o += s.x_sum[0][w]; pre_m += s.x_sum[1][w]; }
-        tot_out += s.x_sum[0][w]; tot_m += s.x_sum[1][w];
-    }
-    on += pre_o; mn += pre_m;
-    if (cs.c.bad) return HGPU_BGZF_ERR_ZLIB;
-    if (cs.c.end_pos > total) return HGPU_BGZF_ERR_ZLIB;         // the block ran past the input
-    const uint32_t o = cs.c.o;
-    if ((uint64_t)o + tot_out > cap) return HGPU_BGZF_ERR_SPACE;
-    if (tot_m > MREC_CAP) return HGPU_BGZF_ERR_ZLIB;
-    bool bad_dist = false;
-    if (t <= E) {
-        uint32_t e2, n2, m2, st2;
-        lane_decode<2>(s, wbase, wend, start, end, e2, n2, m2, st2, out, o + on - n, nullptr, mn - m, bad_dist,
-                       tot_m <= SEG_M ? cs.D : dglobal);
-    }
-    if (__syncthreads_or(bad_dist)) return HGPU_BGZF_ERR_ZLIB;   // distance too far back
-    if (t == 0) { cs.c.o = o + tot_out; cs.c.tot_m = tot_m; }
-    __threadfence_block();
-    __syncthreads();
-    CTA_MARK(cs, 2);
-    return HGPU_OK;
-}
-
-// One match, one thread: w[dst .. dst+len) = w[dst-dist ...], LZ77 semantics (the source may
-// overlap the destination).  Aligned 32-bit stores with a funnel-shifted source when that is
-// safe (a word is only read after every byte of it has been written: dist >= 8, or no overlap).
-__device__ __forceinline__ void lz_copy(uint8_t *w, uint32_t dst, uint32_t dist, uint32_t len)
-{
-    uint8_t *d = w + dst;
-    const uint8_t *s = d - dist;
-    uint32_t n = len;
-    if (dist >= 8 || dist >= len) {
-        while (n && (reinterpret_cast<uintptr_t>(d) & 3)) { *d++ = *s++; n--; }
-        if (n >= 4) {
-            const uint32_t sh = (uint32_t)(reinterpret_cast<uintptr_t>(s) & 3) * 8;
-            const volatile uint32_t *ws = reinterpret_cast<const volatile uint32_t *>(reinterpret_cast<uintptr_t>(s) & ~(uintptr_t)3);
-            volatile uint32_t *wd = reinterpret_cast<volatile uint32_t *>(d);
-            uint32_t lo = *ws++;
-            const uint32_t nw = n >> 2;
-            for (uint32_t k = 0; k < nw; k++) {
-                uint32_t hi = sh ? *ws : 0u;
-                ws++;
-                *wd++ = __funnelshift_r(lo, hi, sh);
-                lo = sh ? hi : *(ws - 1);
-            }
-            d += nw * 4; s += nw * 4; n &= 3;
-        }
-        while (n) { *d++ = *s++; n--; }
-    } else {
-        volatile uint8_t *dv = d;
-        const volatile uint8_t *sv = s;
-        for (uint32_t k = 0; k < n; k++) dv[k] = sv[k];          // in order: later bytes read earlier ones
-    }
-}
-
-// P3: LZ77 resolution of the matches parked by P2, the whole CTA.
-//
-// The matches of a deflate block form a dependency DAG about 130 levels deep with ~18 matches per
-// level on sorted BAM (a record copies from the record before it).  Thread t owns matches
-// t, t+256, ... and takes them in order; a match runs when every earlier match that writes into its
-// source range is done (a contiguous index range, two binary searches over the sorted
-// destinations, precomputed for the whole segment in parallel); one barrier per round.
-__device__ void lz_resolve_cta(CtaSmem &cs, uint8_t *w, uint32_t tot_m, const uint16_t *dglobal)
-{
-    const uint32_t t = threadIdx.x;
-    for (uint32_t seg0 = 0; seg0 < tot_m; seg0 += SEG_M) {
-        const uint32_t n = min(SEG_M, tot_m - seg0);
-        if (tot_m > SEG_M) {                                     // destinations live in the global slot
-            __syncthreads();
-            for (uint32_t i = t; i < n; i += CTA_T) cs.D[i] = dglobal[seg0 + i];
-        }
-        for (uint32_t i = t; i < SEG_M / 32; i += CTA_T) cs.z.done[i] = 0;
-        __syncthreads();
-        // dependency ranges
-        for (uint32_t i = t; i < n; i += CTA_T) {
-            const uint32_t dst = cs.D[i];
-            const uint32_t len = (uint32_t)w[dst] + 3u, dist = ((uint32_t)w[dst + 1] | (uint32_t)w[dst + 2] << 8) + 1u;
-            const uint32_t s0 = dst - dist, s1 = dist < len ? dst : s0 + len;
-            // ub = #{D <= s0}, lb = #{D < s1}, over D[0..i)
-            uint32_t lo0 = 0, hi0 = i, lo1 = 0, hi1 = i;
-            while (lo0 < hi0 || lo1 < hi1) {
-                if (lo0 < hi0) { uint32_t mid = (lo0 + hi0) >> 1; if (cs.D[mid] <= s0) lo0 = mid + 1; else hi0 = mid; }
-                if (lo1 < hi1) { uint32_t mid = (lo1 + hi1) >> 1; if (cs.D[mid] < s1) lo1 = mid + 1; else hi1 = mid; }
-            }
-            const uint32_t first = lo0 ? lo0 - 1 : 0u, end = lo1;
-            cs.z.deps[i] = first < end ? (first | end << 16) : 0u;
-        }
-        __syncthreads();
-        // rounds
-        volatile uint32_t *done = cs.z.done;
-        uint32_t i = t;
-        uint32_t dep = i < n ? cs.z.deps[i] : 0u;
-        for (;;) {
-            if (i < n) {
-                const uint32_t first = dep & 0xffffu, end = dep >> 16;
-                bool ready = true;
-                if (first < end) {
-                    const uint32_t w0 = first >> 5, w1 = (end - 1) >> 5;
-                    for (uint32_t k = w0; k <= w1 && ready; k++) {
-                        uint32_t mask = 0xffffffffu;
-                        if (k == w0) mask &= 0xffffffffu << (first & 31);
-                        if (k == w1) mask &= 0xffffffffu >> (31 - ((end - 1) & 31));
-                        ready = (done[k] & mask) == mask;
-                    }
-                }
-                if (ready) {
-                    __threadfence_block();                           // acquire: the bytes behind the done bits
-                    const uint32_t dst = cs.D[i];
-                    const uint32_t len = (uint32_t)w[dst] + 3u, dist = ((uint32_t)w[dst + 1] | (uint32_t)w[dst + 2] << 8) + 1u;
-                    lz_copy(w, dst, dist, len);
-                    __threadfence_block();                           // release
-                    atomicOr(&cs.z.done[i >> 5], 1u << (i & 31));
-                    i += CTA_T;
-                    dep = i < n ? cs.z.deps[i] : 0u;
-                }
-            }
-            if (!__syncthreads_or(i < n)) break;
-        }
-    }
-    __syncthreads();
-}
-
-// One member: warp 0 walks the deflate block headers, the CTA decodes Huffman bodies.
-// src may point into shared memory (staged block) or global memory.
-__device__ int inflate_member_cta(CtaSmem &cs, const uint8_t *src, uint32_t slen, uint8_t *out, uint32_t cap,
-                                  uint32_t &olen, uint2 *mrec)
-{
-    InflateSmem &s = cs.s;
-    const uint32_t lane = hgpu_lane(), warp = threadIdx.x >> 5;
-    Bits b;
-    const uintptr_t a0 = reinterpret_cast<uintptr_t>(src);
-    const uint32_t mis_bits = (uint32_t)(a0 & 3) * 8;
-    const uint32_t *wbase = reinterpret_cast<const uint32_t *>(a0 - (a0 & 3));
-    const uint32_t *wend = reinterpret_cast<const uint32_t *>((a0 + slen + 3) & ~(uintptr_t)3);
-    const uint32_t total = mis_bits + slen * 8;
-    if (warp == 0) bits_init(b, src, 0, slen);
-    if (threadIdx.x == 0) cs.c.o = 0;
-    __syncthreads();
-    for (;;) {
-        if (warp == 0) {
-            // ---- P1: one deflate block header (same code path as inflate_member) ----
-            int rc = HGPU_OK;
-            uint32_t mode = MODE_NEXT, final_ = 0, body = 0;
-            uint32_t o = cs.c.o;
-            do {
-                bits_fill(b);
-                final_ = bits_get(b, 1);
-                uint32_t type = bits_get(b, 2);
-                if (type == 0) {
-                    bits_drop(b, b.cnt & 7);
-                    bits_fill(b);
-                    uint32_t len = bits_get(b, 16);
-                    bits_fill(b);
-                    uint32_t nlen = bits_get(b, 16);
-                    if (bits_overrun(b) || (len ^ 0xffffu) != nlen) { rc = HGPU_BGZF_ERR_ZLIB; break; }
-                    uint32_t pos = bits_pos(b) >> 3;
-                    if ((uint64_t)pos + len > slen) { rc = HGPU_BGZF_ERR_ZLIB; break; }
-                    if (o + len > cap) { rc = HGPU_BGZF_ERR_SPACE; break; }
-                    for (uint32_t i = lane; i < len; i += 32) out[o + i] = src[pos + i];
-                    o += len;
-                    bits_init(b, src, pos + len, slen);
-                    __syncwarp();
-                } else if (type == 1 || type == 2) {
-                    int r2;
-                    if (type == 1) {
-                        __syncwarp();
-                        for (int i = lane; i < 288; i += 32) s.lens[i] = i < 144 ? 8 : i < 256 ? 9 : i < 280 ? 7 : 8;
-                        __syncwarp();
-                        r2 = build_table<LIT_ROOT, LIT_TABLE>(s, s.lit, 288, false, lit_entry);
-                        if (r2) { rc = HGPU_BGZF_ERR_ZLIB; break; }
-                        __syncwarp();
-                        for (int i = lane; i < 32; i += 32) s.lens[i] = 5;
-                        __syncwarp();
-                        r2 = build_table<DST_ROOT, DST_TABLE>(s, s.dst, 32, false, dst_entry);
-                        if (r2) { rc = HGPU_BGZF_ERR_ZLIB; break; }
-                    } else {
-                        bits_fill(b);
-                        uint32_t hlit = bits_get(b, 5) + 257, hdist = bits_get(b, 5) + 1, hclen = bits_get(b, 4) + 4;
-                        if (hlit > 286 || hdist > 30) { rc = HGPU_BGZF_ERR_ZLIB; break; }
-                        __syncwarp();
-                        if (lane < 19) s.lens[lane] = 0;
-                        __syncwarp();
-                        for (uint32_t i = 0; i < hclen; i++) {
-                            bits_fill(b);
-                            uint32_t v = bits_get(b, 3);
-                            if (lane == 0) s.lens[c_cl_order[i]] = (uint8_t)v;
-                        }
-                        if (bits_overrun(b)) { rc = HGPU_BGZF_ERR_ZLIB; break; }
-                        __syncwarp();
-                        r2 = build_table<7, CL_TABLE>(s, s.cl, 19, false, cl_entry);
-                        if (r2) { rc = HGPU_BGZF_ERR_ZLIB; break; }
-                        uint32_t nsym = hlit + hdist, i = 0, prev = 0;
-                        bool badc = false;
-                        while (i < nsym) {
-                            bits_fill(b);
-                            uint32_t e = s.cl[bits_peek(b, 7)];
-                            if (((e >> 4) & 15) != K_LIT) { badc = true; break; }
-                            bits_drop(b, e & 15);
-                            uint32_t sym = e >> 16;
-                            if (sym < 16) {
-                                if (lane == 0) s.code[i] = (uint16_t)sym;
-                                prev = sym; i++;
-                            } else {
-                                uint32_t rep, val = 0;
-                                if (sym == 16) { if (i == 0) { badc = true; break; } val = prev; rep = 3 + bits_get(b, 2); }
-                                else if (sym == 17) rep = 3 + bits_get(b, 3);
-                                else rep = 11 + bits_get(b, 7);
-                                if (i + rep > nsym) { badc = true; break; }
-                                for (uint32_t k = lane; k < rep; k += 32) s.code[i + k] = (uint16_t)val;
-                                i += rep;
-                                prev = val;
-                            }
-                            if (bits_overrun(b)) { badc = true; break; }
-                        }
-                        if (badc) { rc = HGPU_BGZF_ERR_ZLIB; break; }
-                        __syncwarp();
-                        if (s.code[256] == 0) { rc = HGPU_BGZF_ERR_ZLIB; break; }
-                        uint32_t dl = lane < hdist ? s.code[hlit + lane] : 0;
-                        uint32_t ll[9];
-#pragma unroll
-                        for (int k = 0; k < 9; k++) { uint32_t j = lane + 32 * k; ll[k] = j < hlit ? s.code[j] : 0; }
-                        __syncwarp();
-#pragma unroll
-                        for (int k = 0; k < 9; k++) { uint32_t j = lane + 32 * k; if (j < 288) s.lens[j] = (uint8_t)ll[k]; }
-                        __syncwarp();
-                        r2 = build_table<LIT_ROOT, LIT_TABLE>(s, s.lit, (int)hlit, true, lit_entry);
-                        if (r2) { rc = HGPU_BGZF_ERR_ZLIB; break; }
-                        __syncwarp();
-                        s.lens[lane] = (uint8_t)dl;
-                        __syncwarp();
-                        r2 = build_table<DST_ROOT, DST_TABLE>(s, s.dst, (int)hdist, true, dst_entry);
-                        if (r2) { rc = HGPU_BGZF_ERR_ZLIB; break; }
-                    }
-                    __syncwarp();
-                    if (bits_overrun(b)) { rc = HGPU_BGZF_ERR_ZLIB; break; }
-                    body = mis_bits + bits_pos(b);
-                    if (total - body >= PAR_MIN_BITS) mode = MODE_PAR;
-                    else {
-                        rc = decode_body_uniform(s, b, out, cap, o);
-                        if (rc) break;
-                    }
-                } else { rc = HGPU_BGZF_ERR_ZLIB; break; }
-            } while (0);
-            __syncwarp();
-            if (lane == 0) { cs.c.rc = rc; cs.c.mode = mode; cs.c.final_ = final_; cs.c.body = body; cs.c.o = o; }
-        }
-        __threadfence_block();
-        __syncthreads();
-        CTA_MARK(cs, 0);
-        if (cs.c.rc) return cs.c.rc;
-        const uint32_t final_ = cs.c.final_;
-        if (cs.c.mode == MODE_PAR) {
-            uint16_t *dglobal = reinterpret_cast<uint16_t *>(mrec);
-            int rc = decode_body_cta(cs, wbase, wend, cs.c.body, total, out, cap, dglobal);
-            if (rc) return rc;
-            const uint32_t tot_m = cs.c.tot_m, end_pos = cs.c.end_pos;
-            __syncthreads();                                         // the tables are dead from here: P3 state overlays them
-            lz_resolve_cta(cs, out, tot_m, dglobal);
-            if (warp == 0 && !final_) {
-                // continue the uniform reader right after the end-of-block code
-                uint32_t byte = (end_pos - mis_bits) >> 3, bit = (end_pos - mis_bits) & 7;
-                bits_init(b, src, byte, slen);
-                bits_fill(b);
-                bits_drop(b, bit);
-            }
-            CTA_MARK(cs, 3);
-        }
-        if (final_) break;
-    }
-    olen = cs.c.o;
-    return HGPU_OK;
-}
-
-// CRC-32 of p[0..n) by the CTA (8 warps, one eighth each; slice-by-4 tables in shared memory), CTA-uniform.
-__device__ uint32_t cta_crc32(CtaSmem &cs, const uint8_t *p, uint32_t n)
-{
-    const uint32_t warp = threadIdx.x >> 5;
-    constexpr uint32_t NW = CTA_T / 32;
-    for (uint32_t i = threadIdx.x; i < 1024; i += CTA_T) (&cs.crc_tab[0][0])[i] = (&g_crc_tab[0][0])[i];
-    __syncthreads();
-    const uint32_t q = n / NW;
-    const uint32_t beg = warp * q, len = warp == NW - 1 ? n - (NW - 1) * q : q;
-    uint32_t crc = warp_crc32(cs.crc_tab, p + beg, len);
-    if (hgpu_lane() == 0) cs.c.crc[warp] = crc;
-    __syncthreads();
-    // crc(A||B) = crc(A) * x^(8|B|) ^ crc(B)
-    uint32_t r;
-    if (q == 0) r = cs.c.crc[NW - 1];                                // everything went to the last warp
-    else {
-        const uint32_t xq = xpow_bytes(q), xl = xpow_bytes(n - (NW - 1) * q);
-        r = cs.c.crc[0];
-#pragma unroll
-        for (uint32_t k = 1; k < NW - 1; k++) r = multmodp(xq, r) ^ cs.c.crc[k];
-        r = multmodp(xl, r) ^ cs.c.crc[NW - 1];
-    }
-    __syncthreads();
-    return r;
-}
-
-// stage the compressed block `blk` (blen bytes, global) at cs.stage so that shared and global
-// addresses are congruent mod 16: the 16-byte aligned interior by one bulk copy, the ragged ends
-// by plain loads.  Thread 0 issues; every thread later waits on the mbarrier (phase parity).
-__device__ __forceinline__ void stage_issue(CtaSmem &cs, const uint8_t *blk, uint32_t blen)
-{
-    const uint32_t t = threadIdx.x;
-    const uint32_t mis = (uint32_t)(reinterpret_cast<uintptr_t>(blk) & 15);
-    uint8_t *sp = cs.stage + mis;                                    // byte j of the block -> sp[j]
-    uint32_t head = (16u - mis) & 15u;
-    if (head > blen) head = blen;
-    const uint32_t bulk = (blen - head) & ~15u, tail = blen - head - bulk;
-    if (t < head) sp[t] = blk[t];
-    if (t >= 32 && t - 32 < tail) sp[head + bulk + (t - 32)] = blk[head + bulk + (t - 32)];
-    if (t == 0) {
-        if (bulk) tma_load_1d(sp + head, blk + head, bulk, &cs.mbar);
-        else {
-            uint32_t m = (uint32_t)__cvta_generic_to_shared(&cs.mbar);
-            asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" :: "r"(m) : "memory");
-        }
-    }
-}
-
-__global__ void __launch_bounds__(CTA_T, 2)
-bgzf_inflate_cta_kernel(const uint8_t *__restrict__ in, const uint64_t *__restrict__ in_off,
-                        const uint32_t *__restrict__ in_len, uint32_t n, uint8_t *out,
-                        const uint64_t *__restrict__ out_off, const uint32_t *__restrict__ out_cap,
-                        uint32_t *out_len, int32_t *status, uint32_t *counter, uint2 *mrec_all)
-{
-    extern __shared__ __align__(16) uint8_t dyn_smem[];
-    CtaSmem &cs = *reinterpret_cast<CtaSmem *>(dyn_smem);
-    uint2 *mrec = mrec_all + (size_t)blockIdx.x * MREC_CAP;
-    const uint32_t t = threadIdx.x;
-    if (t == 0) { mbar_init(&cs.mbar, 1); cs.c.job = atomicAdd(counter, 1u); cs.c.phase = 0; }
-    __syncthreads();
-    for (;;) {
-        const uint32_t job = cs.c.job;
-        if (job >= n) break;
-#ifdef HGPU_PROFILE
-        if (t == 0) cs.c.t0 = clock64();
-#endif
-        const uint8_t *blk = in + in_off[job];
-        const uint32_t blen = in_len[job];
-        uint8_t *dst = out + out_off[job];
-        uint32_t cap = out_cap[job];
-        if (cap > 65536u) cap = 65536u;                    // BGZF_MAX_BLOCK_SIZE, bgzf.c:810
-        // shared and global addresses congruent mod 16: the payload's byte i sits at win[pad + i]
-        const uint32_t pad = (uint32_t)(reinterpret_cast<uintptr_t>(dst) & 15);
-        uint8_t *win = cs.win + pad;
-        const bool staged = blen >= 26 && blen <= STAGE_BYTES;
-        const uint32_t parity = cs.c.phase;
-        if (staged) {
-            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");     // earlier generic reads of the staging area vs. the async write
-            stage_issue(cs, blk, blen);
-            mbar_wait(&cs.mbar, parity);
-        }
-        __syncthreads();
-        if (t == 0) { cs.c.next_job = atomicAdd(counter, 1u); if (staged) cs.c.phase = parity ^ 1u; }
-        const uint8_t *cb = staged ? cs.stage + (uint32_t)(reinterpret_cast<uintptr_t>(blk) & 15) : blk;
-        CTA_MARK(cs, 6);
-        int rc = HGPU_OK;
-        uint32_t got = 0;
-        if (blen < 26 || check_header(cb) != 0 || (uint32_t)(cb[16] | cb[17] << 8) + 1u != blen)
-            rc = HGPU_BGZF_ERR_HEADER;
-        else {
-            const uint32_t want = cb[blen - 8] | cb[blen - 7] << 8 | cb[blen - 6] << 16 | (uint32_t)cb[blen - 5] << 24;
-            rc = inflate_member_cta(cs, cb + 18, blen - 18, win, cap, got, mrec);
-            if (rc == HGPU_OK) {
-                __syncthreads();
-                uint32_t crc = cta_crc32(cs, win, got);
-                if (crc != want) rc = HGPU_BGZF_ERR_CRC;
-                CTA_MARK(cs, 4);
-            }
-        }
-        if (rc == HGPU_OK && got) {
-            // ---- write-out: head bytes up to the first 16-byte boundary, bulk copy, tail bytes ----
-            uint32_t head = (16u - pad) & 15u;
-            if (head > got) head = got;
-            const uint32_t bulk = (got - head) & ~15u, tail = got - head - bulk;
-            if (t < head) dst[t] = win[t];
-            if (t >= 32 && t - 32 < tail) dst[head + bulk + (t - 32)] = win[head + bulk + (t - 32)];
-            if (bulk) {
-                // generic-proxy writes to the window must be visible to the async proxy
-                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-                __syncthreads();
-                if (t == 0) {
-                    uint32_t sa = (uint32_t)__cvta_generic_to_shared(win + head);
-                    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;"
-                                 :: "l"(dst + head), "r"(sa), "r"(bulk) : "memory");
-                    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-                    asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");   // the window is reused by the next block
-                }
-            }
-        }
-        __syncthreads();
-        CTA_MARK(cs, 5);
-        if (t == 0) { status[job] = rc; out_len[job] = rc == HGPU_OK ? got : 0; cs.c.job = cs.c.next_job; }
-        __syncthreads();
-    }
-    if (t == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");   // every bulk store has landed before the CTA retires
-}
+#include "bgzf_inflate_cta.cuh"
 
 __global__ void crc32_chunks_kernel(const uint8_t *buf, size_t len, size_t chunk, uint32_t *partial)
 {
@@ -1410,6 +881,7 @@ int ensure_crc_tables(hgpu_ctx *ctx, cudaStream_t st)
 {
     if (g_crc_ready[ctx->device & 63]) return HGPU_OK;
     crc_init_kernel<<<1, 256, 0, st>>>();
+    crc_init2_kernel<<<1, 256, 0, st>>>();
     hgpu_count_launch();
     if (hgpu_check(cudaGetLastError(), "crc init")) return HGPU_ERR_CUDA;
     if (hgpu_check(cudaStreamSynchronize(st), "crc init sync")) return HGPU_ERR_CUDA;   // once per device
@@ -1677,6 +1149,17 @@ int hgpu_launch_bgzf_inflate(hgpu_ctx *ctx, const uint8_t *d_in, const uint64_t 
                                                             d_out_len, d_status, counter, mrec);
     hgpu_count_launch();
     return hgpu_check(cudaGetLastError(), "inflate launch");
+}
+
+extern "C" int hgpu_debug_p2(int job, unsigned int *out)
+{
+#ifdef HGPU_PROFILE
+    if (out) return cudaMemcpyFromSymbol(out, g_dbg, sizeof(uint32_t) * 6 * 256) == cudaSuccess ? 0 : -1;
+    return cudaMemcpyToSymbol(g_dbg_job, &job, sizeof(int)) == cudaSuccess ? 0 : -1;
+#else
+    (void)job; (void)out;
+    return -1;
+#endif
 }
 
 extern "C" int hgpu_debug_profile(unsigned long long *out8)
