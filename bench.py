@@ -199,123 +199,110 @@ def make_corpus(args, rank, world=1):
     return corpus
 
 
-def rans_leg(args, ctx, torch, dev):
-    import htslib_b200 as H
-    """CRAM 3.1 'normal'-profile shaped rANS blocks per slice of 10 000 x 150 bp reads: QS 1.5 MB
-    32-way order-1, BF 15 kB 4-way order-1, CF/AP/NF/FN/BS 10 kB 4-way order-0 (SURVEY.md §8a').
-    Streams are produced by the product's own GPU encoder."""
-    from tools import synth
+def rans_legs(args, ctx, torch, dev, world, dist):
+    """BASELINE.json configs[2]: CRAM 3.1 rANS-Nx16 decode of 30x-WGS-shaped slices, streams written by the
+    UNMODIFIED reference encoder (tools/rans_bench.py), NovaSeq 4-bin and HiSeq ~40-value qualities, every
+    block compared on the device with the generator's input; device time, host-buffer (e2e) time and the
+    reference decoder on the host cores beside it.  Runs at every N (slices shard without a collective)."""
+    from tools import rans_bench
     if args.rans_slices == 0:
         return None
-    rng = np.random.default_rng(4242)
-    uniq = 16                                   # unique slices, tiled to rans_slices (distinct addresses)
-    raws, orders = [], []
-    for s_ in range(uniq):
-        raws.append((synth.novaseq_quals(rng, 1_500_000) + 33).astype(np.uint8).tobytes()); orders.append(5)
-        raws.append(rng.choice(np.array([99, 147, 83, 163], dtype=np.uint16), size=7500).astype("<u2").tobytes()); orders.append(1)
-        for k in range(5):
-            raws.append(np.clip(rng.normal(60, 25, size=10000), 0, 255).astype(np.uint8).tobytes()); orders.append(0)
-    # input manufacture with the product's own GPU encoder (hgpu_rans_nx16_encode_batch_dev); its
-    # streams are checked against the reference decoder in tests/test_gpu_rans_enc.py
-    comps = ctx.rans_nx16_encode(raws, orders, torch.cuda.current_stream().cuda_stream)
-    assert all(c is not None for c in comps)
-    ulens = [len(r) for r in raws]
-    if os.environ.get("RANS_ONLY_QS"):
-        keep = [i for i in range(len(comps)) if ulens[i] > 100000]
-        comps = [comps[i] for i in keep]; raws = [raws[i] for i in keep]; ulens = [ulens[i] for i in keep]
-    wave = H.lib().hgpu_rans_nx16_wave_size(ctx.h)
-    if args.rans_slices < 0:                      # -k: k full waves of quality blocks
-        args.rans_slices = -args.rans_slices * wave
-    per = len(comps) // uniq                    # streams per slice
-    nsl = args.rans_slices                      # exactly this many slices (unique ones tiled round-robin)
-    sel = np.concatenate([np.arange(per) + per * (s_ % uniq) for s_ in range(nsl)])
-    in_len = np.array([len(comps[i]) for i in sel], dtype=np.uint32)
-    out_len = np.array([ulens[i] for i in sel], dtype=np.uint32)
-    # largest streams first so the persistent grid's tail is short
-    order = np.argsort(-out_len.astype(np.int64), kind="stable")
-    in_len, out_len = in_len[order], out_len[order]
-    src_idx = sel[order]
-    in_off = np.concatenate([[0], np.cumsum((in_len.astype(np.int64) + 15) // 16 * 16)[:-1]]).astype(np.uint64)
-    out_off = np.concatenate([[0], np.cumsum((out_len.astype(np.int64) + 15) // 16 * 16)[:-1]]).astype(np.uint64)
-    blob = np.zeros(int(in_off[-1]) + int(in_len[-1]) + 64, dtype=np.uint8)
-    for o, si in zip(in_off, src_idx):
-        c = comps[si]
-        blob[int(o):int(o) + len(c)] = np.frombuffer(c, dtype=np.uint8)
-    t = lambda a: torch.from_numpy(a.view(np.int64) if a.dtype == np.uint64 else a.view(np.int32)).to(dev)
-    d_in = torch.from_numpy(blob).to(dev)
-    d_out = torch.empty(int(out_off[-1]) + int(out_len[-1]) + 64, dtype=torch.uint8, device=dev)
-    d_io, d_il, d_oo, d_ol = t(in_off), t(in_len), t(out_off), t(out_len)
-    n = len(in_len)
-    d_got = torch.zeros(n, dtype=torch.int32, device=dev)
-    d_st = torch.zeros(n, dtype=torch.int32, device=dev)
-    st = torch.cuda.current_stream().cuda_stream   # run_ours made a real (non-default) stream current
-    assert st != 0
-    mx = int(out_len.max())
-    times = []
-    for it in range(2 + 5):
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        ctx.rans_nx16_decode_dev(d_in, d_io, d_il, d_out, d_oo, d_ol, d_got, d_st, mx, st)
-        e1.record()
-        torch.cuda.synchronize()
-        if it >= 2:
-            times.append(e0.elapsed_time(e1))
-    assert int(d_st.abs().sum().item()) == 0, "rANS decode reported errors"
-    # spot-check one QS block against the generator's input
-    k = int(np.where(src_idx == 0)[0][0])
-    got = d_out[int(out_off[k]):int(out_off[k]) + int(out_len[k])].cpu().numpy().tobytes()
-    assert got == raws[0], "rANS spot check against the generator's input"
-    ms = float(np.mean(times))
-    U, Cb = int(out_len.astype(np.int64).sum()), int(in_len.astype(np.int64).sum())
-    hbm, how = peaks()
-    res = {"workload": "CRAM3.1 rANS-Nx16 decode, %d slices x (QS 1.5MB X32-O1 + BF 15kB O1 + 5x10kB O0), NovaSeq 4-bin quals, %d unique slices tiled"
-                       % (nsl, uniq),
-           "streams": n, "resident_streams_per_wave": int(wave), "uncompressed_GB": U / 1e9, "compressed_GB": Cb / 1e9, "ms": ms,
-           "value": U / ms / 1e6, "unit": "GB/s (uncompressed)",
-           "roofline": {"bound": "hbm", "achieved": (U + Cb) / ms / 1e6, "peak": hbm, "unit": "GB/s",
-                        "frac": (U + Cb) / ms / 1e6 / hbm, "traffic": None, "peak_source": how}}
-    try:                                                          # the reference's own decoder on the same streams, beside it
-        res.update(ref_rans_rate(comps, ulens))
-    except Exception as ex:
-        res["cpu_reference_error"] = repr(ex)
-    return res
+    waves = -args.rans_slices if args.rans_slices < 0 else 1
+    out = {}
+    for alphabet in ("novaseq", "hiseq"):
+        try:
+            out[alphabet] = rans_bench.run(ctx, torch, dev, peaks(), alphabet=alphabet, waves=waves, reps=5, world=world,
+                                           dist=dist, e2e=not args.no_e2e, cpu=(world == 1 and not args.no_cpu_baseline))
+        except Exception as ex:                                   # the headline line must still print
+            out[alphabet] = {"error": repr(ex)}
+    head = dict(out["novaseq"])
+    head["hiseq"] = out["hiseq"]
+    head["note"] = ("top level = NovaSeq 4-bin qualities (SURVEY.md 8d first data set); 'hiseq' = the 40-value data set; "
+                    "value = uncompressed GB/s over all GPUs, roofline = (C+U)/t per GPU against the measured copy bandwidth")
+    return head
 
 
-def ref_rans_rate(comps, ulens, seconds=2.0):
-    """rans_uncompress_to_4x16 of the unmodified reference (oracle/_ref) over the given streams: one core, then
-    one thread per host core (ctypes releases the GIL), each for about `seconds`."""
-    from concurrent.futures import ThreadPoolExecutor
-    r = ref_lib()
-    if r is None:
-        return {}
-    r.rans_uncompress_to_4x16.restype = C.c_void_p
-    r.rans_uncompress_to_4x16.argtypes = [C.c_char_p, C.c_uint, C.c_void_p, C.POINTER(C.c_uint)]
-    # the quality blocks carry ~97 % of the bytes; the 10-15 kB blocks would only measure Python's call overhead
-    big = [i for i in range(len(comps)) if ulens[i] >= 100000] or list(range(len(comps)))
-    comps = [comps[i] for i in big]; ulens = [ulens[i] for i in big]
+def bind_to_gpu_numa(local):
+    """Pin this rank's threads (and therefore its first-touch pinned staging) to the NUMA node its GPU
+    hangs off: at N>1 the host side of the e2e path is otherwise bound by cross-socket traffic."""
+    try:
+        import re
+        bus = subprocess.run(["nvidia-smi", "-i", str(local), "--query-gpu=pci.bus_id", "--format=csv,noheader"],
+                             stdout=subprocess.PIPE, text=True, timeout=20).stdout.strip().lower()
+        if not bus:
+            return None
+        if len(bus.split(":")[0]) == 8:
+            bus = bus[4:]
+        node = int(open("/sys/bus/pci/devices/%s/numa_node" % bus).read().strip())
+        if node < 0:
+            return None
+        cpus = open("/sys/devices/system/node/node%d/cpulist" % node).read().strip()
+        ids = set()
+        for part in cpus.split(","):
+            lo, _, hi = part.partition("-")
+            ids.update(range(int(lo), int(hi or lo) + 1))
+        ids &= os.sched_getaffinity(0)
+        if ids:
+            os.sched_setaffinity(0, ids)
+        return {"numa_node": node, "cpus": len(ids)}
+    except Exception:
+        return None
 
-    def work(k, until):
-        out = (C.c_uint8 * max(1, max(ulens)))()
-        done = 0
-        i = k
-        while time.perf_counter() < until:
-            m = C.c_uint(ulens[i % len(comps)])
-            if not r.rans_uncompress_to_4x16(comps[i % len(comps)], len(comps[i % len(comps)]), out, C.byref(m)):
-                raise RuntimeError("reference decoder failed on stream %d" % (i % len(comps)))
-            done += m.value
-            i += 1
-        return done
-    t0 = time.perf_counter()
-    one = work(0, t0 + seconds) / (time.perf_counter() - t0)
-    cores = len(os.sched_getaffinity(0))
-    allc = 0.0
-    for _ in range(3):                                            # best of three: the first pass also warms the cores up
-        t0 = time.perf_counter()
-        with ThreadPoolExecutor(cores) as ex:
-            tot = sum(ex.map(lambda k: work(k, t0 + seconds), range(cores)))
-        allc = max(allc, tot / (time.perf_counter() - t0))
-    return {"cpu_reference_1core_GBps": one / 1e9, "cpu_reference_allcores_GBps": allc / 1e9, "cpu_reference_cores": cores,
-            "cpu_reference_sample": "%d quality blocks, %.0f s per arm (all-core arm: best of 3), rans_uncompress_to_4x16 of oracle/_ref" % (len(comps), seconds)}
+
+def strong_leg(args, ctx, torch, dev, dist, world, rank, corpus, d_in, d_io, d_il, d_out, d_oo, d_cap, d_len, d_st, stream, steps):
+    """STRONG split: ONE file of args.gb uncompressed GB whose blocks shard across the ranks in
+    contiguous ranges (hgpu_shard_range).  The file is the concatenation, in rank order, of the first 1/N of
+    every rank's resident corpus (each rank generated its own blocks).  Per step: rank 0 broadcasts the BAM
+    header block over NCCL, the ranks all-gather their ranges' uncompressed lengths (-> global output bases),
+    each rank inflates its own range; time = max over ranks; no collective on the data path."""
+    import htslib_b200 as H
+    clen, ulen = corpus["clen"], corpus["ulen"]
+    k = len(clen) // world                                  # blocks of this rank's part
+    kk = torch.tensor([k], device=dev, dtype=torch.int64)
+    dist.all_reduce(kk, op=dist.ReduceOp.MIN)
+    k = int(kk.item())
+    # the global unit table every rank needs for hgpu_shard_range: the uncompressed length of every block of the file
+    mine = torch.from_numpy(ulen[:k].astype(np.int32)).to(dev)
+    allu = [torch.empty_like(mine) for _ in range(world)]
+    dist.all_gather(allu, mine)
+    g_ulen = torch.cat(allu).cpu().numpy().astype(np.uint32)
+    first, count, out_base = H.shard_range(g_ulen, world, rank)
+    assert count == k and first == rank * k, (first, count, k)
+    hdr_txt = ("@HD\tVN:1.6\tSO:coordinate\n" + "".join("@SQ\tSN:chr%d\tLN:%d\n" % (c + 1, 248956422 - c * 5000000) for c in range(24))
+               + "@RG\tID:grp1\tSM:synthetic\n").encode()
+    hdr = torch.zeros(len(hdr_txt), dtype=torch.uint8, device=dev)
+    if rank == 0:
+        hdr.copy_(torch.frombuffer(bytearray(hdr_txt), dtype=torch.uint8))
+    my_u = torch.tensor([int(ulen[:k].astype(np.int64).sum())], device=dev, dtype=torch.int64)
+    lens = [torch.zeros_like(my_u) for _ in range(world)]
+    sl = slice(0, k)
+    a_io, a_il, a_oo, a_cap = d_io[sl].contiguous(), d_il[sl].contiguous(), d_oo[sl].contiguous(), d_cap[sl].contiguous()
+    a_len, a_st = d_len[sl].contiguous(), d_st[sl].contiguous()
+
+    def step():
+        dist.broadcast(hdr, src=0)                          # the one collective north_star names: header (and reference) to every rank
+        dist.all_gather(lens, my_u)                         # global output bases = prefix sums of these
+        ctx.bgzf_inflate_dev(d_in, a_io, a_il, d_out, a_oo, a_cap, a_len, a_st, stream)
+    for _ in range(2):
+        step()
+    torch.cuda.synchronize(); dist.barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        step()
+    e1.record()
+    torch.cuda.synchronize()
+    tt = torch.tensor([e0.elapsed_time(e1)], device=dev)
+    dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+    ms = float(tt.item()) / steps
+    dist.barrier()
+    assert int(a_st.abs().sum().item()) == 0
+    assert bytes(hdr.cpu().numpy().tobytes()) == hdr_txt
+    tot = int(sum(int(x.item()) for x in lens))
+    assert int(np.cumsum([0] + [int(x.item()) for x in lens])[rank]) == out_base
+    return {"scaling": "strong", "value": tot / ms / 1e6, "unit": "GB/s", "ms_per_step": ms, "uncompressed_bytes_total": tot,
+            "blocks_per_gpu": k, "collectives_per_step": "NCCL broadcast of the BAM header block (%d B) + all-gather of %d x 8 B range lengths; none on the data path" % (len(hdr_txt), world),
+            "shard": "hgpu_shard_range: rank r takes blocks [r*k, (r+1)*k) and writes at the global output base the all-gather gives"}
 
 
 def run_ours(args):
@@ -327,11 +314,13 @@ def run_ours(args):
     assert torch.cuda.is_available(), "bench.py needs a GPU (there is no CPU fallback)"
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    dist = None
     if world > 1:
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=dev)
     ctx = H.Context(local)
     corpus = make_corpus(args, rank, world)
+    numa = bind_to_gpu_numa(local) if world > 1 else None       # after the generators: they want every core
     comp, clen, ulen = corpus["comp"], corpus["clen"], corpus["ulen"]
     nb = len(clen)
     in_off = np.concatenate([[0], np.cumsum(clen.astype(np.int64))[:-1]]).astype(np.uint64)
@@ -463,6 +452,7 @@ def run_ours(args):
         except Exception as ex:
             bam_extra = {"error": repr(ex)}
 
+    d_out_keep = d_out
     # ---- e2e: host buffers through the C-ABI file entry point ----
     e2e = None
     if not args.no_e2e:
@@ -472,8 +462,6 @@ def run_ours(args):
         h_file[Cb:].copy_(torch.frombuffer(bytearray(synth.BGZF_EOF), dtype=torch.uint8))
         h_out = torch.empty(U, dtype=torch.uint8).pin_memory()
         fn, on = h_file.numpy(), h_out.numpy()
-        del d_out
-        torch.cuda.empty_cache()
         rc, n, bad = ctx.bgzf_inflate_file_host(fn, on)           # warm-up (allocates staging)
         assert rc == 0 and n == U, (rc, n, bad, H.last_error())
         assert zlib.crc32(on[:int(ulen[:k_shard].astype(np.int64).sum())].tobytes()) == corpus["shard_crcs"][0]
@@ -493,6 +481,20 @@ def run_ours(args):
                "d2h_bytes_per_step": U + nb * 8, "api": "hgpu_bgzf_inflate_file_host (pinned host buffers, 3-stream chunk pipeline)"}
         del h_file, h_out
 
+    # ---- legs every rank takes part in ----
+    strong = None
+    if world > 1:
+        try:
+            strong = strong_leg(args, ctx, torch, dev, dist, world, rank, corpus, d_in, d_io, d_il, d_out_keep, d_oo, d_cap, d_len, d_st, stream, max(2, min(args.steps, 5)))
+        except Exception as ex:
+            strong = {"error": repr(ex)}
+    del d_in, d_out_keep, d_out
+    torch.cuda.empty_cache()
+    rans = None
+    try:
+        rans = rans_legs(args, ctx, torch, dev, world, dist)
+    except Exception as ex:
+        rans = {"error": repr(ex)}
     if rank != 0:
         return
     hbm, how = peaks()
@@ -527,13 +529,13 @@ def run_ours(args):
         cb = run_cpu_baseline(corpus, args.cpu_sample_gb)
         if cb:
             out["cpu_baseline"] = cb
+    if rans:
+        out["rans"] = rans
+    if strong:
+        out["strong"] = strong
+    if numa:
+        out["config"]["numa_binding"] = numa
     if world == 1:
-        try:
-            rl = rans_leg(args, ctx, torch, dev)
-            if rl:
-                out.setdefault("extra", {})["rans_nx16_decode"] = rl
-        except Exception as ex:                                   # the headline line must still print
-            out.setdefault("extra", {})["rans_nx16_decode"] = {"error": repr(ex)}
         try:
             tl = tok3_leg(args, ctx)
             if tl:
@@ -629,7 +631,9 @@ def run_reference(args):
         "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "u8", "data": "synthetic",
         "config": {"workload": "BGZF inflate of synthetic 150bp BAM (same generator as the GPU arm), zlib level %d blocks" % args.level,
-                   "sample": sample},
+                   "sample": sample,
+                   "note": "a steady-state rate: each step decodes the first %.1f GB of the same file the GPU arm decodes whole; "
+                           "zlib arm of bgzf.c (libdeflate, which htslib recommends and which is roughly 2x faster, is not in this image)" % args.cpu_sample_gb},
         "cpu_baseline": {"value": v, "unit": "GB/s", "cores": cores, "kind": "reference", "sample": sample},
         "e2e": {"value": v, "unit": "GB/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }))

@@ -48,7 +48,6 @@ struct InflateSmem {
             uint32_t sub_alloc;
         };
         struct {                     // match execution
-            uint2 ptab[32 * 9];      // piece table of the current match batch (a match has <= 9 pieces)
             uint2 rbuf[32];          // match records parked by the serial decoder
         };
         struct {                     // CTA-per-block decode: what the 256 sub-range decoders exchange
@@ -80,6 +79,8 @@ struct Prof {
 #endif
 
 __device__ uint32_t g_crc_tab[4][256];      // slice-by-4 tables, filled once by crc_init_kernel
+__device__ uint32_t g_xpow_lo[256];         // x^(8 i) mod P            (crc_init2_kernel)
+__device__ uint32_t g_xpow_hi[256];         // x^(8 * 256 i) mod P
 
 __global__ void crc_init_kernel()
 {
@@ -315,7 +316,7 @@ __device__ uint32_t warp_crc32(const uint32_t (*tab)[256], const uint8_t *out, u
     if (c == 0) return __shfl_sync(0xffffffffu, crc, 0);
     // combine: crc(A||B) = crc(A) * x^(8|B|) ^ crc(B)   (crc32_combine).  Level d merges blocks
     // of d lanes; the right-hand block is always d*c bytes long.
-    uint32_t xp = xpow_bytes(c);
+    uint32_t xp = c < 65536u ? multmodp(g_xpow_hi[c >> 8], g_xpow_lo[c & 255u]) : xpow_bytes(c);      // x^(8c) mod P
     for (int d = 1; d < 32; d <<= 1) {
         uint32_t right = __shfl_down_sync(0xffffffffu, crc, d);
         if ((lane & (2 * d - 1)) == 0) crc = multmodp(xp, crc) ^ right;
@@ -348,8 +349,58 @@ constexpr int GRP = GRP_N;
 
 __device__ __forceinline__ uint32_t low_mask(uint32_t n) { return n >= 32u ? 0xffffffffu : (1u << n) - 1u; }
 
+// predicated global-memory accesses (straight-line code: `if (c) x = *p` would become a divergent branch)
+__device__ __forceinline__ uint32_t gld8_if(const uint8_t *a, uint32_t c)
+{ uint32_t v; asm volatile("{\n\t.reg .pred q;\n\tsetp.ne.u32 q, %2, 0;\n\tmov.u32 %0, 0;\n\t@q ld.u8 %0, [%1];\n\t}" : "=r"(v) : "l"(a), "r"(c) : "memory"); return v; }
+__device__ __forceinline__ uint32_t gld32_if(const uint8_t *a, uint32_t c)
+{ uint32_t v; asm volatile("{\n\t.reg .pred q;\n\tsetp.ne.u32 q, %2, 0;\n\tmov.u32 %0, 0;\n\t@q ld.u32 %0, [%1];\n\t}" : "=r"(v) : "l"(a), "r"(c) : "memory"); return v; }
+__device__ __forceinline__ void gst8_if(uint8_t *a, uint32_t v, uint32_t c)
+{ asm volatile("{\n\t.reg .pred q;\n\tsetp.ne.u32 q, %2, 0;\n\t@q st.u8 [%0], %1;\n\t}" :: "l"(a), "r"(v), "r"(c) : "memory"); }
+__device__ __forceinline__ void gst32_if(uint8_t *a, uint32_t v, uint32_t c)
+{ asm volatile("{\n\t.reg .pred q;\n\tsetp.ne.u32 q, %2, 0;\n\t@q st.u32 [%0], %1;\n\t}" :: "l"(a), "r"(v), "r"(c) : "memory"); }
+
+// One match, one lane: d[0..n) = s[0..n), no overlap (dist >= len).  Aligned 32-bit stores with a
+// funnel-shifted source, every load of a chunk (<= 32 bytes) issued before its stores: a chunk costs one
+// round trip to L2, and the lanes of a round pay it together.  act = 0: the lane moves nothing.
+__device__ __forceinline__ void lane_copy(uint8_t *d, const uint8_t *s, uint32_t n, uint32_t act)
+{
+    if (!act) n = 0;
+    uint32_t h = (0u - (uint32_t)reinterpret_cast<uintptr_t>(d)) & 3u;
+    if (h > n) h = n;
+    const uint32_t nw = (n - h) >> 2, tl = (n - h) & 3u;
+    const uint8_t *ts = s + h + 4u * nw;
+    uint8_t *td = d + h + 4u * nw;
+    const uint32_t hb0 = gld8_if(s, h > 0), hb1 = gld8_if(s + 1, h > 1), hb2 = gld8_if(s + 2, h > 2);
+    const uint32_t tb0 = gld8_if(ts, tl > 0), tb1 = gld8_if(ts + 1, tl > 1), tb2 = gld8_if(ts + 2, tl > 2);
+    uint8_t *dw = d + h;
+    const uint8_t *sw = s + h;
+    const uint32_t sh = ((uint32_t)reinterpret_cast<uintptr_t>(sw) & 3u) * 8u;
+    const uint8_t *sa = sw - (reinterpret_cast<uintptr_t>(sw) & 3);
+    uint32_t rem = nw;
+    uint32_t W0 = gld32_if(sa, rem > 0);
+    while (rem) {
+        // the word behind the last needed one is read only when the source is misaligned (it then lies inside the match)
+        const uint32_t W1 = gld32_if(sa + 4, rem > 1 || sh), W2 = gld32_if(sa + 8, rem > 2 || (rem > 1 && sh)), W3 = gld32_if(sa + 12, rem > 3 || (rem > 2 && sh)),
+                       W4 = gld32_if(sa + 16, rem > 4 || (rem > 3 && sh)), W5 = gld32_if(sa + 20, rem > 5 || (rem > 4 && sh)), W6 = gld32_if(sa + 24, rem > 6 || (rem > 5 && sh)),
+                       W7 = gld32_if(sa + 28, rem > 7 || (rem > 6 && sh)), W8 = gld32_if(sa + 32, rem > 8 || (rem > 7 && sh));
+        gst32_if(dw, __funnelshift_r(W0, W1, sh), 1);
+        gst32_if(dw + 4, __funnelshift_r(W1, W2, sh), rem > 1);
+        gst32_if(dw + 8, __funnelshift_r(W2, W3, sh), rem > 2);
+        gst32_if(dw + 12, __funnelshift_r(W3, W4, sh), rem > 3);
+        gst32_if(dw + 16, __funnelshift_r(W4, W5, sh), rem > 4);
+        gst32_if(dw + 20, __funnelshift_r(W5, W6, sh), rem > 5);
+        gst32_if(dw + 24, __funnelshift_r(W6, W7, sh), rem > 6);
+        gst32_if(dw + 28, __funnelshift_r(W7, W8, sh), rem > 7);
+        W0 = W8; sa += 32; dw += 32;
+        rem = rem > 8 ? rem - 8 : 0;
+    }
+    gst8_if(d, hb0, h > 0); gst8_if(d + 1, hb1, h > 1); gst8_if(d + 2, hb2, h > 2);
+    gst8_if(td, tb0, tl > 0); gst8_if(td + 1, tb1, tl > 1); gst8_if(td + 2, tb2, tl > 2);
+}
+
 __device__ __forceinline__ void exec_batch(uint8_t *out, InflateSmem &s, uint2 rec, uint32_t nrec)
 {
+    (void)s;
     const uint32_t lane = hgpu_lane();
     const bool have = lane < nrec;
     const uint32_t len = have ? (rec.y & 0xffffu) : 0u, dist = rec.y >> 16;
@@ -378,43 +429,12 @@ __device__ __forceinline__ void exec_batch(uint8_t *out, InflateSmem &s, uint2 r
         const bool ready = !((done >> lane) & 1u) && (dep & ~done) == 0u;
         const uint32_t R = __ballot_sync(0xffffffffu, ready);
         const uint32_t Rov = __ballot_sync(0xffffffffu, ready && ov);
-        const uint32_t P = (ready && !ov) ? (len + 31u) >> 5 : 0u;
-        uint32_t inc = P;
-#pragma unroll
-        for (int d = 1; d < 32; d <<= 1) {
-            uint32_t t = __shfl_up_sync(0xffffffffu, inc, d);
-            if (lane >= (uint32_t)d) inc += t;
-        }
-        const uint32_t TP = __shfl_sync(0xffffffffu, inc, 31);
 #ifdef HGPU_PROFILE
-        if (lane == 0) { atomicAdd(&g_prof[8], 1ull); atomicAdd(&g_prof[10], (unsigned long long)TP); atomicAdd(&g_prof[11], (unsigned long long)__popc(Rov)); }
+        if (lane == 0) { atomicAdd(&g_prof[8], 1ull); atomicAdd(&g_prof[11], (unsigned long long)__popc(Rov)); }
 #endif
-        if (P) {
-            uint32_t q = inc - P;
-            for (uint32_t off = 0; off < len; off += 32, q++) {
-                uint32_t plen = len - off < 32u ? len - off : 32u;
-                s.ptab[q] = make_uint2((dst + off) | (plen << 16), src + off);
-            }
-        }
+        // every ready match that does not overlap its own source: one lane each, word copies
+        lane_copy(out + (have ? dst : 0u), out + (have ? src : 0u), len, ready && !ov);
         __syncwarp();
-        for (uint32_t a = 0; a < TP; a += GRP) {
-            const uint32_t n = TP - a < (uint32_t)GRP ? TP - a : (uint32_t)GRP;
-            const uint2 *pt = s.ptab + a;
-            uint8_t v[GRP];
-            uint32_t px[GRP];
-#pragma unroll
-            for (int j = 0; j < GRP; j++) {
-                if ((uint32_t)j >= n) break;
-                uint2 d = pt[j];
-                px[j] = d.x;
-                if (lane < (d.x >> 16)) v[j] = out[d.y + lane];
-            }
-#pragma unroll
-            for (int j = 0; j < GRP; j++) {
-                if ((uint32_t)j >= n) break;
-                if (lane < (px[j] >> 16)) out[(px[j] & 0xffffu) + lane] = v[j];
-            }
-        }
         // overlapping matches of this round: the source is the `dist` bytes before the
         // destination, repeated
         for (uint32_t m = Rov; m; m &= m - 1) {
@@ -603,6 +623,8 @@ __device__ void run_matches(InflateSmem &s, uint8_t *out, const uint2 *mrec, uin
     __syncwarp();
 }
 
+#include "bgzf_huff.cuh"
+
 constexpr uint32_t PAR_MIN_BITS = 32 * 96;      // below this a deflate block is decoded serially
 constexpr uint32_t MREC_CAP = 65536 / 3 + 64;   // a match yields >= 3 bytes of a <= 64 KiB member
 
@@ -613,19 +635,34 @@ __device__ int decode_body_parallel(InflateSmem &s, const uint32_t *wbase, const
                                     uint32_t &end_pos, Prof &pf)
 {
     const uint32_t lane = hgpu_lane();
-    const uint32_t S = (total - body + 31) / 32;
-    uint32_t start = body + lane * S;
-    uint32_t end = lane == 31 ? total : min(total, body + (lane + 1) * S);
-    if (start > total) start = total;
-    uint32_t exitp = 0, n = 0, m = 0, st = ST_RUN;
-    bool need = true, dummy = false;
+    // 32 sub-ranges cut on word boundaries; every lane walks from PREROLL bits in front of its cut (so that
+    // it has usually found the true token grid by the time it reaches its own range) and counts from the cut
+    const uint32_t w0 = body >> 5, nwords = ((total + 31u) >> 5) - w0, Sw = (nwords + 31u) / 32u;
+    const uint32_t cut = lane == 0 ? body : min(total, (w0 + lane * Sw) << 5);
+    const uint32_t end = lane == 31 ? total : min(total, (w0 + (lane + 1) * Sw) << 5);
+    uint32_t start = cut, exitp = 0, n = 0, m = 0, st = ST_RUN, rc_ = 0;
+    bool dummy = false;
+    {
+        const uint32_t pre = lane == 0 ? body : max(body, cut - min(cut, PREROLL));
+        uint32_t p0 = cut;
+        huff_walk<0, false, false>(s, 0, wbase, wend, cut, pre, end, cut < end, 0, exitp, n, m, st, rc_, 0, 0, 0, nullptr, dummy, cut, &p0);
+        if (cut < end) start = p0; else exitp = start;
+    }
+    // a lane whose predecessor's exit is not its start walks again from there.  Only lanes up to the first
+    // one that currently ends in an end-of-block code matter.
     for (int round = 0; round < 34; round++) {
-        if (need) lane_decode<0>(s, wbase, wend, start, end, exitp, n, m, st, nullptr, 0, nullptr, 0, dummy);
-        uint32_t prev = __shfl_up_sync(0xffffffffu, exitp, 1);
-        uint32_t ns = lane == 0 ? start : prev;
-        need = ns != start;
-        start = ns;
+        const uint32_t prev = __shfl_up_sync(0xffffffffu, exitp, 1);
+        const uint32_t eobs = __ballot_sync(0xffffffffu, st == ST_EOB);
+        const uint32_t Em = eobs ? (uint32_t)__ffs(eobs) - 1u : 32u;
+        const uint32_t ns = lane == 0 ? start : prev;
+        const bool need = ns != start && lane <= Em;
         if (!__any_sync(0xffffffffu, need)) break;
+        if (need) start = ns;
+        const bool thru = need && start >= end;                  // the predecessor ran through this whole range
+        if (thru) { exitp = start; n = 0; m = 0; st = ST_RUN; }
+        uint32_t e2, n2, m2, s2;
+        huff_walk<0, false, false>(s, 0, wbase, wend, cut, start, end, need && !thru, 0, e2, n2, m2, s2, rc_, 0, 0, 0, nullptr, dummy, start);
+        if (need && !thru) { exitp = e2; n = n2; m = m2; st = s2; }
     }
     pf.mark(1);
     // the chain is now consistent: lane i starts where lane i-1 stopped
@@ -648,9 +685,10 @@ __device__ int decode_body_parallel(InflateSmem &s, const uint32_t *wbase, const
     if ((uint64_t)o + tot_out > cap) return HGPU_BGZF_ERR_SPACE;
     if (tot_m > MREC_CAP) return HGPU_BGZF_ERR_ZLIB;           // impossible within 64 KiB of output
     bool bad_dist = false;
-    if (lane <= E) {
+    {
         uint32_t e2, n2, m2, st2;
-        lane_decode<1>(s, wbase, wend, start, end, e2, n2, m2, st2, out, o + on - n, mrec, mn - m, bad_dist);
+        huff_walk<3, false, false>(s, 0, wbase, wend, cut, start, end, lane <= E, 0, e2, n2, m2, st2, rc_, 0, o + on - n, mn - m, nullptr, bad_dist,
+                                   0, nullptr, out, mrec);
     }
     if (__any_sync(0xffffffffu, bad_dist)) return HGPU_BGZF_ERR_ZLIB;   // distance too far back
     __syncwarp();
@@ -799,10 +837,10 @@ __device__ int check_header(const uint8_t *h)
     return ((h[3] & 4) && (h[10] | h[11] << 8) == 6 && h[12] == 'B' && h[13] == 'C' && (h[14] | h[15] << 8) == 2) ? 0 : -1;
 }
 
-constexpr int INFLATE_WARPS = 4;      // warps per CTA; they share only the CRC tables
+constexpr int INFLATE_WARPS = 5;      // warps per CTA; they share only the CRC tables (5 x 10 KB + 4 KB: four CTAs = 20 warps per SM)
 
 #ifndef INFL_LB
-#define INFL_LB 5
+#define INFL_LB 4
 #endif
 __global__ void __launch_bounds__(32 * INFLATE_WARPS, INFL_LB)
 bgzf_inflate_kernel(const uint8_t *__restrict__ in, const uint64_t *__restrict__ in_off,
@@ -1111,9 +1149,10 @@ int hgpu_launch_bgzf_inflate(hgpu_ctx *ctx, const uint8_t *d_in, const uint64_t 
     if (hgpu_check(cudaSetDevice(ctx->device), "cudaSetDevice")) return HGPU_ERR_CUDA;
     int rc = ensure_crc_tables(ctx, st);
     if (rc) return rc;
-    // HGPU_INFLATE_WARP=1 selects the round-1 warp-per-block kernel (output window in global memory)
-    // for A/B measurements; the product path is the CTA-per-block kernel (window in shared memory).
-    static const bool use_warp = getenv("HGPU_INFLATE_WARP") && getenv("HGPU_INFLATE_WARP")[0] == '1';
+    // The product path is the warp-per-block kernel (20 blocks in flight per SM, LZ77 through L2 with
+    // per-lane word copies: 201 GB/s on sorted BAM).  HGPU_INFLATE_CTA=1 selects the CTA-per-block kernel
+    // (window in shared memory, 2 blocks per SM: 127 GB/s) for A/B measurements.
+    static const bool use_warp = !(getenv("HGPU_INFLATE_CTA") && getenv("HGPU_INFLATE_CTA")[0] == '1');
     static bool attr_set[64];                          // function attributes are per device
     const int dv = ctx->device & 63;
     const size_t dyn_w = 4096 + INFLATE_WARPS * sizeof(InflateSmem), dyn_c = sizeof(CtaSmem);

@@ -9,6 +9,7 @@
 // HGPU_CRAM_UNSUPPORTED and stay with the host library.
 #include "hgpu_internal.h"
 #include <vector>
+#include <new>
 #include <string.h>
 
 extern "C" int hgpu_rans4x8_decode_batch_dev(hgpu_ctx *ctx, const uint8_t *d_in, const uint64_t *d_in_off,
@@ -18,7 +19,12 @@ extern "C" int hgpu_arith_decode_batch_dev(hgpu_ctx *ctx, const uint8_t *d_in, c
         const uint32_t *d_in_len, uint32_t n, uint8_t *d_out, const uint64_t *d_out_off, const uint32_t *d_out_len,
         uint32_t *d_got_len, int32_t *d_status, uint32_t max_out_len, void *stream);
 
-extern "C" int hgpu_cram_uncompress_blocks_host(hgpu_ctx *ctx, const uint8_t *file, uint64_t file_len,
+// Size fields of a CRAM block are untrusted.  A block that claims more than this is refused on its own
+// (HGPU_CRAM_ERR_DECODE, what the reference's cram_uncompress_block returns when its malloc fails); blocks above
+// BIG_BLOCK are launched one at a time so that their scratch (3 x size per resident CTA) is sized for one CTA.
+static const uint32_t MAX_BLOCK = 1u << 30, BIG_BLOCK = 16u << 20;
+
+static int cram_uncompress_impl(hgpu_ctx *ctx, const uint8_t *file, uint64_t file_len,
         const hgpu_cram_block *blocks, uint32_t n, uint8_t *out, const uint64_t *out_off,
         uint32_t *got_len, int32_t *status)
 {
@@ -34,6 +40,7 @@ extern "C" int hgpu_cram_uncompress_blocks_host(hgpu_ctx *ctx, const uint8_t *fi
         got_len[i] = 0;
         if (b.data_off < b.hdr_len || b.data_off + (uint64_t)b.comp_size + 4 > file_len) { hgpu_set_error("block %u lies outside the file image", i); return HGPU_ERR_ARG; }
         status[i] = b.method <= 8 ? HGPU_OK : HGPU_CRAM_ERR_DECODE;           // default: -1 (cram_io.c:1749)
+        if (b.uncomp_size > MAX_BLOCK) { status[i] = HGPU_CRAM_ERR_DECODE; continue; }
         if (b.method <= 8) idx[b.method].push_back(i);
         if (b.uncomp_size && (b.method == 4 || b.method == 5 || b.method == 6)) {
             if (out_off[i] < out_lo) out_lo = out_off[i];
@@ -55,6 +62,7 @@ extern "C" int hgpu_cram_uncompress_blocks_host(hgpu_ctx *ctx, const uint8_t *fi
             if (b.uncomp_size == 0) continue;
             uint32_t cap = hgpu_tok3_out_bound(file + b.data_off, b.comp_size);
             if (cap < 1024) cap = 1024;
+            if (cap > b.uncomp_size + 1024u) cap = b.uncomp_size + 1024u;     // the block header bounds what the stream may claim
             t_in_off.push_back(b.data_off); t_in_len.push_back(b.comp_size);
             t_out_off.push_back(acc); t_cap.push_back(cap);
             acc += cap;
@@ -125,7 +133,11 @@ extern "C" int hgpu_cram_uncompress_blocks_host(hgpu_ctx *ctx, const uint8_t *fi
 
     // ---- device staging: file image, the output span (same layout as the caller's), job arrays
     std::vector<uint32_t> order;                                              // job order: 4x8, Nx16, arith
-    for (int m : {4, 5, 6}) for (uint32_t i : idx[m]) if (blocks[i].uncomp_size) order.push_back(i);
+    uint32_t big5 = 0, big6 = 0;                                              // blocks launched on their own, at the end of their group
+    for (int m : {4, 5, 6}) {
+        for (uint32_t i : idx[m]) if (blocks[i].uncomp_size && (m == 4 || blocks[i].uncomp_size <= BIG_BLOCK)) order.push_back(i);
+        if (m != 4) for (uint32_t i : idx[m]) if (blocks[i].uncomp_size > BIG_BLOCK) { order.push_back(i); (m == 5 ? big5 : big6)++; }
+    }
     const uint32_t nj = (uint32_t)order.size();
     uint32_t n4 = 0, n5 = 0, n6 = 0, max5 = 0, max6 = 0;
     std::vector<uint64_t> jio(nj), joo(nj), coff(n);
@@ -134,8 +146,8 @@ extern "C" int hgpu_cram_uncompress_blocks_host(hgpu_ctx *ctx, const uint8_t *fi
         const hgpu_cram_block &b = blocks[order[k]];
         jio[k] = b.data_off; jil[k] = b.comp_size; joo[k] = out_off[order[k]] - out_lo; jol[k] = b.uncomp_size;
         if (b.method == 4) n4++;
-        else if (b.method == 5) { n5++; if (b.uncomp_size > max5) max5 = b.uncomp_size; }
-        else { n6++; if (b.uncomp_size > max6) max6 = b.uncomp_size; }
+        else if (b.method == 5) { n5++; if (b.uncomp_size > max5 && b.uncomp_size <= BIG_BLOCK) max5 = b.uncomp_size; }
+        else { n6++; if (b.uncomp_size > max6 && b.uncomp_size <= BIG_BLOCK) max6 = b.uncomp_size; }
     }
     for (uint32_t i = 0; i < n; i++) { coff[i] = blocks[i].data_off - blocks[i].hdr_len; clen[i] = blocks[i].hdr_len + blocks[i].comp_size; }
     auto up = [](uint64_t x) { return (x + 255) & ~(uint64_t)255; };
@@ -167,15 +179,24 @@ extern "C" int hgpu_cram_uncompress_blocks_host(hgpu_ctx *ctx, const uint8_t *fi
         rc = hgpu_rans4x8_decode_batch_dev(ctx, base + o_file, d_jio, d_jil, n4, base + o_out, d_joo, d_jol, d_got, d_st, s);
         if (rc) return rc;
     }
-    if (n5) {
-        rc = hgpu_launch_rans_nx16(ctx, base + o_file, d_jio + n4, d_jil + n4, n5, base + o_out, d_joo + n4, d_jol + n4,
+    std::vector<uint32_t> nomem;                                              // big blocks whose own scratch could not be had
+    if (n5 - big5) {
+        rc = hgpu_launch_rans_nx16(ctx, base + o_file, d_jio + n4, d_jil + n4, n5 - big5, base + o_out, d_joo + n4, d_jol + n4,
                                    d_got + n4, d_st + n4, max5, s);
         if (rc) return rc;
     }
-    if (n6) {
-        rc = hgpu_arith_decode_batch_dev(ctx, base + o_file, d_jio + n4 + n5, d_jil + n4 + n5, n6, base + o_out, d_joo + n4 + n5,
+    for (uint32_t k = n4 + n5 - big5; k < n4 + n5; k++) {
+        rc = hgpu_launch_rans_nx16(ctx, base + o_file, d_jio + k, d_jil + k, 1, base + o_out, d_joo + k, d_jol + k, d_got + k, d_st + k, jol[k], s);
+        if (rc == HGPU_ERR_NOMEM) nomem.push_back(k); else if (rc) return rc;
+    }
+    if (n6 - big6) {
+        rc = hgpu_arith_decode_batch_dev(ctx, base + o_file, d_jio + n4 + n5, d_jil + n4 + n5, n6 - big6, base + o_out, d_joo + n4 + n5,
                                          d_jol + n4 + n5, d_got + n4 + n5, d_st + n4 + n5, max6, s);
         if (rc) return rc;
+    }
+    for (uint32_t k = n4 + n5 + n6 - big6; k < nj; k++) {
+        rc = hgpu_arith_decode_batch_dev(ctx, base + o_file, d_jio + k, d_jil + k, 1, base + o_out, d_joo + k, d_jol + k, d_got + k, d_st + k, jol[k], s);
+        if (rc == HGPU_ERR_NOMEM) nomem.push_back(k); else if (rc) return rc;
     }
     std::vector<uint32_t> jgot(nj), crc(n);
     std::vector<int32_t> jst(nj);
@@ -187,6 +208,7 @@ extern "C" int hgpu_cram_uncompress_blocks_host(hgpu_ctx *ctx, const uint8_t *fi
     if (hgpu_check(cudaMemcpyAsync(crc.data(), base + o_crc, (size_t)n * 4, cudaMemcpyDeviceToHost, s), "D2H")) return HGPU_ERR_CUDA;
     if (hgpu_check(cudaStreamSynchronize(s), "sync")) return HGPU_ERR_CUDA;
 
+    for (uint32_t k : nomem) jst[k] = HGPU_CRAM_ERR_DECODE;                    // never launched: its status word is stale
     // ---- results, in the reference's order of checks: CRC first, then the codec, then the size
     for (uint32_t k = 0; k < nj; k++) {
         const uint32_t i = order[k];
@@ -232,4 +254,20 @@ extern "C" int hgpu_cram_uncompress_blocks_host(hgpu_ctx *ctx, const uint8_t *fi
         if (crc[i] != want) { status[i] = HGPU_CRAM_ERR_CRC; got_len[i] = 0; }
     }
     return HGPU_OK;
+}
+
+extern "C" int hgpu_cram_uncompress_blocks_host(hgpu_ctx *ctx, const uint8_t *file, uint64_t file_len,
+        const hgpu_cram_block *blocks, uint32_t n, uint8_t *out, const uint64_t *out_off,
+        uint32_t *got_len, int32_t *status)
+{
+    // no C++ exception may cross the C ABI (a host buffer sized from a crafted file: std::bad_alloc)
+    try {
+        return cram_uncompress_impl(ctx, file, file_len, blocks, n, out, out_off, got_len, status);
+    } catch (const std::bad_alloc &) {
+        hgpu_set_error("out of host memory");
+        return HGPU_ERR_NOMEM;
+    } catch (...) {
+        hgpu_set_error("internal error");
+        return HGPU_ERR_CUDA;
+    }
 }

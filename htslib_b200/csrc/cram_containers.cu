@@ -72,6 +72,7 @@ extern "C" long hgpu_cram_scan_containers(const uint8_t *file, uint64_t len, hgp
         c.landmark0 = (uint32_t)nl;
         for (int32_t k = 0; k < c.n_landmarks; k++) {
             const int32_t v = r.itf8();
+            if (r.err) break;                                        // a corrupt count must not spin through 2^31 reads
             if (landmarks && nl < landmark_cap) landmarks[nl] = v;
             nl++;
         }

@@ -12,6 +12,7 @@
 // compiled reference on every container of every CRAM fixture.  Input is the UNCOMPRESSED payload of the
 // compression-header block (content type 1); CRAM 4.0's codecs are reported as "?".
 #include "hgpu_internal.h"
+#include <new>
 #include <string>
 #include <vector>
 #include <algorithm>
@@ -135,7 +136,7 @@ const char *const k_series[] = {"RN", "QS", "IN", "SC", "BF", "CF", "AP", "RG", 
 
 }  // namespace
 
-extern "C" long hgpu_cram_parse_compression_header(const uint8_t *hdr, uint32_t len, int major_version,
+static long hgpu_cram_parse_compression_header_impl(const uint8_t *hdr, uint32_t len, int major_version,
         hgpu_cram_series *series, long cap, char *text, size_t text_cap)
 {
     if (!hdr || major_version != 3) { hgpu_set_error("compression header: CRAM 3.x only"); return -1; }
@@ -214,4 +215,19 @@ extern "C" long hgpu_cram_parse_compression_header(const uint8_t *hdr, uint32_t 
         text[n] = 0;
     }
     return (long)out.size();
+}
+
+// no C++ exception may cross the C ABI (host buffers are sized from untrusted input: std::bad_alloc)
+extern "C" long hgpu_cram_parse_compression_header(const uint8_t *hdr, uint32_t len, int major_version,
+        hgpu_cram_series *series, long cap, char *text, size_t text_cap)
+{
+    try {
+        return hgpu_cram_parse_compression_header_impl(hdr, len, major_version, series, cap, text, text_cap);
+    } catch (const std::bad_alloc &) {
+        hgpu_set_error("out of host memory");
+        return -1;
+    } catch (...) {
+        hgpu_set_error("internal error");
+        return -1;
+    }
 }

@@ -54,26 +54,26 @@ extern "C" long hgpu_cram_scan_blocks(const uint8_t *file, uint64_t len, hgpu_cr
         int32_t clen = (int32_t)(p[0] | p[1] << 8 | p[2] << 16 | (uint32_t)p[3] << 24), v, nblk, nland;
         p += 4;
         int k;
-        for (int f = 0; f < 4; f++) { if (!(k = itf8(p, end, &v))) return -1; p += k; }       // ref id, start, span, n records
-        if (!(k = ltf8_len(p, end))) return -1; p += k;                                          // record counter
-        if (!(k = ltf8_len(p, end))) return -1; p += k;                                          // bases
-        if (!(k = itf8(p, end, &nblk))) return -1; p += k;
-        if (!(k = itf8(p, end, &nland))) return -1; p += k;
-        for (int f = 0; f < nland; f++) { if (!(k = itf8(p, end, &v))) return -1; p += k; }
-        if (end - p < 4) return -1;
+        for (int f = 0; f < 4; f++) { if (!(k = itf8(p, end, &v))) { hgpu_set_error("truncated or malformed CRAM container/block header"); return -1; } p += k; }       // ref id, start, span, n records
+        if (!(k = ltf8_len(p, end))) { hgpu_set_error("truncated or malformed CRAM container/block header"); return -1; } p += k;                                          // record counter
+        if (!(k = ltf8_len(p, end))) { hgpu_set_error("truncated or malformed CRAM container/block header"); return -1; } p += k;                                          // bases
+        if (!(k = itf8(p, end, &nblk))) { hgpu_set_error("truncated or malformed CRAM container/block header"); return -1; } p += k;
+        if (!(k = itf8(p, end, &nland))) { hgpu_set_error("truncated or malformed CRAM container/block header"); return -1; } p += k;
+        for (int f = 0; f < nland; f++) { if (!(k = itf8(p, end, &v))) { hgpu_set_error("truncated or malformed CRAM container/block header"); return -1; } p += k; }
+        if (end - p < 4) { hgpu_set_error("truncated or malformed CRAM container/block header"); return -1; }
         p += 4;                                                                                  // container CRC32
         if (clen < 0 || (uint64_t)(end - p) < (uint64_t)clen) { hgpu_set_error("container %u runs past the file", container); return -1; }
         const uint8_t *cend = p + clen;
         while (p < cend) {
-            if (cend - p < 2) return -1;
+            if (cend - p < 2) { hgpu_set_error("truncated or malformed CRAM container/block header"); return -1; }
             hgpu_cram_block b;
             const uint8_t *hdr = p;
             b.method = p[0]; b.content_type = p[1]; b.container = container;
             p += 2;
             int32_t cs, us;
-            if (!(k = itf8(p, cend, &b.content_id))) return -1; p += k;
-            if (!(k = itf8(p, cend, &cs))) return -1; p += k;
-            if (!(k = itf8(p, cend, &us))) return -1; p += k;
+            if (!(k = itf8(p, cend, &b.content_id))) { hgpu_set_error("truncated or malformed CRAM container/block header"); return -1; } p += k;
+            if (!(k = itf8(p, cend, &cs))) { hgpu_set_error("truncated or malformed CRAM container/block header"); return -1; } p += k;
+            if (!(k = itf8(p, cend, &us))) { hgpu_set_error("truncated or malformed CRAM container/block header"); return -1; } p += k;
             if (cs < 0 || us < 0 || (uint64_t)(cend - p) < (uint64_t)cs + 4) { hgpu_set_error("block runs past its container"); return -1; }
             b.data_off = (uint64_t)(p - file);
             b.hdr_len = (uint16_t)(p - hdr);

@@ -15,6 +15,7 @@
 // here a model is tot, sentinel, max_sym+1 live slots, the zero terminator and the terminal, which
 // is the same machine (c_simple_model.h:85-169) in (max_sym+5)*4 bytes instead of 1040.
 #include "hgpu_internal.h"
+#include <new>
 #include <vector>
 #include <string.h>
 #include <stdlib.h>
@@ -317,7 +318,7 @@ int h_read_param(FqzParam &pm, uint32_t &max_sym, const uint8_t *in, size_t in_s
 }  // namespace
 
 // One batch of fqzcomp streams, HOST buffers.  out_cap[i]: the block's uncomp_size; status HGPU_OK / HGPU_FQZ_ERR.
-extern "C" int hgpu_fqz_decode_batch_host(hgpu_ctx *ctx, const uint8_t *in, const uint64_t *in_off,
+static int hgpu_fqz_decode_batch_host_impl(hgpu_ctx *ctx, const uint8_t *in, const uint64_t *in_off,
         const uint32_t *in_len, uint32_t n, uint8_t *out, const uint64_t *out_off, const uint32_t *out_cap,
         uint32_t *got_len, int32_t *status)
 {
@@ -330,7 +331,9 @@ extern "C" int hgpu_fqz_decode_batch_host(hgpu_ctx *ctx, const uint8_t *in, cons
 
     std::vector<FqzStream> streams(n);
     std::vector<FqzParam> params;
-    uint64_t in_end = 0, out_end = 0, model_words_total = 0, flag_bytes = 0;
+    const uint64_t MODEL_BUDGET = 6ull << 30;
+    std::vector<uint32_t> wave_first(1, 0u);                                  // first stream of every wave
+    uint64_t in_end = 0, out_end = 0, model_words_total = 0 /* largest wave */, wave_words = 0, flag_bytes = 0;
     for (uint32_t s = 0; s < n; s++) {
         FqzStream &S = streams[s];
         memset(&S, 0, sizeof(S));
@@ -376,8 +379,14 @@ extern "C" int hgpu_fqz_decode_batch_host(hgpu_ctx *ctx, const uint8_t *in, cons
         S.nparam = (uint32_t)nparam; S.gflags = gflags; S.max_sel = max_sel; S.nsym = gmax + 1;
         S.param0 = (uint32_t)pmark;
         for (int i = 0; i < 256; i++) S.stab[i] = (uint16_t)stab[i];
-        S.model_off = model_words_total;
-        model_words_total += (uint64_t)CTX_SIZE * (S.nsym + 4) + 4 * 260 + 6 + 6 + (max_sel + 1 + 4) + 8;
+        // Model arenas are handed out per WAVE: a 65 536-context arena is 11 MB at 40 symbols and 68 MB at 256, so an
+        // archive-profile file with thousands of quality blocks would ask for hundreds of GB at once.  Streams are
+        // decoded in waves whose arenas fit MODEL_BUDGET (one stream alone may exceed it); a wave reuses the arena.
+        const uint64_t words = (uint64_t)CTX_SIZE * (S.nsym + 4) + 4 * 260 + 6 + 6 + (max_sel + 1 + 4) + 8;
+        if (wave_words && (wave_words + words) * 4 > MODEL_BUDGET) { wave_first.push_back(s); wave_words = 0; }
+        S.model_off = wave_words;
+        wave_words += words;
+        if (wave_words > model_words_total) model_words_total = wave_words;
         S.flag_off = flag_bytes;
         if (gflags & GFLAG_DO_REV) flag_bytes += ((uint64_t)ulen + 16) & ~(uint64_t)15;
         S.host_status = HGPU_OK;
@@ -397,22 +406,43 @@ extern "C" int hgpu_fqz_decode_batch_host(hgpu_ctx *ctx, const uint8_t *in, cons
     if (hgpu_check(cudaMemcpyAsync(base + o_streams, streams.data(), (size_t)n * sizeof(FqzStream), cudaMemcpyHostToDevice, st), "H2D")) return HGPU_ERR_CUDA;
     if (hgpu_check(cudaMemcpyAsync(base + o_params, params.data(), params.size() * sizeof(FqzParam), cudaMemcpyHostToDevice, st), "H2D")) return HGPU_ERR_CUDA;
     if (flag_bytes && hgpu_check(cudaMemsetAsync(base + o_flags, 0, flag_bytes, st), "memset")) return HGPU_ERR_CUDA;
-    for (uint32_t first = 0; first < n; first += 65535u) {                  // gridDim.y limit
-        const uint32_t cnt = n - first < 65535u ? n - first : 65535u;
-        fqz_init_models_kernel<<<dim3(64, cnt), 256, 0, st>>>((const FqzStream *)(base + o_streams) + first, (uint32_t *)(base + o_models));
-        if (hgpu_check(cudaGetLastError(), "fqz_init_models_kernel")) return HGPU_ERR_CUDA;
+    wave_first.push_back(n);
+    for (size_t w = 0; w + 1 < wave_first.size(); w++) {                      // waves run back to back on one stream: the arena is reused
+        const uint32_t w0 = wave_first[w], wn = wave_first[w + 1] - w0;
+        if (!wn) continue;
+        for (uint32_t first = 0; first < wn; first += 65535u) {               // gridDim.y limit
+            const uint32_t cnt = wn - first < 65535u ? wn - first : 65535u;
+            fqz_init_models_kernel<<<dim3(64, cnt), 256, 0, st>>>((const FqzStream *)(base + o_streams) + w0 + first, (uint32_t *)(base + o_models));
+            if (hgpu_check(cudaGetLastError(), "fqz_init_models_kernel")) return HGPU_ERR_CUDA;
+            hgpu_count_launch();
+        }
+        fqz_decode_kernel<<<(wn + 31) / 32, 32, 0, st>>>((const FqzStream *)(base + o_streams) + w0, wn, (const FqzParam *)(base + o_params),
+                                                        base + o_in, (uint32_t *)(base + o_models), base + o_flags, base + o_out,
+                                                        (uint32_t *)(base + o_got) + w0, (int32_t *)(base + o_st) + w0);
+        if (hgpu_check(cudaGetLastError(), "fqz_decode_kernel")) return HGPU_ERR_CUDA;
         hgpu_count_launch();
     }
-    fqz_decode_kernel<<<(n + 31) / 32, 32, 0, st>>>((const FqzStream *)(base + o_streams), n, (const FqzParam *)(base + o_params),
-                                                   base + o_in, (uint32_t *)(base + o_models), base + o_flags, base + o_out,
-                                                   (uint32_t *)(base + o_got), (int32_t *)(base + o_st));
-    if (hgpu_check(cudaGetLastError(), "fqz_decode_kernel")) return HGPU_ERR_CUDA;
-    hgpu_count_launch();
     if (hgpu_check(cudaMemcpyAsync(got_len, base + o_got, (size_t)n * 4, cudaMemcpyDeviceToHost, st), "D2H")) return HGPU_ERR_CUDA;
     if (hgpu_check(cudaMemcpyAsync(status, base + o_st, (size_t)n * 4, cudaMemcpyDeviceToHost, st), "D2H")) return HGPU_ERR_CUDA;
     if (hgpu_check(cudaMemcpyAsync(out, base + o_out, out_end, cudaMemcpyDeviceToHost, st), "D2H")) return HGPU_ERR_CUDA;
     if (hgpu_check(cudaStreamSynchronize(st), "sync")) return HGPU_ERR_CUDA;
     return HGPU_OK;
+}
+
+// no C++ exception may cross the C ABI (host buffers are sized from untrusted input: std::bad_alloc)
+extern "C" int hgpu_fqz_decode_batch_host(hgpu_ctx *ctx, const uint8_t *in, const uint64_t *in_off,
+        const uint32_t *in_len, uint32_t n, uint8_t *out, const uint64_t *out_off, const uint32_t *out_cap,
+        uint32_t *got_len, int32_t *status)
+{
+    try {
+        return hgpu_fqz_decode_batch_host_impl(ctx, in, in_off, in_len, n, out, out_off, out_cap, got_len, status);
+    } catch (const std::bad_alloc &) {
+        hgpu_set_error("out of host memory");
+        return HGPU_ERR_NOMEM;
+    } catch (...) {
+        hgpu_set_error("internal error");
+        return HGPU_ERR_CUDA;
+    }
 }
 
 // Drop-in for the reference symbol (fqzcomp_qual.h): malloc'd result or NULL.  lengths/nlengths as in the

@@ -15,6 +15,7 @@
 // fqz_update_ctx :344-386, RC_Encode / RC_ShiftLow c_range_coder.h:77-146, SIMPLE_MODEL_encodeSymbol
 // c_simple_model.h:112-133) — the same sequential machine as the decoder, so streams are the parallel axis.
 #include "hgpu_internal.h"
+#include <new>
 #include <vector>
 #include <string.h>
 #include <math.h>
@@ -229,7 +230,7 @@ extern "C" uint32_t hgpu_fqz_compress_bound(uint32_t in_len, uint32_t nrec)
     return b > 4294967295.0 ? 0xffffffffu : (uint32_t)b;
 }
 
-extern "C" int hgpu_fqz_encode_batch_host(hgpu_ctx *ctx, const uint8_t *in, const uint64_t *in_off, const uint32_t *in_len,
+static int hgpu_fqz_encode_batch_host_impl(hgpu_ctx *ctx, const uint8_t *in, const uint64_t *in_off, const uint32_t *in_len,
         const uint32_t *rec_len, const uint64_t *rec_off, const uint32_t *nrec, uint32_t n, int strat,
         uint8_t *out, const uint64_t *out_off, const uint32_t *out_cap, uint32_t *out_len, int32_t *status)
 {
@@ -355,4 +356,20 @@ extern "C" int hgpu_fqz_encode_batch_host(hgpu_ctx *ctx, const uint8_t *in, cons
     if (hgpu_check(cudaMemcpyAsync(out, base + o_out, out_end, cudaMemcpyDeviceToHost, st), "D2H")) return HGPU_ERR_CUDA;
     if (hgpu_check(cudaStreamSynchronize(st), "sync")) return HGPU_ERR_CUDA;
     return HGPU_OK;
+}
+
+// no C++ exception may cross the C ABI (host buffers are sized from untrusted input: std::bad_alloc)
+extern "C" int hgpu_fqz_encode_batch_host(hgpu_ctx *ctx, const uint8_t *in, const uint64_t *in_off, const uint32_t *in_len,
+        const uint32_t *rec_len, const uint64_t *rec_off, const uint32_t *nrec, uint32_t n, int strat,
+        uint8_t *out, const uint64_t *out_off, const uint32_t *out_cap, uint32_t *out_len, int32_t *status)
+{
+    try {
+        return hgpu_fqz_encode_batch_host_impl(ctx, in, in_off, in_len, rec_len, rec_off, nrec, n, strat, out, out_off, out_cap, out_len, status);
+    } catch (const std::bad_alloc &) {
+        hgpu_set_error("out of host memory");
+        return HGPU_ERR_NOMEM;
+    } catch (...) {
+        hgpu_set_error("internal error");
+        return HGPU_ERR_CUDA;
+    }
 }

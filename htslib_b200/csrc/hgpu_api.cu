@@ -151,7 +151,7 @@ extern "C" long hgpu_bgzf_scan(const uint8_t *file, uint64_t flen, uint64_t *off
 // Pipelined whole-file inflate with host buffers.  Chunks of blocks flow through three streams
 // (H2D copy, kernel, D2H copy each in stream order) so that transfers of neighbouring chunks
 // overlap the kernel.
-extern "C" int hgpu_bgzf_inflate_file_host(hgpu_ctx *ctx, const uint8_t *file, uint64_t file_len,
+static int hgpu_bgzf_inflate_file_host_impl(hgpu_ctx *ctx, const uint8_t *file, uint64_t file_len,
                                            uint8_t *out, uint64_t out_cap, uint64_t *out_len, long *bad_block)
 {
     if (!ctx || !file || !out_len) { hgpu_set_error("bad argument"); return HGPU_ERR_ARG; }
@@ -231,6 +231,21 @@ extern "C" int hgpu_bgzf_inflate_file_host(hgpu_ctx *ctx, const uint8_t *file, u
     return HGPU_OK;
 }
 
+// no C++ exception may cross the C ABI (host buffers are sized from untrusted input: std::bad_alloc)
+extern "C" int hgpu_bgzf_inflate_file_host(hgpu_ctx *ctx, const uint8_t *file, uint64_t file_len,
+                                           uint8_t *out, uint64_t out_cap, uint64_t *out_len, long *bad_block)
+{
+    try {
+        return hgpu_bgzf_inflate_file_host_impl(ctx, file, file_len, out, out_cap, out_len, bad_block);
+    } catch (const std::bad_alloc &) {
+        hgpu_set_error("out of host memory");
+        return HGPU_ERR_NOMEM;
+    } catch (...) {
+        hgpu_set_error("internal error");
+        return HGPU_ERR_CUDA;
+    }
+}
+
 // Multi-GPU sharding rule: unit i goes to rank floor(i*world/n), i.e. rank r owns
 // the contiguous range [ceil(r*n/world), ceil((r+1)*n/world)), so every rank's output is one
 // contiguous byte range of the decompressed stream and no data-path collective is needed.
@@ -252,7 +267,7 @@ extern "C" int hgpu_shard_range(uint64_t n_units, const uint32_t *unit_out_len, 
 
 // A batch of individual blocks with HOST buffers (the thread-pool job seam):
 // H2D of the gathered compressed blocks, one launch, D2H of the slots and the per-block results.
-extern "C" int hgpu_bgzf_inflate_blocks_host(hgpu_ctx *ctx, const uint8_t *in, const uint64_t *in_off,
+static int hgpu_bgzf_inflate_blocks_host_impl(hgpu_ctx *ctx, const uint8_t *in, const uint64_t *in_off,
         const uint32_t *in_len, uint32_t n, uint8_t *out, const uint64_t *out_off, const uint32_t *out_cap,
         uint32_t *out_len, int32_t *status)
 {
@@ -289,11 +304,27 @@ extern "C" int hgpu_bgzf_inflate_blocks_host(hgpu_ctx *ctx, const uint8_t *in, c
     return HGPU_OK;
 }
 
+// no C++ exception may cross the C ABI (host buffers are sized from untrusted input: std::bad_alloc)
+extern "C" int hgpu_bgzf_inflate_blocks_host(hgpu_ctx *ctx, const uint8_t *in, const uint64_t *in_off,
+        const uint32_t *in_len, uint32_t n, uint8_t *out, const uint64_t *out_off, const uint32_t *out_cap,
+        uint32_t *out_len, int32_t *status)
+{
+    try {
+        return hgpu_bgzf_inflate_blocks_host_impl(ctx, in, in_off, in_len, n, out, out_off, out_cap, out_len, status);
+    } catch (const std::bad_alloc &) {
+        hgpu_set_error("out of host memory");
+        return HGPU_ERR_NOMEM;
+    } catch (...) {
+        hgpu_set_error("internal error");
+        return HGPU_ERR_CUDA;
+    }
+}
+
 // A batch of bgzf_job-shaped blocks: every block has its OWN host buffers (bgzf.c:92-101 keeps
 // comp_data / uncomp_data inside each pooled job).  Gather into pinned staging, one H2D, one
 // launch, one D2H, scatter.  ctx == NULL uses the process-wide context of the reference-named
 // shims (one batch at a time).  uncomp_len[i]: in = room in uncomp[i], out = inflated length.
-extern "C" int hgpu_bgzf_inflate_jobs_host(hgpu_ctx *ctx, uint32_t n, const uint8_t *const *comp, const uint32_t *comp_len,
+static int hgpu_bgzf_inflate_jobs_host_impl(hgpu_ctx *ctx, uint32_t n, const uint8_t *const *comp, const uint32_t *comp_len,
                                            uint8_t *const *uncomp, uint32_t *uncomp_len, int32_t *status)
 {
     if (n && (!comp || !comp_len || !uncomp || !uncomp_len || !status)) { hgpu_set_error("bad argument"); return HGPU_ERR_ARG; }
@@ -351,6 +382,21 @@ extern "C" int hgpu_bgzf_inflate_jobs_host(hgpu_ctx *ctx, uint32_t n, const uint
     }
 }
 
+// no C++ exception may cross the C ABI (host buffers are sized from untrusted input: std::bad_alloc)
+extern "C" int hgpu_bgzf_inflate_jobs_host(hgpu_ctx *ctx, uint32_t n, const uint8_t *const *comp, const uint32_t *comp_len,
+                                           uint8_t *const *uncomp, uint32_t *uncomp_len, int32_t *status)
+{
+    try {
+        return hgpu_bgzf_inflate_jobs_host_impl(ctx, n, comp, comp_len, uncomp, uncomp_len, status);
+    } catch (const std::bad_alloc &) {
+        hgpu_set_error("out of host memory");
+        return HGPU_ERR_NOMEM;
+    } catch (...) {
+        hgpu_set_error("internal error");
+        return HGPU_ERR_CUDA;
+    }
+}
+
 // zlib-compatible combine on the host side of the ABI: crc(A||B) from crc(A), crc(B), |B|
 static uint32_t h_multmodp(uint32_t a, uint32_t b)
 {
@@ -368,14 +414,23 @@ static uint32_t h_xpow_bytes(uint64_t n)
     return p;
 }
 
-extern "C" uint32_t hgpu_crc32(hgpu_ctx *ctx, uint32_t crc, const void *buf, size_t len)
+// *status (may be NULL) = HGPU_OK or the error; on error the incoming crc is returned unchanged AND
+// hgpu_last_error() is set — a caller that cannot take a status must check hgpu_crc32_failed().
+static thread_local int g_crc_failed = 0;
+extern "C" int hgpu_crc32_failed(void) { return g_crc_failed; }
+static uint32_t crc32_impl(hgpu_ctx *ctx, uint32_t crc, const void *buf, size_t len, int *status)
 {
-    if (!ctx || len == 0 || !buf) return crc;
-    if (cudaSetDevice(ctx->device) != cudaSuccess) return crc;
+    int dummy;
+    if (!status) status = &dummy;
+    *status = HGPU_OK;
+    if (!ctx) { hgpu_set_error("bad argument"); *status = HGPU_ERR_ARG; return crc; }
+    if (len == 0 || !buf) return crc;
+    *status = HGPU_ERR_CUDA;
+    if (hgpu_check(cudaSetDevice(ctx->device), "cudaSetDevice")) return crc;
     const size_t chunk = 1u << 20;
     size_t nchunk = (len + chunk - 1) / chunk;
     size_t data = (len + 255) & ~(size_t)255;
-    if (hgpu_ensure_stage(ctx, data + nchunk * 4 + 256)) return crc;
+    if (hgpu_ensure_stage(ctx, data + nchunk * 4 + 256)) { *status = HGPU_ERR_NOMEM; return crc; }
     uint8_t *d = ctx->d_stage;
     uint32_t *d_part = (uint32_t *)(d + data);
     if (hgpu_check(cudaMemcpyAsync(d, buf, len, cudaMemcpyHostToDevice, ctx->stream), "H2D")) return crc;
@@ -387,6 +442,16 @@ extern "C" uint32_t hgpu_crc32(hgpu_ctx *ctx, uint32_t crc, const void *buf, siz
         size_t n = (i + 1 == nchunk) ? len - i * chunk : chunk;
         crc = h_multmodp(h_xpow_bytes(n), crc) ^ part[i];
     }
+    *status = HGPU_OK;
+    return crc;
+}
+
+extern "C" uint32_t hgpu_crc32(hgpu_ctx *ctx, uint32_t crc, const void *buf, size_t len)
+{
+    int st = HGPU_OK;
+    try { crc = crc32_impl(ctx, crc, buf, len, &st); }
+    catch (...) { hgpu_set_error("out of host memory"); st = HGPU_ERR_NOMEM; }
+    g_crc_failed = st != HGPU_OK;
     return crc;
 }
 
@@ -401,7 +466,7 @@ extern "C" int hgpu_rans_nx16_decode_batch_dev(hgpu_ctx *ctx, const uint8_t *d_i
                                  d_status, max_out_len, stream ? (cudaStream_t)stream : ctx->stream);
 }
 
-extern "C" int hgpu_rans_nx16_decode_batch_host(hgpu_ctx *ctx, const uint8_t *in, const uint64_t *in_off,
+static int hgpu_rans_nx16_decode_batch_host_impl(hgpu_ctx *ctx, const uint8_t *in, const uint64_t *in_off,
         const uint32_t *in_len, uint32_t n, uint8_t *out, const uint64_t *out_off, const uint32_t *out_len,
         uint32_t *got_len, int32_t *status)
 {
@@ -439,6 +504,22 @@ extern "C" int hgpu_rans_nx16_decode_batch_host(hgpu_ctx *ctx, const uint8_t *in
     if (hgpu_check(cudaStreamSynchronize(s), "sync")) return HGPU_ERR_CUDA;
     for (uint32_t i = 0; i < n; i++) { if (got_len) got_len[i] = got[i]; if (status) status[i] = st[i]; }
     return HGPU_OK;
+}
+
+// no C++ exception may cross the C ABI (host buffers are sized from untrusted input: std::bad_alloc)
+extern "C" int hgpu_rans_nx16_decode_batch_host(hgpu_ctx *ctx, const uint8_t *in, const uint64_t *in_off,
+        const uint32_t *in_len, uint32_t n, uint8_t *out, const uint64_t *out_off, const uint32_t *out_len,
+        uint32_t *got_len, int32_t *status)
+{
+    try {
+        return hgpu_rans_nx16_decode_batch_host_impl(ctx, in, in_off, in_len, n, out, out_off, out_len, got_len, status);
+    } catch (const std::bad_alloc &) {
+        hgpu_set_error("out of host memory");
+        return HGPU_ERR_NOMEM;
+    } catch (...) {
+        hgpu_set_error("internal error");
+        return HGPU_ERR_CUDA;
+    }
 }
 
 // ------------------------------------------------------------------------------------------ shims
@@ -508,7 +589,10 @@ extern "C" uint32_t hts_crc32(uint32_t crc, const void *buf, size_t len)
     std::lock_guard<std::mutex> lock(g_shim_mu);
     hgpu_ctx *ctx = shim_ctx();
     if (!ctx) { fprintf(stderr, "htsgpu: hts_crc32 without a CUDA device: %s\n", hgpu_last_error()); abort(); }
-    return hgpu_crc32(ctx, crc, buf, len);
+    // hts_crc32 has no error channel (bgzf.c:620): a checksum that was not computed must not be returned as one
+    const uint32_t r = hgpu_crc32(ctx, crc, buf, len);
+    if (hgpu_crc32_failed()) { fprintf(stderr, "htsgpu: hts_crc32 failed on the device: %s\n", hgpu_last_error()); abort(); }
+    return r;
 }
 
 extern "C" int hgpu_bgzf_compress_batch_dev(hgpu_ctx *ctx, const uint8_t *d_in, const uint64_t *d_in_off,

@@ -48,13 +48,14 @@ struct WarpScratch {
     int pass;                // 0: small-table passes (defer what they cannot hold), 1: everything else
     mutable bool defer;      // set when a small-table pass hands the stream to pass 1
     struct Hook *hook;       // non-null: top-level plain streams stop after the table build (rans_nx16_fast.cuh)
+    bool compact = false;    // prefer the compact table form even when the full one would fit (many streams per warp)
 };
 
 // What a hooked dec_order0/1 hands back instead of running its symbol loop.
 struct Hook {
     int mode;                // HOOK_X32: only 32-way streams stop; HOOK_N4: only 4-way streams stop
     bool taken;
-    uint32_t order, N, shift, ncol, ipos, U, R, row0, tab_bytes;
+    uint32_t order, N, shift, lb, ncol, ipos, U, R, row0, tab_bytes;
     const uint8_t *in; uint32_t in_len;
     uint8_t *out;
     uint8_t *lut; uint32_t *fb;
@@ -111,11 +112,20 @@ __device__ int read_alphabet(const uint8_t *p, const uint8_t *end, uint32_t *F)
     return (int)(p - s);
 }
 
+// Two forms of the slot -> symbol map of a row:
+//   full     lb == shift: lut[row][m] is the symbol of slot m                      (1 << shift bytes per row)
+//   compact  lb <  shift: lut[row][m >> (shift - lb)] is the symbol that owns the FIRST slot of that
+//            bucket; the symbol of m is found by walking the row's records forward while m lies behind
+//            the record's range (one step in the common case: 64 buckets for at most a few dozen symbols).
+//            A 40-symbol order-1 table is 9 KiB instead of 47 KiB (shift 10) / 170 KiB (shift 12), so
+//            it stays in shared memory; rows no valid stream enters ("null rows") only exist in full form.
+constexpr uint32_t COMPACT_LB = 6;
 struct Table {
-    uint8_t *lut;      // [rows][1<<shift]
+    uint8_t *lut;      // [rows][1<<lb]
     uint32_t *fb;      // [rows][ncol]  byte | start<<8 | (f-1)<<20
     uint32_t ncol;     // compact alphabet size
     uint32_t shift;
+    uint32_t lb;       // index bits of a lut row
     bool     in_smem;
 };
 
@@ -153,12 +163,15 @@ __device__ void fill_row(const Table &t, uint32_t row, const uint32_t *f, const 
                          const uint8_t *symof, bool wrap12)
 {
     const uint32_t lane = hgpu_lane();
-    uint8_t *lrow = t.lut + ((size_t)row << t.shift);
+    uint8_t *lrow = t.lut + ((size_t)row << t.lb);
     uint32_t *frow = t.fb + (size_t)row * t.ncol;
+    const uint32_t cs = t.shift - t.lb, rnd = (1u << cs) - 1u;
     for (uint32_t k = 0; k < t.ncol; k++) {
         uint32_t fk = f[k], c0 = cum[k];
         if (!fk) continue;
-        for (uint32_t y = lane; y < fk; y += 32) lrow[c0 + y] = (uint8_t)k;
+        // buckets whose first slot lies in [c0, c0 + fk)   (cs == 0: every slot)
+        const uint32_t b0 = (c0 + rnd) >> cs, b1 = (c0 + fk + rnd) >> cs;
+        for (uint32_t y = b0 + lane; y < b1; y += 32) lrow[y] = (uint8_t)k;
     }
     for (uint32_t k = lane; k < t.ncol; k += 32) {
         uint32_t fk = f[k];
@@ -171,8 +184,8 @@ __device__ void fill_row(const Table &t, uint32_t row, const uint32_t *f, const 
 __device__ void fill_null_row(const Table &t, uint32_t row)
 {
     const uint32_t lane = hgpu_lane();
-    uint8_t *lrow = t.lut + ((size_t)row << t.shift);
-    for (uint32_t y = lane; y < (1u << t.shift); y += 32) lrow[y] = 0;
+    uint8_t *lrow = t.lut + ((size_t)row << t.lb);       // (only ever called on a full table)
+    for (uint32_t y = lane; y < (1u << t.lb); y += 32) lrow[y] = 0;
     if (lane == 0) t.fb[(size_t)row * t.ncol] = 0;     // byte 0, start 0, f 1
 }
 
@@ -260,12 +273,28 @@ __device__ __forceinline__ void renorm_fast(uint32_t &R, bool active, const uint
     rel += 2u * __popc(bal);
 }
 
-template <bool SMEM>
+// record of slot m in one row; COMPACT: start from the bucket's first symbol and walk forward (warp-uniform loop)
+template <bool COMPACT>
+__device__ __forceinline__ uint32_t row_lookup(const uint8_t *lut, const uint32_t *fb, uint32_t m, uint32_t cs)
+{
+    uint32_t k = lut[COMPACT ? m >> cs : m];
+    uint32_t e = fb[k];
+    if (COMPACT) {
+        for (;;) {
+            const bool go = m >= ((e >> 8) & 0xfffu) + (e >> 20) + 1u;      // m lies behind this record's range
+            if (!__any_sync(0xffffffffu, go)) break;
+            if (go) e = fb[++k];
+        }
+    }
+    return e;
+}
+
+template <bool SMEM, bool COMPACT = false>
 __device__ void loop_order0(uint8_t *smem, const Table &t, const uint8_t *in, uint32_t in_len, uint32_t ipos,
                             uint8_t *out, uint32_t U, uint32_t N, uint32_t R)
 {
     const uint32_t lane = hgpu_lane();
-    const uint32_t mask = (1u << t.shift) - 1, shift = t.shift;
+    const uint32_t mask = (1u << t.shift) - 1, shift = t.shift, cs = t.shift - t.lb;
     const uint8_t *lut = t.lut;
     const uint32_t *fb = t.fb;
     uint8_t *ring = smem + SM_RING;
@@ -279,7 +308,7 @@ __device__ void loop_order0(uint8_t *smem, const Table &t, const uint8_t *in, ui
         while (i + (32u - lane) <= U && ipos + rel + 64u <= in_len) {
             ring_ensure(ring, wr, ipos + rel, 64);
             uint32_t m = R & mask;
-            uint32_t e = fb[lut[m]], q = R >> shift;
+            uint32_t e = row_lookup<COMPACT>(lut, fb, m, cs), q = R >> shift;
             R = (e >> 20) * q + q + m - ((e >> 8) & 0xfffu);
             out[i] = (uint8_t)e;
             renorm_fast(R, true, ring, rel);
@@ -291,7 +320,7 @@ __device__ void loop_order0(uint8_t *smem, const Table &t, const uint8_t *in, ui
         ring_ensure(ring, wr, ipos, 64);
         bool act = mine && i < U;
         uint32_t m = R & mask;
-        uint32_t e = fb[lut[m]], q = R >> shift;
+        uint32_t e = row_lookup<COMPACT>(lut, fb, m, cs), q = R >> shift;
         if (act) {
             R = (e >> 20) * q + q + m - ((e >> 8) & 0xfffu);
             out[i] = (uint8_t)e;
@@ -312,12 +341,12 @@ __device__ __forceinline__ void renorm_fast_s(uint32_t &R, bool active, uint32_t
     rel += 2u * __popc(bal);
 }
 
-template <bool SMEM, bool FULL>
+template <bool SMEM, bool FULL, bool COMPACT = false>
 __device__ void loop_order1(uint8_t *smem, const Table &t, const uint8_t *in, uint32_t in_len, uint32_t ipos,
                             uint8_t *out, uint32_t U, uint32_t N, uint32_t R, uint32_t row0)
 {
     const uint32_t lane = hgpu_lane();
-    const uint32_t mask = (1u << t.shift) - 1, shift = t.shift;
+    const uint32_t mask = (1u << t.shift) - 1, shift = t.shift, lb = t.lb, cs = t.shift - t.lb;
     const uint8_t *lut = t.lut;
     const uint8_t *fbb = reinterpret_cast<const uint8_t *>(t.fb);
     const uint32_t sm_base = (uint32_t)__cvta_generic_to_shared(smem);
@@ -330,19 +359,26 @@ __device__ void loop_order1(uint8_t *smem, const Table &t, const uint8_t *in, ui
     const uint32_t seg = U / N;
     uint8_t *op = out + (size_t)(mine ? lane : 0) * seg;
     const uint32_t fstride = t.ncol * 4u;
-    uint32_t lrow = row0 << shift, frow = row0 * fstride, acc = 0;
+    uint32_t lrow = row0 << lb, frow = row0 * fstride, acc = 0;
 
     // one symbol for the lanes in ACTIVE; the record carries the next row's offsets
 #define RANS_O1_CORE(ACTIVE)                                                                       \
         uint32_t m = R & mask;                                                                     \
-        uint32_t k = SMEM ? lds_u8(lut_a + lrow + m) : (uint32_t)lut[lrow + m];                    \
+        uint32_t k = SMEM ? lds_u8(lut_a + lrow + (COMPACT ? m >> cs : m)) : (uint32_t)lut[lrow + m]; \
         uint32_t e = SMEM ? lds_u32(fb_a + frow + k * 4u)                                          \
                           : *reinterpret_cast<const uint32_t *>(fbb + frow + k * 4u);              \
+        if (COMPACT) {      /* walk forward while m lies behind the record's range */             \
+            for (;;) {                                                                             \
+                const bool go_ = m >= ((e >> 8) & 0xfffu) + (e >> 20) + 1u;                        \
+                if (!__any_sync(0xffffffffu, go_)) break;                                          \
+                if (go_) { k++; e = lds_u32(fb_a + frow + k * 4u); }                               \
+            }                                                                                      \
+        }                                                                                          \
         if (ACTIVE) {                                                                              \
             uint32_t q = R >> shift;                                                               \
             R = (e >> 20) * q + q + m - ((e >> 8) & 0xfffu);                                       \
             acc = __funnelshift_l(acc, e, 24);                                                     \
-            lrow = k << shift;                                                                     \
+            lrow = k << lb;                                                                        \
             frow = k * fstride;                                                                    \
         }
 
@@ -411,19 +447,26 @@ __device__ int load_states(const uint8_t *p, const uint8_t *end, uint32_t N, uin
     return __any_sync(0xffffffffu, R < RANS_L) ? -1 : 0;
 }
 
-__device__ Table place_table(uint8_t *smem, const WarpScratch &ws, uint32_t rows, uint32_t ncol, uint32_t shift)
+__device__ __forceinline__ uint32_t table_bytes(uint32_t rows, uint32_t ncol, uint32_t lb)
+{ return (((rows << lb) + 15u) & ~15u) + rows * ncol * 4u; }
+
+// full_only: the caller met a row that needs the full form
+__device__ Table place_table(uint8_t *smem, const WarpScratch &ws, uint32_t rows, uint32_t ncol, uint32_t shift, bool full_only = false)
 {
     Table t;
-    uint32_t lut_bytes = ((rows << shift) + 15u) & ~15u;
-    uint32_t need = lut_bytes + rows * ncol * 4u;
     (void)smem;
+    const uint32_t need_f = table_bytes(rows, ncol, shift), need_c = table_bytes(rows, ncol, COMPACT_LB);
+    uint32_t lb = shift;
+    if (!full_only && need_c <= ws.tab_cap && (ws.compact || need_f > ws.tab_cap)) lb = COMPACT_LB;
+    const uint32_t need = lb == shift ? need_f : need_c;
     if (need > ws.tab_cap && !ws.gtab) ws.defer = true;                 // caller bails out
     uint8_t *base = need <= ws.tab_cap ? ws.tab_base : ws.gtab;
     t.in_smem = need <= ws.tab_cap;
     t.lut = base;
-    t.fb = reinterpret_cast<uint32_t *>(base + lut_bytes);
+    t.fb = reinterpret_cast<uint32_t *>(base + (((rows << lb) + 15u) & ~15u));
     t.ncol = ncol;
     t.shift = shift;
+    t.lb = lb;
     return t;
 }
 
@@ -490,12 +533,13 @@ __device__ int dec_order0(uint8_t *smem, const WarpScratch &ws, const uint8_t *i
             __syncwarp();
         }
         h.taken = true; h.order = 0; h.N = N; h.shift = 12; h.ncol = ncol; h.ipos = ipos; h.U = U; h.R = R; h.row0 = 0;
-        h.in = in; h.in_len = in_len; h.out = out; h.lut = t.lut; h.fb = t.fb;
-        h.tab_bytes = ((4096u + 15u) & ~15u) + ncol * 4u;
+        h.in = in; h.in_len = in_len; h.out = out; h.lut = t.lut; h.fb = t.fb; h.lb = t.lb;
+        h.tab_bytes = table_bytes(1, ncol, t.lb);
         return RC_HOOKED;
     }
-    if (t.in_smem) loop_order0<true>(smem, t, in, in_len, ipos, out, U, N, R);
-    else           loop_order0<false>(smem, t, in, in_len, ipos, out, U, N, R);
+    if (t.lb != t.shift) loop_order0<true, true>(smem, t, in, in_len, ipos, out, U, N, R);
+    else if (t.in_smem)  loop_order0<true>(smem, t, in, in_len, ipos, out, U, N, R);
+    else                 loop_order0<false>(smem, t, in, in_len, ipos, out, U, N, R);
     __syncwarp();
     return 0;
 }
@@ -549,6 +593,8 @@ __device__ int dec_order1(uint8_t *smem, const WarpScratch &ws, const uint8_t *i
     Table t = place_table(smem, ws, ncol, ncol, shift);
     if (ws.defer) return -1;
     const uint32_t total = 1u << shift;
+    const uint8_t *rows_at = p;
+build_rows:
     uint16_t *Fcap = (top && ws.hook && N == 32 && ncol <= 16) ? ws.hook->Fcap : nullptr;
     if (Fcap) {                                   // row 16 = per-row "null row" flags
         __syncwarp();
@@ -556,6 +602,7 @@ __device__ int dec_order1(uint8_t *smem, const WarpScratch &ws, const uint8_t *i
         __syncwarp();
     }
     for (uint32_t r = 0; r < ncol; r++) {
+        if (t.lb != shift && (r == 0 && !zero_in_a0)) goto need_full;
         if (r == 0 && !zero_in_a0) { fill_null_row(t, 0); continue; }
         // decode_freq_d (:425-456): one varint per alphabet symbol, zero followed by a run of zeros
         const uint8_t *q = p;
@@ -578,6 +625,7 @@ __device__ int dec_order1(uint8_t *smem, const WarpScratch &ws, const uint8_t *i
         __syncwarp();
         if (q == p) return -1;
         p = q;
+        if (!T && t.lb != shift) goto need_full;
         if (!T) { fill_null_row(t, r); continue; }
         if (T != total) {                         // normalise_freq_shift
             int sh = 0; uint32_t tt = T;
@@ -596,6 +644,14 @@ __device__ int dec_order1(uint8_t *smem, const WarpScratch &ws, const uint8_t *i
         }
         __syncwarp();
     }
+    if (false) {
+need_full:  // a row no valid stream enters exists only in the full form: place the table again and re-read the rows
+        __syncwarp();
+        t = place_table(smem, ws, ncol, ncol, shift, true);
+        if (ws.defer) return -1;
+        p = rows_at;
+        goto build_rows;
+    }
     __syncwarp();
     if (!t.in_smem) __threadfence_block();
     if (after_tab) p = after_tab;
@@ -606,11 +662,14 @@ __device__ int dec_order1(uint8_t *smem, const WarpScratch &ws, const uint8_t *i
     if (top && ws.hook && t.in_smem && ws.hook->mode == (N == 32 ? HOOK_X32 : HOOK_N4)) {
         Hook &h = *ws.hook;
         h.taken = true; h.order = 1; h.N = N; h.shift = shift; h.ncol = ncol; h.ipos = ipos; h.U = U; h.R = R; h.row0 = 0;
-        h.in = in; h.in_len = in_len; h.out = out; h.lut = t.lut; h.fb = t.fb;
-        h.tab_bytes = (((ncol << shift) + 15u) & ~15u) + ncol * ncol * 4u;
+        h.in = in; h.in_len = in_len; h.out = out; h.lut = t.lut; h.fb = t.fb; h.lb = t.lb;
+        h.tab_bytes = table_bytes(ncol, ncol, t.lb);
         return RC_HOOKED;
     }
-    if (t.in_smem) {
+    if (t.lb != shift) {
+        if (N == 32) loop_order1<true, true, true>(smem, t, in, in_len, ipos, out, U, N, R, 0);
+        else         loop_order1<true, false, true>(smem, t, in, in_len, ipos, out, U, N, R, 0);
+    } else if (t.in_smem) {
         if (N == 32) loop_order1<true, true>(smem, t, in, in_len, ipos, out, U, N, R, 0);
         else         loop_order1<true, false>(smem, t, in, in_len, ipos, out, U, N, R, 0);
     } else           loop_order1<false, false>(smem, t, in, in_len, ipos, out, U, N, R, 0);

@@ -90,7 +90,7 @@ __device__ bool fast32_emit(uint8_t *smem, const Hook &h, uint32_t job, uint32_t
 {
     const uint32_t lane = hgpu_lane();
     const uint16_t *Fc = h.Fcap;
-    if (h.ncol > 16 || h.U < F32_MIN_U) return false;
+    if (h.ncol > 16 || h.U < F32_MIN_U || h.lb != h.shift) return false;
     // emit alphabet: symbols with a non-zero frequency in any row (order 1: byte 0 may own only the start row)
     uint32_t emit = 0, nullrows = 0;
     const uint32_t rows = h.order ? h.ncol : 1;
@@ -507,8 +507,11 @@ rans_prep32_kernel(const uint8_t *__restrict__ in, const uint64_t *__restrict__ 
         else if (rc == RC_HOOKED) {
             if (fast32_emit(smem, hook, job, (uint32_t)(hook.in - sin), jobs, njobs)) st = RANS_PENDING;
             else {
-                Table t; t.lut = hook.lut; t.fb = hook.fb; t.ncol = hook.ncol; t.shift = hook.shift; t.in_smem = true;
-                if (hook.order) loop_order1<true, true>(smem, t, hook.in, hook.in_len, hook.ipos, hook.out, hook.U, 32, hook.R, hook.row0);
+                Table t; t.lut = hook.lut; t.fb = hook.fb; t.ncol = hook.ncol; t.shift = hook.shift; t.lb = hook.lb; t.in_smem = true;
+                if (hook.lb != hook.shift) {
+                    if (hook.order) loop_order1<true, true, true>(smem, t, hook.in, hook.in_len, hook.ipos, hook.out, hook.U, 32, hook.R, hook.row0);
+                    else            loop_order0<true, true>(smem, t, hook.in, hook.in_len, hook.ipos, hook.out, hook.U, 32, hook.R);
+                } else if (hook.order) loop_order1<true, true>(smem, t, hook.in, hook.in_len, hook.ipos, hook.out, hook.U, 32, hook.R, hook.row0);
                 else            loop_order0<true>(smem, t, hook.in, hook.in_len, hook.ipos, hook.out, hook.U, 32, hook.R);
                 __syncwarp();
                 st = HGPU_OK;
@@ -522,12 +525,12 @@ rans_prep32_kernel(const uint8_t *__restrict__ in, const uint64_t *__restrict__ 
 // tile4: eight 4-way streams per warp, one per quad of lanes
 // ---------------------------------------------------------------------------------------------
 struct Quad {
-    uint32_t lut_a, fb_a, mask, shift, rowsz, fstride, ipos, in_len, U, order, job, got;
+    uint32_t lut_a, fb_a, mask, shift, cs, rowsz, fstride, ipos, in_len, U, order, job, got;
     const uint8_t *in;
     uint8_t *out;
     uint32_t R[4];
 };
-constexpr uint32_t T4_POOL = 40960, T4_QUADS = SM_TAB + T4_POOL, T4_SMEM = T4_QUADS + 8 * sizeof(Quad);
+constexpr uint32_t T4_POOL = 8192, T4_QUADS = SM_TAB + T4_POOL, T4_SMEM = T4_QUADS + 8 * sizeof(Quad);      // compact tables: eight streams' worth
 
 __device__ __forceinline__ void renorm_quad(uint32_t &R, bool act, const uint8_t *in, uint32_t &ipos, uint32_t in_len,
                                             uint32_t qsh, uint32_t zlt)
@@ -549,7 +552,7 @@ __device__ void tile4_run(const Quad *quads, uint32_t nq, uint32_t idle_a)
     const bool live = q < nq;
     const Quad &Q = quads[live ? q : 0];
     const uint32_t lut_a = live ? Q.lut_a : idle_a, fb_a = live ? Q.fb_a : idle_a;
-    const uint32_t mask = live ? Q.mask : 0u, shift = Q.shift, rowsz = live ? Q.rowsz : 0u, fstride = live ? Q.fstride : 0u;
+    const uint32_t mask = live ? Q.mask : 0u, shift = Q.shift, cs = Q.cs, rowsz = live ? Q.rowsz : 0u, fstride = live ? Q.fstride : 0u;
     const uint32_t in_len = Q.in_len, U = live ? Q.U : 0u, order = Q.order;
     const uint8_t *in = Q.in;
     uint32_t ipos = Q.ipos, R = Q.R[z];
@@ -563,8 +566,13 @@ __device__ void tile4_run(const Quad *quads, uint32_t nq, uint32_t idle_a)
     for (uint32_t i = 0; i < maxsteps; i++) {
         const bool act = i < nsteps;
         uint32_t m = R & mask;
-        uint32_t k = lds_u8(lut_a + lrow + m);
+        uint32_t k = lds_u8(lut_a + lrow + (m >> cs));
         uint32_t e = lds_u32(fb_a + frow + k * 4u);
+        for (;;) {                                           // compact rows: walk forward while m lies behind the record's range
+            const bool go = live && m >= ((e >> 8) & 0xfffu) + (e >> 20) + 1u;
+            if (!__any_sync(0xffffffffu, go)) break;
+            if (go) { k++; e = lds_u32(fb_a + frow + k * 4u); }
+        }
         if (act) {
             uint32_t qq = R >> shift;
             R = (e >> 20) * qq + qq + m - ((e >> 8) & 0xfffu);
@@ -579,8 +587,13 @@ __device__ void tile4_run(const Quad *quads, uint32_t nq, uint32_t idle_a)
         const bool act = order ? (z == 3 && t < rem) : (t == 0 && z < rem);
         if (!__any_sync(0xffffffffu, act)) break;
         uint32_t m = R & mask;
-        uint32_t k = lds_u8(lut_a + lrow + m);
+        uint32_t k = lds_u8(lut_a + lrow + (m >> cs));
         uint32_t e = lds_u32(fb_a + frow + k * 4u);
+        for (;;) {
+            const bool go = live && m >= ((e >> 8) & 0xfffu) + (e >> 20) + 1u;
+            if (!__any_sync(0xffffffffu, go)) break;
+            if (go) { k++; e = lds_u32(fb_a + frow + k * 4u); }
+        }
         if (act) {
             uint32_t qq = R >> shift;
             R = (e >> 20) * qq + qq + m - ((e >> 8) & 0xfffu);
@@ -592,7 +605,7 @@ __device__ void tile4_run(const Quad *quads, uint32_t nq, uint32_t idle_a)
     __syncwarp();
 }
 
-__global__ void __launch_bounds__(32, 5)
+__global__ void __launch_bounds__(32, 16)
 rans_tile4_kernel(const uint8_t *__restrict__ in, const uint64_t *__restrict__ in_off,
                   const uint32_t *__restrict__ in_len, const uint32_t *__restrict__ list, const uint32_t *__restrict__ counts,
                   uint8_t *out, const uint64_t *__restrict__ out_off, const uint32_t *__restrict__ out_len,
@@ -610,6 +623,7 @@ rans_tile4_kernel(const uint8_t *__restrict__ in, const uint64_t *__restrict__ i
     ws.tblbuf = scratch + (size_t)blockIdx.x * scratch_per_cta;
     ws.max_out = max_out;
     ws.pass = 0; ws.defer = false; ws.hook = &hook;
+    ws.compact = true;                               // eight streams' tables share the pool
     const uint32_t n = counts[1];
     const uint32_t NONE = 0xffffffffu;
     uint32_t carry = NONE;
@@ -643,8 +657,8 @@ rans_tile4_kernel(const uint8_t *__restrict__ in, const uint64_t *__restrict__ i
                     Quad &Q = quads[nq];
                     Q.lut_a = (uint32_t)__cvta_generic_to_shared(hook.lut);
                     Q.fb_a = (uint32_t)__cvta_generic_to_shared(hook.fb);
-                    Q.mask = (1u << hook.shift) - 1u; Q.shift = hook.shift;
-                    Q.rowsz = hook.order ? 1u << hook.shift : 0u;
+                    Q.mask = (1u << hook.shift) - 1u; Q.shift = hook.shift; Q.cs = hook.shift - hook.lb;
+                    Q.rowsz = hook.order ? 1u << hook.lb : 0u;
                     Q.fstride = hook.order ? hook.ncol * 4u : 0u;
                     Q.ipos = hook.ipos; Q.in_len = hook.in_len; Q.U = hook.U; Q.order = hook.order; Q.job = job; Q.got = got;
                     Q.in = hook.in; Q.out = hook.out;

@@ -54,7 +54,7 @@ extern "C" uint32_t hgpu_tok3_out_bound(const uint8_t *in, uint32_t len)
     return ulen + 1024;
 }
 
-extern "C" int hgpu_tok3_decode_batch_host(hgpu_ctx *ctx, const uint8_t *in, const uint64_t *in_off,
+static int hgpu_tok3_decode_batch_host_impl(hgpu_ctx *ctx, const uint8_t *in, const uint64_t *in_off,
         const uint32_t *in_len, uint32_t n, uint8_t *out, const uint64_t *out_off, const uint32_t *out_cap,
         uint32_t *out_len, int32_t *status)
 {
@@ -250,6 +250,22 @@ extern "C" int hgpu_tok3_decode_batch_host(hgpu_ctx *ctx, const uint8_t *in, con
     cudaEventElapsedTime(&g_tok3_ms[0], tev[0], tev[1]);
     cudaEventElapsedTime(&g_tok3_ms[1], tev[1], tev[2]);
     return HGPU_OK;
+}
+
+// no C++ exception may cross the C ABI (host buffers are sized from untrusted input: std::bad_alloc)
+extern "C" int hgpu_tok3_decode_batch_host(hgpu_ctx *ctx, const uint8_t *in, const uint64_t *in_off,
+        const uint32_t *in_len, uint32_t n, uint8_t *out, const uint64_t *out_off, const uint32_t *out_cap,
+        uint32_t *out_len, int32_t *status)
+{
+    try {
+        return hgpu_tok3_decode_batch_host_impl(ctx, in, in_off, in_len, n, out, out_off, out_cap, out_len, status);
+    } catch (const std::bad_alloc &) {
+        hgpu_set_error("out of host memory");
+        return HGPU_ERR_NOMEM;
+    } catch (...) {
+        hgpu_set_error("internal error");
+        return HGPU_ERR_CUDA;
+    }
 }
 
 // device time of the last hgpu_tok3_decode_batch_host call: [0] token-stream entropy decode, [1] name rebuild

@@ -161,7 +161,7 @@ extern "C" uint32_t hgpu_tok3_compress_bound(uint32_t in_len)
     return b > 0xffffffffull ? 0xffffffffu : (uint32_t)b;
 }
 
-extern "C" int hgpu_tok3_encode_batch_host(hgpu_ctx *ctx, const uint8_t *in, const uint64_t *in_off, const uint32_t *in_len,
+static int hgpu_tok3_encode_batch_host_impl(hgpu_ctx *ctx, const uint8_t *in, const uint64_t *in_off, const uint32_t *in_len,
         uint32_t n, uint8_t *out, const uint64_t *out_off, const uint32_t *out_cap, uint32_t *out_len, int32_t *status)
 {
     if (!ctx || (n && (!in || !in_off || !in_len || !out || !out_off || !out_cap || !out_len || !status))) {
@@ -301,4 +301,19 @@ extern "C" int hgpu_tok3_encode_batch_host(hgpu_ctx *ctx, const uint8_t *in, con
     }
     for (uint32_t b = 0; b < n; b++) out_len[b] = status[b] == HGPU_OK ? wp[b] : 0;
     return HGPU_OK;
+}
+
+// no C++ exception may cross the C ABI (host buffers are sized from untrusted input: std::bad_alloc)
+extern "C" int hgpu_tok3_encode_batch_host(hgpu_ctx *ctx, const uint8_t *in, const uint64_t *in_off, const uint32_t *in_len,
+        uint32_t n, uint8_t *out, const uint64_t *out_off, const uint32_t *out_cap, uint32_t *out_len, int32_t *status)
+{
+    try {
+        return hgpu_tok3_encode_batch_host_impl(ctx, in, in_off, in_len, n, out, out_off, out_cap, out_len, status);
+    } catch (const std::bad_alloc &) {
+        hgpu_set_error("out of host memory");
+        return HGPU_ERR_NOMEM;
+    } catch (...) {
+        hgpu_set_error("internal error");
+        return HGPU_ERR_CUDA;
+    }
 }

@@ -114,6 +114,8 @@ int hgpu_bgzf_inflate_file_host(hgpu_ctx *ctx, const uint8_t *file, uint64_t fil
 
 /* CRC-32 of a host buffer computed on the device == hts_crc32 (bgzf.c:620-622, htslib.map:657) */
 uint32_t hgpu_crc32(hgpu_ctx *ctx, uint32_t crc, const void *buf, size_t len);
+/* 1 if the calling thread's last hgpu_crc32 failed (it then returned its crc argument unchanged and set hgpu_last_error) */
+int hgpu_crc32_failed(void);
 
 /* ------------------------------------------------------------------------------------------
  * rANS Nx16 ("RANS_PR", CRAM 3.1 block method 5) — replaces rans_uncompress_to_4x16
