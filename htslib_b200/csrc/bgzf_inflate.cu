@@ -630,6 +630,66 @@ constexpr uint32_t MREC_CAP = 65536 / 3 + 64;   // a match yields >= 3 bytes of 
 
 // Parallel decode of one Huffman block body starting at bit `body` of the member (bit 0 = first
 // bit of word wbase[0], i.e. positions include the alignment offset).  total = end of input.
+// A/B on B200 (tools/prof_inflate.py, profiles/r2_inflate_ab.txt): for the warp kernel the register-buffered bit reader
+// below beats the position-based branch-free walk of bgzf_huff.cuh (its two stream loads per symbol come from global
+// memory here, not from a staged copy), and 5 warps per CTA (20 per SM) are no faster than 4.  -DHGPU_NEW_WALK selects the other.
+#ifndef HGPU_NEW_WALK
+__device__ int decode_body_parallel(InflateSmem &s, const uint32_t *wbase, const uint32_t *wend, uint32_t body,
+                                    uint32_t total, uint8_t *out, uint32_t cap, uint32_t &o, uint2 *mrec,
+                                    uint32_t &end_pos, Prof &pf)
+{
+    const uint32_t lane = hgpu_lane();
+    const uint32_t S = (total - body + 31) / 32;
+    uint32_t start = body + lane * S;
+    uint32_t end = lane == 31 ? total : min(total, body + (lane + 1) * S);
+    if (start > total) start = total;
+    uint32_t exitp = 0, n = 0, m = 0, st = ST_RUN;
+    bool need = true, dummy = false;
+    for (int round = 0; round < 34; round++) {
+        if (need) lane_decode<0>(s, wbase, wend, start, end, exitp, n, m, st, nullptr, 0, nullptr, 0, dummy);
+        uint32_t prev = __shfl_up_sync(0xffffffffu, exitp, 1);
+        uint32_t ns = lane == 0 ? start : prev;
+        need = ns != start;
+        start = ns;
+        if (!__any_sync(0xffffffffu, need)) break;
+    }
+    pf.mark(1);
+    // the chain is now consistent: lane i starts where lane i-1 stopped
+    uint32_t eob = __ballot_sync(0xffffffffu, st == ST_EOB);
+    uint32_t bad = __ballot_sync(0xffffffffu, st == ST_BAD);
+    if (!eob) return HGPU_BGZF_ERR_ZLIB;                       // input ends without an end-of-block code
+    uint32_t E = __ffs(eob) - 1;
+    if (bad & ((2u << E) - 1u)) return HGPU_BGZF_ERR_ZLIB;     // invalid code at or before the end of block
+    uint32_t last = __shfl_sync(0xffffffffu, exitp, E);
+    if (last > total) return HGPU_BGZF_ERR_ZLIB;               // the block ran past the input
+    if (lane > E) { n = 0; m = 0; }
+    // exclusive prefix sums of bytes and matches
+    uint32_t on = n, mn = m;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        uint32_t a = __shfl_up_sync(0xffffffffu, on, d), c = __shfl_up_sync(0xffffffffu, mn, d);
+        if (lane >= (uint32_t)d) { on += a; mn += c; }
+    }
+    uint32_t tot_out = __shfl_sync(0xffffffffu, on, 31), tot_m = __shfl_sync(0xffffffffu, mn, 31);
+    if ((uint64_t)o + tot_out > cap) return HGPU_BGZF_ERR_SPACE;
+    if (tot_m > MREC_CAP) return HGPU_BGZF_ERR_ZLIB;           // impossible within 64 KiB of output
+    bool bad_dist = false;
+    if (lane <= E) {
+        uint32_t e2, n2, m2, st2;
+        lane_decode<1>(s, wbase, wend, start, end, e2, n2, m2, st2, out, o + on - n, mrec, mn - m, bad_dist);
+    }
+    if (__any_sync(0xffffffffu, bad_dist)) return HGPU_BGZF_ERR_ZLIB;   // distance too far back
+    __syncwarp();
+    __threadfence_block();
+    pf.mark(2);
+    run_matches(s, out, mrec, tot_m);
+    pf.mark(3);
+    o += tot_out;
+    end_pos = last;
+    return HGPU_OK;
+}
+
+#else
 __device__ int decode_body_parallel(InflateSmem &s, const uint32_t *wbase, const uint32_t *wend, uint32_t body,
                                     uint32_t total, uint8_t *out, uint32_t cap, uint32_t &o, uint2 *mrec,
                                     uint32_t &end_pos, Prof &pf)
@@ -701,6 +761,7 @@ __device__ int decode_body_parallel(InflateSmem &s, const uint32_t *wbase, const
     return HGPU_OK;
 }
 
+#endif
 // ---------------------------------------------------------------------------------------------
 // One BGZF member: headers + table construction are warp-uniform, bodies go to one of the two
 // decoders above.
@@ -837,7 +898,10 @@ __device__ int check_header(const uint8_t *h)
     return ((h[3] & 4) && (h[10] | h[11] << 8) == 6 && h[12] == 'B' && h[13] == 'C' && (h[14] | h[15] << 8) == 2) ? 0 : -1;
 }
 
-constexpr int INFLATE_WARPS = 5;      // warps per CTA; they share only the CRC tables (5 x 10 KB + 4 KB: four CTAs = 20 warps per SM)
+#ifndef HGPU_INFLATE_WARPS
+#define HGPU_INFLATE_WARPS 4
+#endif
+constexpr int INFLATE_WARPS = HGPU_INFLATE_WARPS;      // warps per CTA; they share only the CRC tables (4 x 10 KB + 4 KB: four CTAs = 16 warps per SM)
 
 #ifndef INFL_LB
 #define INFL_LB 4

@@ -2,6 +2,7 @@
 // include/htsgpu.h, the pipelined host-buffer paths and the reference-named shims.
 // No CPU fallback anywhere: without a usable CUDA device every entry point fails.
 #include "hgpu_internal.h"
+#include <algorithm>
 #include <atomic>
 #include <mutex>
 #include <stdarg.h>
@@ -294,7 +295,20 @@ static int hgpu_bgzf_inflate_blocks_host_impl(hgpu_ctx *ctx, const uint8_t *in, 
     if (hgpu_check(cudaMemcpyAsync(d_cap, out_cap, n * 4, cudaMemcpyHostToDevice, s), "H2D")) return HGPU_ERR_CUDA;
     rc = hgpu_launch_bgzf_inflate(ctx, d_in, d_ioff, d_ilen, n, d_out, d_ooff, d_cap, d_got, d_st, s);
     if (rc) return rc;
-    if (hgpu_check(cudaMemcpyAsync(out, d_out, out_end, cudaMemcpyDeviceToHost, s), "D2H")) return HGPU_ERR_CUDA;
+    // only the slots come back: runs of slots that touch (the usual 64 KiB stride is one run) are one copy each,
+    // and nothing of the caller's buffer outside the slots is written
+    {
+        std::vector<uint32_t> ord(n);
+        for (uint32_t i = 0; i < n; i++) ord[i] = i;
+        std::sort(ord.begin(), ord.end(), [&](uint32_t a, uint32_t b) { return out_off[a] < out_off[b]; });
+        uint64_t r0 = out_off[ord[0]], r1 = r0 + out_cap[ord[0]];
+        for (uint32_t k = 1; k <= n; k++) {
+            const bool more = k < n;
+            if (more && out_off[ord[k]] <= r1) { const uint64_t e = out_off[ord[k]] + out_cap[ord[k]]; if (e > r1) r1 = e; continue; }
+            if (r1 > r0 && hgpu_check(cudaMemcpyAsync(out + r0, d_out + r0, r1 - r0, cudaMemcpyDeviceToHost, s), "D2H")) return HGPU_ERR_CUDA;
+            if (more) { r0 = out_off[ord[k]]; r1 = r0 + out_cap[ord[k]]; }
+        }
+    }
     std::vector<uint32_t> got(n);
     std::vector<int32_t> st(n);
     if (hgpu_check(cudaMemcpyAsync(got.data(), d_got, n * 4, cudaMemcpyDeviceToHost, s), "D2H")) return HGPU_ERR_CUDA;
@@ -496,7 +510,20 @@ static int hgpu_rans_nx16_decode_batch_host_impl(hgpu_ctx *ctx, const uint8_t *i
     if (hgpu_check(cudaMemcpyAsync(d_olen, out_len, n * 4, cudaMemcpyHostToDevice, s), "H2D")) return HGPU_ERR_CUDA;
     rc = hgpu_launch_rans_nx16(ctx, d_in, d_ioff, d_ilen, n, d_out, d_ooff, d_olen, d_got, d_st, max_out, s);
     if (rc) return rc;
-    if (hgpu_check(cudaMemcpyAsync(out, d_out, out_end, cudaMemcpyDeviceToHost, s), "D2H")) return HGPU_ERR_CUDA;
+    // only the slots come back, in runs: slots that touch, or are separated by alignment padding (< 16 bytes, which
+    // may be overwritten), travel in one copy
+    {
+        std::vector<uint32_t> ord(n);
+        for (uint32_t i = 0; i < n; i++) ord[i] = i;
+        std::sort(ord.begin(), ord.end(), [&](uint32_t a, uint32_t b) { return out_off[a] < out_off[b]; });
+        uint64_t r0 = out_off[ord[0]], r1 = r0 + out_len[ord[0]];
+        for (uint32_t k = 1; k <= n; k++) {
+            const bool more = k < n;
+            if (more && out_off[ord[k]] < r1 + 16) { const uint64_t e = out_off[ord[k]] + out_len[ord[k]]; if (e > r1) r1 = e; continue; }
+            if (r1 > r0 && hgpu_check(cudaMemcpyAsync(out + r0, d_out + r0, r1 - r0, cudaMemcpyDeviceToHost, s), "D2H")) return HGPU_ERR_CUDA;
+            if (more) { r0 = out_off[ord[k]]; r1 = r0 + out_len[ord[k]]; }
+        }
+    }
     std::vector<uint32_t> got(n);
     std::vector<int32_t> st(n);
     if (hgpu_check(cudaMemcpyAsync(got.data(), d_got, n * 4, cudaMemcpyDeviceToHost, s), "D2H")) return HGPU_ERR_CUDA;
