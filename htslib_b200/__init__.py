@@ -269,6 +269,29 @@ class Context:
                                     seq_off.data_ptr(), status.data_ptr(), stream), "bam_unpack")
         return dict(n=n, rec_off=rec_off, core=core, data=data, data_off=data_off, seq=seq, qual=qual, seq_off=seq_off, status=status)
 
+    def sam_format_dev(self, core, data, data_off, n, target_names, stream=0):
+        """SAM text lines (sam_format1 + newline) of n unpacked records on the device (hgpu_sam_format_dev).
+        target_names: list of bytes (the header's @SQ names).  Returns (text uint8 tensor, out_off int64[n+1], status)."""
+        import numpy as np
+        import torch
+        dev = core.device
+        L = lib()
+        L.hgpu_sam_format_dev.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p, C.c_int32,
+                                          C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+        blob = b"".join(target_names) + b"\0"
+        noff = np.concatenate([[0], np.cumsum([len(x) for x in target_names])]).astype(np.int64)
+        d_names = torch.from_numpy(np.frombuffer(blob, dtype=np.uint8).copy()).to(dev)
+        d_noff = torch.from_numpy(noff).to(dev)
+        out_off = torch.empty(n + 1, dtype=torch.int64, device=dev)
+        status = torch.zeros(max(1, n), dtype=torch.int32, device=dev)
+        args = (self.h, core.data_ptr(), data.data_ptr(), data_off.data_ptr(), n, d_names.data_ptr(), d_noff.data_ptr(), len(target_names))
+        check(L.hgpu_sam_format_dev(*args, None, out_off.data_ptr(), status.data_ptr(), stream), "sam_format(layout)")
+        torch.cuda.synchronize()
+        total = int(out_off[n].item())
+        out = torch.empty(max(1, total), dtype=torch.uint8, device=dev)
+        check(L.hgpu_sam_format_dev(*args, out.data_ptr(), out_off.data_ptr(), None, stream), "sam_format")
+        return out[:total], out_off, status
+
     def bam_pack_dev(self, core, data, data_off, n, stream=0):
         """bam_write1 data movement on the device: returns (out uint8 tensor, out_off int64[n+1], status)."""
         import torch

@@ -461,3 +461,156 @@ extern "C" int hgpu_bam_pack_dev(hgpu_ctx *ctx, const hgpu_bam1_core *d_core, co
     hgpu_count_launch();
     return hgpu_check(cudaGetLastError(), "bam pack launch");
 }
+
+// =============================================================================================
+// SAM text — sam_format1_append (sam.c:4324-4404) + the '\n' sam_write1 adds, for n unpacked records.
+// One walker per record formats into `out` at the record's offset; the same walker run with a null
+// sink is the size pass (its sizes are prefix-summed into out_off).  Fields exactly as the
+// reference prints them: QNAME (without the padding NULs), FLAG, RNAME / '*', POS+1, MAPQ,
+// CIGAR ("<len><op>" per operation, BAM_CIGAR_STR "MIDNSHP=XB??????", or '*'), RNEXT ('*', '=' or the
+// name), PNEXT+1, TLEN, SEQ (seq_nt16_str "=ACMGRSVTWYHKDBN", high nibble first, sam_internal.h:63-118)
+// or '*', QUAL+33 or '*' when qual[0] == 0xff (sam.c:4370), then the aux fields TAG:TYPE:VALUE
+// (sam_format_aux1, htslib/sam.h:1463-1630): A, c/C/s/S/i/I -> 'i', Z, H, B arrays of integers.
+// Floating-point values ('f', 'd', B:f) are printed by the reference with printf("%g") / kputd;
+// records that carry one are flagged status 1 and left to the host (zero bytes), so is a record
+// with corrupted aux data (status -1, the reference returns -1 there).
+// =============================================================================================
+namespace {
+
+struct Sink {
+    uint8_t *p;            // null: count only
+    uint64_t n;
+    __device__ __forceinline__ void put(uint32_t c) { if (p) p[n] = (uint8_t)c; n++; }
+    __device__ __forceinline__ void puts(const uint8_t *s, uint32_t l) { if (p) for (uint32_t i = 0; i < l; i++) p[n + i] = s[i]; n += l; }
+    __device__ void putu(uint64_t v)
+    {
+        uint8_t b[20];
+        int k = 0;
+        do { b[k++] = (uint8_t)('0' + v % 10); v /= 10; } while (v);
+        if (p) for (int i = 0; i < k; i++) p[n + i] = b[k - 1 - i];
+        n += k;
+    }
+    __device__ void puti(int64_t v) { if (v < 0) { put('-'); putu((uint64_t)0 - (uint64_t)v); } else putu((uint64_t)v); }
+};
+
+__device__ int sam_format_record(const hgpu_bam1_core &c, const uint8_t *d, uint32_t l_data, const uint8_t *names,
+                                 const uint64_t *name_off, int32_t n_targets, Sink &o)
+{
+    if (c.l_qname == 0) return -1;
+    const uint32_t cig_off = c.l_qname, seq_off = cig_off + 4u * c.n_cigar, qual_off = seq_off + ((uint32_t)c.l_qseq + 1u) / 2u,
+                   aux_off = qual_off + (uint32_t)c.l_qseq;
+    if (c.l_qseq < 0 || aux_off > l_data || c.tid >= n_targets || c.mtid >= n_targets) return -1;
+    o.puts(d, (uint32_t)c.l_qname - 1u - c.l_extranul); o.put('\t');
+    o.putu(c.flag); o.put('\t');
+    if (c.tid >= 0) { o.puts(names + name_off[c.tid], (uint32_t)(name_off[c.tid + 1] - name_off[c.tid])); o.put('\t'); }
+    else { o.put('*'); o.put('\t'); }
+    o.puti(c.pos + 1); o.put('\t');
+    o.putu(c.qual); o.put('\t');
+    if (c.n_cigar) {
+        for (uint32_t i = 0; i < c.n_cigar; i++) {
+            const uint8_t *q = d + cig_off + 4u * i;
+            const uint32_t v = q[0] | q[1] << 8 | q[2] << 16 | (uint32_t)q[3] << 24;
+            o.putu(v >> 4);
+            o.put("MIDNSHP=XB??????"[v & 15]);
+        }
+    } else o.put('*');
+    o.put('\t');
+    if (c.mtid < 0) { o.put('*'); o.put('\t'); }
+    else if (c.mtid == c.tid) { o.put('='); o.put('\t'); }
+    else { o.puts(names + name_off[c.mtid], (uint32_t)(name_off[c.mtid + 1] - name_off[c.mtid])); o.put('\t'); }
+    o.puti(c.mpos + 1); o.put('\t');
+    o.puti(c.isize); o.put('\t');
+    if (c.l_qseq) {
+        const uint8_t *s = d + seq_off, *q = d + qual_off;
+        if (o.p) for (int32_t i = 0; i < c.l_qseq; i++) o.p[o.n + i] = "=ACMGRSVTWYHKDBN"[(s[i >> 1] >> ((~i & 1) << 2)) & 15];
+        o.n += (uint32_t)c.l_qseq;
+        o.put('\t');
+        if (q[0] == 0xff) o.put('*');
+        else { if (o.p) for (int32_t i = 0; i < c.l_qseq; i++) o.p[o.n + i] = (uint8_t)(q[i] + 33); o.n += (uint32_t)c.l_qseq; }
+    } else { o.put('*'); o.put('\t'); o.put('*'); }
+    const uint8_t *s = d + aux_off, *end = d + l_data;
+    while (end - s >= 4) {
+        o.put('\t');
+        o.put(s[0]); o.put(s[1]); o.put(':');
+        const uint8_t type = s[2];
+        s += 3;
+        auto le = [&](int nb) { uint64_t v = 0; for (int k = 0; k < nb; k++) v |= (uint64_t)s[k] << (8 * k); return v; };
+        if (type == 'C') { o.put('i'); o.put(':'); o.putu(s[0]); s += 1; }
+        else if (type == 'c') { o.put('i'); o.put(':'); o.puti((int8_t)s[0]); s += 1; }
+        else if (type == 'S') { if (end - s < 2) return -1; o.put('i'); o.put(':'); o.putu(le(2)); s += 2; }
+        else if (type == 's') { if (end - s < 2) return -1; o.put('i'); o.put(':'); o.puti((int16_t)le(2)); s += 2; }
+        else if (type == 'I') { if (end - s < 4) return -1; o.put('i'); o.put(':'); o.putu(le(4)); s += 4; }
+        else if (type == 'i') { if (end - s < 4) return -1; o.put('i'); o.put(':'); o.puti((int32_t)le(4)); s += 4; }
+        else if (type == 'A') { o.put('A'); o.put(':'); o.put(s[0]); s += 1; }
+        else if (type == 'f' || type == 'd') return 1;
+        else if (type == 'Z' || type == 'H') {
+            o.put(type); o.put(':');
+            while (s < end && *s) o.put(*s++);
+            if (s >= end) return -1;
+            s++;
+        } else if (type == 'B') {
+            const uint8_t sub = *s++;
+            int sz = (sub == 'A' || sub == 'c' || sub == 'C') ? 1 : (sub == 's' || sub == 'S') ? 2 : (sub == 'i' || sub == 'I' || sub == 'f') ? 4 : 0;
+            if (sz == 0 || end - s < 4) return -1;
+            const uint32_t cnt = (uint32_t)le(4);
+            s += 4;
+            if ((size_t)(end - s) / (size_t)sz < cnt) return -1;
+            if (sub == 'f') return 1;
+            if (sub == 'A') return -1;                               // sam_format_aux1's second switch has no 'A'
+            o.put('B'); o.put(':'); o.put(sub);
+            for (uint32_t i = 0; i < cnt; i++) {
+                o.put(',');
+                const uint64_t v = le(sz);
+                if (sub == 'c') o.puti((int8_t)v); else if (sub == 's') o.puti((int16_t)v); else if (sub == 'i') o.puti((int32_t)v); else o.putu(v);
+                s += sz;
+            }
+        } else return -1;
+    }
+    o.put('\n');
+    return 0;
+}
+
+__global__ void sam_format_kernel(const hgpu_bam1_core *core, const uint8_t *data, const uint64_t *data_off, uint64_t n,
+                                  const uint8_t *names, const uint64_t *name_off, int32_t n_targets,
+                                  uint8_t *out, uint64_t *out_off, uint64_t *dummy, int32_t *status)
+{
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i > n) return;
+    if (i == n) { if (!out) { out_off[n] = 0; dummy[n] = 0; } return; }
+    const hgpu_bam1_core c = core[i];
+    const uint32_t l_data = (uint32_t)(data_off[i + 1] - data_off[i]);
+    Sink o;
+    o.p = out ? out + out_off[i] : nullptr;
+    o.n = 0;
+    if (out && out_off[i + 1] == out_off[i]) return;                 // flagged by the size pass: no bytes
+    const int rc = sam_format_record(c, data + data_off[i], l_data, names, name_off, n_targets, o);
+    if (!out) { out_off[i] = rc == 0 ? o.n : 0; dummy[i] = 0; if (status) status[i] = rc; }
+}
+
+}  // namespace
+
+// d_out == NULL: fills d_out_off[0..n] (exclusive prefix sums of the line lengths; total = last entry) and d_status.
+// d_out != NULL: writes the lines.  d_names / d_name_off[0..n_targets]: the @SQ names of the header, back to back.
+extern "C" int hgpu_sam_format_dev(hgpu_ctx *ctx, const hgpu_bam1_core *d_core, const uint8_t *d_data, const uint64_t *d_data_off,
+                                   uint64_t n, const uint8_t *d_names, const uint64_t *d_name_off, int32_t n_targets,
+                                   uint8_t *d_out, uint64_t *d_out_off, int32_t *d_status, void *stream)
+{
+    if (!ctx || !d_core || !d_data || !d_data_off || !d_out_off || (n_targets > 0 && (!d_names || !d_name_off))) { hgpu_set_error("bad argument"); return HGPU_ERR_ARG; }
+    cudaStream_t st = stream ? (cudaStream_t)stream : ctx->stream;
+    const uint64_t m = n + 1, nt = (m + TILE - 1) / TILE;
+    if (!d_out) {
+        int rc = hgpu_ensure_bam(ctx, (nt * 2 + m) * sizeof(uint64_t) + 64);
+        if (rc) return rc;
+        uint64_t *ta = (uint64_t *)ctx->d_bam, *tb = ta + nt, *dummy = tb + nt;
+        sam_format_kernel<<<(unsigned)((m + 127) / 128), 128, 0, st>>>(d_core, d_data, d_data_off, n, d_names, d_name_off, n_targets, nullptr, d_out_off, dummy, d_status);
+        scan_tiles_reduce<<<(unsigned)nt, 256, 0, st>>>(d_out_off, dummy, m, ta, tb);
+        scan_tile_sums<<<1, 1024, 0, st>>>(ta, tb, nt);
+        scan_tiles_apply<<<(unsigned)nt, 256, 0, st>>>(d_out_off, dummy, m, ta, tb);
+        hgpu_count_launch(4);
+        return hgpu_check(cudaGetLastError(), "sam format layout launch");
+    }
+    if (n == 0) return HGPU_OK;
+    sam_format_kernel<<<(unsigned)((m + 127) / 128), 128, 0, st>>>(d_core, d_data, d_data_off, n, d_names, d_name_off, n_targets, d_out, d_out_off, nullptr, nullptr);
+    hgpu_count_launch();
+    return hgpu_check(cudaGetLastError(), "sam format launch");
+}

@@ -49,6 +49,9 @@ static int grow(uint8_t **p, size_t *cap, size_t want, bool pinned)
     cudaError_t e = pinned ? cudaMallocHost((void **)p, ncap) : cudaMalloc((void **)p, ncap);
     if (e != cudaSuccess) { hgpu_set_error("alloc of %zu bytes failed: %s", ncap, cudaGetErrorString(e)); cudaGetLastError(); return HGPU_ERR_NOMEM; }
     *cap = ncap;
+    // HGPU_POISON=1 (tests): fill fresh buffers with a pattern so that a read of bytes nobody wrote shows up as a wrong result
+    static const bool poison = getenv("HGPU_POISON") && getenv("HGPU_POISON")[0] == '1';
+    if (poison && !pinned) cudaMemset(*p, 0xCD, ncap);
     return HGPU_OK;
 }
 int hgpu_ensure_scratch(hgpu_ctx *c, size_t b) { return grow(&c->d_scratch, &c->d_scratch_cap, b, false); }
@@ -147,6 +150,59 @@ extern "C" long hgpu_bgzf_scan(const uint8_t *file, uint64_t flen, uint64_t *off
         p += bl;
     }
     return n;
+}
+
+// ---- .gzi / uncompressed-offset <-> virtual-offset arithmetic over a scanned file (bgzf.c:2336-2621) ----
+// The GPU paths deliver a file's blocks packed back to back, so "where is uncompressed byte u" is index
+// arithmetic over the scan table: the same table bgzf_index_build_init / bgzf_index_add_block keep and
+// bgzf_index_dump writes (one {compressed address, uncompressed address} pair per block start but the first).
+// terminating = 1: the table a READER builds (bgzf_index_build_init + reading to the end, `bgzip -r`): every block start
+// but the first, the EOF marker's included ("one extra record when indexing files opened for reading", :2387-2389).
+// terminating = 0: the table a WRITER builds (`bgzip -i`, bgzf_flush :1976-1979): one pair per non-empty block it wrote.
+extern "C" long hgpu_bgzf_gzi_entries(const uint64_t *off, const uint32_t *isize, long n, int terminating,
+                                      uint64_t *caddr, uint64_t *uaddr, long cap)
+{
+    if (n < 0 || (n && (!off || !isize))) { hgpu_set_error("bad argument"); return -1; }
+    uint64_t u = 0;
+    long k = 0;
+    for (long i = 0; i < n; i++) {
+        if (i > 0 && (terminating || isize[i])) { if (k < cap) { if (caddr) caddr[k] = off[i]; if (uaddr) uaddr[k] = u; } k++; }
+        u += isize[i];
+    }
+    return k;
+}
+
+// serialised form (bgzf_index_dump_hfile :2385-2415): u64 count, then count x {u64 caddr, u64 uaddr}, little endian
+extern "C" long hgpu_bgzf_gzi_dump(const uint64_t *caddr, const uint64_t *uaddr, long n, uint8_t *out, size_t cap)
+{
+    const size_t need = 8 + (size_t)n * 16;
+    if (n < 0 || (n && (!caddr || !uaddr))) { hgpu_set_error("bad argument"); return -1; }
+    if (!out || cap < need) return (long)need;
+    auto put = [&](size_t at, uint64_t v) { for (int b = 0; b < 8; b++) out[at + b] = (uint8_t)(v >> (8 * b)); };
+    put(0, (uint64_t)n);
+    for (long i = 0; i < n; i++) { put(8 + (size_t)i * 16, caddr[i]); put(16 + (size_t)i * 16, uaddr[i]); }
+    return (long)need;
+}
+
+// bgzf_useek (:2540-2608): the virtual offset (block address << 16 | offset in the block) of uncompressed offset u.
+// The block is the last one whose uncompressed address is <= u (entry -1 = the first block at {0, 0}).
+extern "C" uint64_t hgpu_bgzf_useek(const uint64_t *caddr, const uint64_t *uaddr, long n, uint64_t u)
+{
+    long lo = 0, hi = n - 1;                                  // first entry with uaddr > u
+    while (lo <= hi) { long mid = (lo + hi) / 2; if (u < uaddr[mid]) hi = mid - 1; else lo = mid + 1; }
+    const long i = lo - 1;                                    // -1: the first block
+    const uint64_t ca = i < 0 ? 0 : caddr[i], ua = i < 0 ? 0 : uaddr[i];
+    return ca << 16 | ((u - ua) & 0xffffu);
+}
+
+// the inverse: uncompressed offset of a virtual offset, or (uint64)-1 if its block address is not a block start
+extern "C" uint64_t hgpu_bgzf_utell(const uint64_t *caddr, const uint64_t *uaddr, long n, uint64_t voffset)
+{
+    const uint64_t ca = voffset >> 16;
+    if (ca == 0) return voffset & 0xffffu;
+    long lo = 0, hi = n - 1;
+    while (lo <= hi) { long mid = (lo + hi) / 2; if (caddr[mid] < ca) lo = mid + 1; else if (caddr[mid] > ca) hi = mid - 1; else return uaddr[mid] + (voffset & 0xffffu); }
+    return ~0ull;
 }
 
 // Pipelined whole-file inflate with host buffers.  Chunks of blocks flow through three streams

@@ -530,9 +530,31 @@ struct Quad {
     uint8_t *out;
     uint32_t R[4];
 };
-constexpr uint32_t T4_POOL = 8192, T4_QUADS = SM_TAB + T4_POOL, T4_SMEM = T4_QUADS + 8 * sizeof(Quad);      // compact tables: eight streams' worth
+constexpr uint32_t T4_POOL = 8192, T4_QUADS = SM_TAB + T4_POOL;                  // compact tables: eight streams' worth
+constexpr uint32_t T4_RING = 256;                                                // per quad: a window of its word stream, ring[off & 255] = stream byte off
+constexpr uint32_t T4_RINGS = (T4_QUADS + 8 * (uint32_t)sizeof(Quad) + 15u) & ~15u, T4_SMEM = T4_RINGS + 8 * T4_RING;
 
-__device__ __forceinline__ void renorm_quad(uint32_t &R, bool act, const uint8_t *in, uint32_t &ipos, uint32_t in_len,
+// The renormalisation words of a quad come from its 256-byte ring (a global round trip per step at 16 warps per SM was
+// what bounded this kernel: 9.9 ms for the small blocks of 13 000 slices).  refill: lane z of the quad brings the 16
+// stream bytes at loaded + 16 z (aligned words, funnel-shifted), 64 bytes per quad and call.
+__device__ __forceinline__ void quad_refill(uint32_t ring_a, const uint8_t *in, uint32_t in_len, uint32_t &loaded, uint32_t z, bool go)
+{
+    if (go) {
+        const uint32_t off = loaded + 16u * z;
+        const uintptr_t g = reinterpret_cast<uintptr_t>(in) + off, ga = g & ~(uintptr_t)3;
+        const uintptr_t lim = (reinterpret_cast<uintptr_t>(in) + in_len + 3) & ~(uintptr_t)3;
+        const uint32_t sh = (uint32_t)(g & 3) * 8u;
+        uint32_t w[5];
+#pragma unroll
+        for (int k = 0; k < 5; k++) w[k] = ga + 4u * k < lim ? *reinterpret_cast<const uint32_t *>(ga + 4u * k) : 0u;
+        const uint32_t ra = ring_a + (off & (T4_RING - 1u));
+        asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" :: "r"(ra), "r"(__funnelshift_r(w[0], w[1], sh)), "r"(__funnelshift_r(w[1], w[2], sh)),
+                     "r"(__funnelshift_r(w[2], w[3], sh)), "r"(__funnelshift_r(w[3], w[4], sh)) : "memory");
+        loaded += 64u;
+    }
+}
+
+__device__ __forceinline__ void renorm_quad(uint32_t &R, bool act, uint32_t ring_a, uint32_t &ipos, uint32_t in_len,
                                             uint32_t qsh, uint32_t zlt)
 {
     bool need = act && R < RANS_L;
@@ -540,13 +562,15 @@ __device__ __forceinline__ void renorm_quad(uint32_t &R, bool act, const uint8_t
     if (bal) {
         uint32_t wpos = ipos + 2u * __popc((bal >> qsh) & zlt);
         bool ok = need && wpos + 2u <= in_len;
-        if (ok) R = (R << 16) | in[wpos] | (uint32_t)in[wpos + 1] << 8;
+        // two byte reads: the word stream starts at any byte offset, so a word may wrap around the ring's end
+        const uint32_t w = lds_u8(ring_a + (wpos & (T4_RING - 1u))) | lds_u8(ring_a + ((wpos + 1u) & (T4_RING - 1u))) << 8;
+        if (ok) R = (R << 16) | w;
         uint32_t bok = __ballot_sync(0xffffffffu, ok);
         ipos += 2u * __popc((bok >> qsh) & 15u);
     }
 }
 
-__device__ void tile4_run(const Quad *quads, uint32_t nq, uint32_t idle_a)
+__device__ void tile4_run(const Quad *quads, uint32_t nq, uint32_t idle_a, uint32_t rings_a)
 {
     const uint32_t lane = hgpu_lane(), q = lane >> 2, z = lane & 3, qsh = lane & 28u, zlt = (1u << z) - 1u;
     const bool live = q < nq;
@@ -563,8 +587,16 @@ __device__ void tile4_run(const Quad *quads, uint32_t nq, uint32_t idle_a)
 #pragma unroll
     for (int d = 16; d; d >>= 1) maxsteps = max(maxsteps, __shfl_xor_sync(0xffffffffu, maxsteps, d));
     uint32_t lrow = 0, frow = 0;
+    const uint32_t ring_a = rings_a + q * T4_RING;
+    uint32_t loaded = ipos & ~15u;                           // the ring holds stream bytes [loaded - 256, loaded)
+    for (int f = 0; f < 3; f++) quad_refill(ring_a, in, in_len, loaded, z, live);
+    __syncwarp();
     for (uint32_t i = 0; i < maxsteps; i++) {
         const bool act = i < nsteps;
+        {   // a step takes at most 8 bytes: keep 72 ahead (never more than 136 held)
+            const bool fill = live && loaded - ipos < 72u;
+            if (__any_sync(0xffffffffu, fill)) { quad_refill(ring_a, in, in_len, loaded, z, fill); __syncwarp(); }
+        }
         uint32_t m = R & mask;
         uint32_t k = lds_u8(lut_a + lrow + (m >> cs));
         uint32_t e = lds_u32(fb_a + frow + k * 4u);
@@ -579,7 +611,7 @@ __device__ void tile4_run(const Quad *quads, uint32_t nq, uint32_t idle_a)
             op[(size_t)i * istride] = (uint8_t)e;
             lrow = k * rowsz; frow = k * fstride;
         }
-        renorm_quad(R, act, in, ipos, in_len, qsh, zlt);
+        renorm_quad(R, act, ring_a, ipos, in_len, qsh, zlt);
     }
     // tails: order 0 — the first U mod 4 states give one more symbol (rANS_static4x16pr.c:320-327);
     //        order 1 — the last state runs on for U mod 4 symbols (:760-790)
@@ -600,7 +632,7 @@ __device__ void tile4_run(const Quad *quads, uint32_t nq, uint32_t idle_a)
             Q.out[order ? (size_t)4 * nsteps + t : (size_t)4 * nsteps + z] = (uint8_t)e;
             lrow = k * rowsz; frow = k * fstride;
         }
-        renorm_quad(R, act, in, ipos, in_len, qsh, zlt);
+        renorm_quad(R, act, ring_a, ipos, in_len, qsh, zlt);
     }
     __syncwarp();
 }
@@ -676,7 +708,7 @@ rans_tile4_kernel(const uint8_t *__restrict__ in, const uint64_t *__restrict__ i
             continue;
         }
         __syncwarp();
-        tile4_run(quads, nq, (uint32_t)__cvta_generic_to_shared(smem + SM_TAB));
+        tile4_run(quads, nq, (uint32_t)__cvta_generic_to_shared(smem + SM_TAB), (uint32_t)__cvta_generic_to_shared(smem + T4_RINGS));
         if (lane < nq) { status[quads[lane].job] = HGPU_OK; got_len[quads[lane].job] = quads[lane].got; }
         __syncwarp();
     }

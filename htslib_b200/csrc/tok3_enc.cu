@@ -234,11 +234,11 @@ static int hgpu_tok3_encode_batch_host_impl(hgpu_ctx *ctx, const uint8_t *in, co
                    o_jord = o_jil + up((uint64_t)nj * 4), o_jcap = o_jord + up((uint64_t)nj * 4), o_jlen = o_jcap + up((uint64_t)nj * 4),
                    o_jst = o_jlen + up((uint64_t)nj * 4), o_comp = o_jst + up((uint64_t)nj * 4), total = o_comp + up(comp_bytes + 64);
     // growing the staging buffer would move it: the arena must be rebuilt by pass 1 anyway, but the input has to be re-uploaded
-    const uint8_t *before = ctx->d_stage;
+    const size_t cap_before = ctx->d_stage_cap;      // (a re-allocation may land on the same address: compare capacities, not pointers)
     rc = hgpu_ensure_stage(ctx, total + 4096);
     if (rc) return rc;
     base = ctx->d_stage;
-    if (base != before) {
+    if (ctx->d_stage_cap != cap_before) {
         if (hgpu_check(cudaMemcpyAsync(base + o_in, in, in_end, cudaMemcpyHostToDevice, s), "H2D")) return HGPU_ERR_CUDA;
         if (hgpu_check(cudaMemcpyAsync(base + o_ioff, in_off, (size_t)n * 8, cudaMemcpyHostToDevice, s), "H2D")) return HGPU_ERR_CUDA;
         if (hgpu_check(cudaMemcpyAsync(base + o_ilen, in_len, (size_t)n * 4, cudaMemcpyHostToDevice, s), "H2D")) return HGPU_ERR_CUDA;

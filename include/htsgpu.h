@@ -104,6 +104,20 @@ int hgpu_shard_range(uint64_t n_units, const uint32_t *unit_out_len, int world, 
 long hgpu_bgzf_scan(const uint8_t *file, uint64_t file_len,
                     uint64_t *off, uint32_t *len, uint32_t *isize, long cap);
 
+/* .gzi / uncompressed-offset <-> virtual-offset arithmetic over a scanned file (bgzf_index_build_init,
+ * bgzf_index_add_block, bgzf_index_dump, bgzf_useek, bgzf_utell: bgzf.c:2336-2621).  The batch paths return a
+ * file's payloads packed back to back; these give the index the reference keeps per block.
+ * hgpu_bgzf_gzi_entries: off/isize from hgpu_bgzf_scan (every block of the file, the EOF block included) ->
+ *   {caddr, uaddr} pairs; terminating = 1: the table a reader builds (`bgzip -r`: every block start but the first, the EOF
+ *   marker's included), 0: the table a writer builds (`bgzip -i`: one pair per non-empty block but the first); returns the count.
+ * hgpu_bgzf_gzi_dump: the .gzi byte image (u64 count + pairs, little endian); returns its size (also when out is NULL / too small).
+ * hgpu_bgzf_useek: virtual offset (block address << 16 | offset) of uncompressed offset u; hgpu_bgzf_utell: the inverse
+ *   ((uint64)-1 when the block address is not a block start). */
+long hgpu_bgzf_gzi_entries(const uint64_t *off, const uint32_t *isize, long n, int terminating, uint64_t *caddr, uint64_t *uaddr, long cap);
+long hgpu_bgzf_gzi_dump(const uint64_t *caddr, const uint64_t *uaddr, long n, uint8_t *out, size_t cap);
+uint64_t hgpu_bgzf_useek(const uint64_t *caddr, const uint64_t *uaddr, long n, uint64_t u);
+uint64_t hgpu_bgzf_utell(const uint64_t *caddr, const uint64_t *uaddr, long n, uint64_t voffset);
+
 /* Whole-file-image inflate with HOST buffers: scan + H2D + kernel + D2H, pipelined in chunks.
  * out must hold out_cap bytes; *out_len receives the total.  Blocks are packed back to back in
  * `out` in file order (what bgzf_read would deliver).  Returns HGPU_OK, or the first failing
@@ -195,6 +209,14 @@ typedef struct hgpu_cram_block {
 } hgpu_cram_block;
 long hgpu_cram_scan_blocks(const uint8_t *file, uint64_t len, hgpu_cram_block *blocks, long cap,
                            int *major, int *minor);
+
+/* cram_write_block (cram/cram_io.c:1511-1563) for a batch of blocks: method, content type, ITF8 content id / sizes,
+ * payload, and the CRC-32 over header + payload, the CRCs of all blocks from one device launch.  blocks[i]: method,
+ * content_type, content_id, comp_size, uncomp_size are read (a RAW block carries uncomp_size bytes); payload[i] -> its
+ * bytes (host).  The blocks are written back to back into out; out_off[i] (may be NULL) = where block i starts,
+ * *out_len = total.  HGPU_ERR_NOMEM with *out_len = the bytes needed when cap is too small. */
+int hgpu_cram_write_blocks_host(hgpu_ctx *ctx, const hgpu_cram_block *blocks, const uint8_t *const *payload, uint32_t n,
+                                uint8_t *out, uint64_t cap, uint64_t *out_off, uint64_t *out_len);
 
 /* CRAM 3.x compression header on the host: the record and tag encoding maps of a container
  * (cram_decode_compression_header, cram/cram_decode.c:144-538, and the *_decode_init parsers of
@@ -386,6 +408,17 @@ int hgpu_bam_unpack_dev(hgpu_ctx *ctx, const uint8_t *d_stream, uint64_t len,
 int hgpu_bam_pack_dev(hgpu_ctx *ctx, const hgpu_bam1_core *d_core, const uint8_t *d_data,
                       const uint64_t *d_data_off, uint64_t n, uint8_t *d_out, uint64_t *d_out_off,
                       int32_t *d_status, void *stream);
+
+/* SAM text of n unpacked records — sam_format1_append (sam.c:4324-4404) + the newline sam_write1 adds.
+ * core / data / data_off: what hgpu_bam_unpack_dev produced.  d_names + d_name_off[0..n_targets]: the header's
+ * @SQ names back to back (h->target_name[tid]).  Two calls, like hgpu_bam_pack_dev: with d_out == NULL it fills
+ * d_out_off[0..n] (exclusive prefix sums of the line lengths; the total is the last entry) and d_status; with
+ * d_out it writes the lines.  status[i]: 0; 1 when the record carries a floating-point aux value ('f', 'd',
+ * B:f — printed by printf("%g") / kputd in the reference; left to the host, zero bytes); -1 for what makes
+ * the reference return -1 (l_qname == 0, corrupted aux data). */
+int hgpu_sam_format_dev(hgpu_ctx *ctx, const hgpu_bam1_core *d_core, const uint8_t *d_data, const uint64_t *d_data_off,
+                        uint64_t n, const uint8_t *d_names, const uint64_t *d_name_off, int32_t n_targets,
+                        uint8_t *d_out, uint64_t *d_out_off, int32_t *d_status, void *stream);
 
 /* Sizes pass for step 2: fills d_data_off[0..n] and d_seq_off[0..n] (exclusive prefix sums of
  * l_data and l_qseq) so the caller can allocate; totals are the last entries. */

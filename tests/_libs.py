@@ -255,6 +255,53 @@ def ref_bam_read_all(img):
     return out
 
 
+class KString(C.Structure):       # kstring_t, htslib/kstring.h
+    _fields_ = [("l", C.c_size_t), ("m", C.c_size_t), ("s", C.c_void_p)]
+
+
+def ref_sam_format_all(img):
+    """Every record of a BGZF BAM image through the compiled reference's bam_read1 + sam_format1.
+    Returns (target names, [line bytes or None when sam_format1 fails])."""
+    r = ref()
+    r.hopen.restype = C.c_void_p
+    r.hopen.argtypes = [C.c_char_p, C.c_char_p, C.c_void_p, C.c_size_t]
+    r.bgzf_hopen.restype = C.c_void_p
+    r.bgzf_hopen.argtypes = [C.c_void_p, C.c_char_p]
+    r.bgzf_close.argtypes = [C.c_void_p]
+    r.bam_hdr_read.restype = C.c_void_p
+    r.bam_hdr_read.argtypes = [C.c_void_p]
+    r.sam_hdr_destroy.argtypes = [C.c_void_p]
+    r.sam_hdr_nref.argtypes = [C.c_void_p]
+    r.sam_hdr_tid2name.restype = C.c_char_p
+    r.sam_hdr_tid2name.argtypes = [C.c_void_p, C.c_int]
+    r.bam_init1.restype = C.POINTER(Bam1)
+    r.bam_read1.argtypes = [C.c_void_p, C.POINTER(Bam1)]
+    r.bam_destroy1.argtypes = [C.POINTER(Bam1)]
+    r.sam_format1.argtypes = [C.c_void_p, C.POINTER(Bam1), C.POINTER(KString)]
+    libc = C.CDLL(None)
+    libc.malloc.restype = C.c_void_p
+    libc.malloc.argtypes = [C.c_size_t]
+    libc.free.argtypes = [C.c_void_p]
+    mem = libc.malloc(max(1, len(img)))
+    C.memmove(mem, bytes(img), len(img))
+    fp = r.bgzf_hopen(r.hopen(b"mem:", b"r:", mem, len(img)), b"r")
+    hdr = r.bam_hdr_read(fp)
+    assert hdr
+    names = [r.sam_hdr_tid2name(hdr, i) for i in range(r.sam_hdr_nref(hdr))]
+    b = r.bam_init1()
+    ks = KString(0, 0, None)
+    lines = []
+    while r.bam_read1(fp, b) >= 0:
+        n = r.sam_format1(hdr, b, C.byref(ks))
+        lines.append(C.string_at(ks.s, ks.l) if n >= 0 else None)
+    if ks.s:
+        libc.free(ks.s)
+    r.bam_destroy1(b)
+    r.sam_hdr_destroy(hdr)
+    r.bgzf_close(fp)
+    return names, lines
+
+
 def orc_bam_unpack_all(stream):
     """Records of an inflated BAM record stream (header already removed) through the oracle.
     Returns list of (status, core tuple, data, seq, qual) or raises on a broken chain."""
