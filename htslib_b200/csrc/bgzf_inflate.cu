@@ -636,7 +636,7 @@ constexpr uint32_t MREC_CAP = 65536 / 3 + 64;   // a match yields >= 3 bytes of 
 #ifndef HGPU_NEW_WALK
 __device__ int decode_body_parallel(InflateSmem &s, const uint32_t *wbase, const uint32_t *wend, uint32_t body,
                                     uint32_t total, uint8_t *out, uint32_t cap, uint32_t &o, uint2 *mrec,
-                                    uint32_t &end_pos, Prof &pf)
+                                    uint32_t &end_pos, Prof &pf, uint32_t mcap = MREC_CAP)
 {
     const uint32_t lane = hgpu_lane();
     const uint32_t S = (total - body + 31) / 32;
@@ -672,7 +672,7 @@ __device__ int decode_body_parallel(InflateSmem &s, const uint32_t *wbase, const
     }
     uint32_t tot_out = __shfl_sync(0xffffffffu, on, 31), tot_m = __shfl_sync(0xffffffffu, mn, 31);
     if ((uint64_t)o + tot_out > cap) return HGPU_BGZF_ERR_SPACE;
-    if (tot_m > MREC_CAP) return HGPU_BGZF_ERR_ZLIB;           // impossible within 64 KiB of output
+    if (tot_m > mcap) return HGPU_BGZF_ERR_ZLIB;           // impossible within 64 KiB of output
     bool bad_dist = false;
     if (lane <= E) {
         uint32_t e2, n2, m2, st2;
@@ -692,7 +692,7 @@ __device__ int decode_body_parallel(InflateSmem &s, const uint32_t *wbase, const
 #else
 __device__ int decode_body_parallel(InflateSmem &s, const uint32_t *wbase, const uint32_t *wend, uint32_t body,
                                     uint32_t total, uint8_t *out, uint32_t cap, uint32_t &o, uint2 *mrec,
-                                    uint32_t &end_pos, Prof &pf)
+                                    uint32_t &end_pos, Prof &pf, uint32_t mcap = MREC_CAP)
 {
     const uint32_t lane = hgpu_lane();
     // 32 sub-ranges cut on word boundaries; every lane walks from PREROLL bits in front of its cut (so that
@@ -743,7 +743,7 @@ __device__ int decode_body_parallel(InflateSmem &s, const uint32_t *wbase, const
     }
     uint32_t tot_out = __shfl_sync(0xffffffffu, on, 31), tot_m = __shfl_sync(0xffffffffu, mn, 31);
     if ((uint64_t)o + tot_out > cap) return HGPU_BGZF_ERR_SPACE;
-    if (tot_m > MREC_CAP) return HGPU_BGZF_ERR_ZLIB;           // impossible within 64 KiB of output
+    if (tot_m > mcap) return HGPU_BGZF_ERR_ZLIB;           // impossible within 64 KiB of output
     bool bad_dist = false;
     {
         uint32_t e2, n2, m2, st2;
@@ -767,7 +767,7 @@ __device__ int decode_body_parallel(InflateSmem &s, const uint32_t *wbase, const
 // decoders above.
 // ---------------------------------------------------------------------------------------------
 __device__ int inflate_member(InflateSmem &s, const uint8_t *src, uint32_t slen, uint8_t *out, uint32_t cap,
-                              uint32_t &olen, uint2 *mrec, Prof &pf)
+                              uint32_t &olen, uint2 *mrec, Prof &pf, uint32_t mcap = MREC_CAP)
 {
     const uint32_t lane = hgpu_lane();
     Bits b;
@@ -872,7 +872,7 @@ __device__ int inflate_member(InflateSmem &s, const uint8_t *src, uint32_t slen,
             pf.mark(0);
             if (total - body >= PAR_MIN_BITS) {
                 uint32_t end_pos = 0;
-                rc = decode_body_parallel(s, wbase, wend, body, total, out, cap, o, mrec, end_pos, pf);
+                rc = decode_body_parallel(s, wbase, wend, body, total, out, cap, o, mrec, end_pos, pf, mcap);
                 if (rc) return rc;
                 // continue the uniform reader right after the end-of-block code
                 uint32_t byte = (end_pos - mis_bits) >> 3, bit = (end_pos - mis_bits) & 7;
@@ -954,6 +954,73 @@ bgzf_inflate_kernel(const uint8_t *__restrict__ in, const uint64_t *__restrict__
     }
 }
 
+
+// ---------------------------------------------------------------------------------------------
+// Plain gzip members of any size — zlib_mem_inflate as cram_uncompress_block uses it for GZIP blocks
+// (cram/cram_io.c:1068-1157, :1600-1616): RFC 1952 header (FEXTRA / FNAME / FCOMMENT / FHCRC skipped), raw
+// DEFLATE through the same member decoder as a BGZF block, CRC-32 and ISIZE from the trailer.  One warp per
+// member.  Limits: a single deflate block with more than GZ_MREC matches is refused (ERR_ZLIB -> the caller's host
+// library); CRAM writes its GZIP blocks with memLevel 9 (cram_io.c zlib_mem_deflate): at most 32 767 symbols per block.
+// ---------------------------------------------------------------------------------------------
+constexpr uint32_t GZ_MREC = 32768 + 64;
+
+__device__ int gzip_header_len(const uint8_t *h, uint32_t n)
+{
+    if (n < 18 || h[0] != 31 || h[1] != 139 || h[2] != 8 || (h[3] & 0xe0)) return -1;
+    const uint32_t flg = h[3];
+    uint32_t p = 10;
+    if (flg & 4) { if (p + 2 > n) return -1; p += 2u + (h[p] | h[p + 1] << 8); }
+    if (flg & 8) { while (p < n && h[p]) p++; p++; }
+    if (flg & 16) { while (p < n && h[p]) p++; p++; }
+    if (flg & 2) p += 2;
+    return p + 8 <= n ? (int)p : -1;
+}
+
+__global__ void __launch_bounds__(32 * INFLATE_WARPS, INFL_LB)
+gzip_inflate_kernel(const uint8_t *__restrict__ in, const uint64_t *__restrict__ in_off,
+                    const uint32_t *__restrict__ in_len, uint32_t n, uint8_t *out,
+                    const uint64_t *__restrict__ out_off, const uint32_t *__restrict__ out_cap,
+                    uint32_t *out_len, int32_t *status, uint32_t *counter, uint2 *mrec_all)
+{
+    extern __shared__ __align__(16) uint8_t dyn_smem[];
+    uint32_t (*crc_tab)[256] = reinterpret_cast<uint32_t (*)[256]>(dyn_smem);
+    InflateSmem *smem_all = reinterpret_cast<InflateSmem *>(dyn_smem + 4096);
+    for (int i = threadIdx.x; i < 1024; i += blockDim.x) (&crc_tab[0][0])[i] = (&g_crc_tab[0][0])[i];
+    __syncthreads();
+    InflateSmem &s = smem_all[threadIdx.x >> 5];
+    uint2 *mrec = mrec_all + ((size_t)blockIdx.x * INFLATE_WARPS + (threadIdx.x >> 5)) * GZ_MREC;
+    const uint32_t lane = hgpu_lane();
+    for (;;) {
+        uint32_t job = 0;
+        if (lane == 0) job = atomicAdd(counter, 1u);
+        job = __shfl_sync(0xffffffffu, job, 0);
+        if (job >= n) break;
+        const uint8_t *blk = in + in_off[job];
+        const uint32_t blen = in_len[job];
+        uint8_t *dst = out + out_off[job];
+        const uint32_t cap = out_cap[job];
+        int rc = HGPU_OK;
+        uint32_t got = 0;
+        const int hl = gzip_header_len(blk, blen);
+        if (hl < 0) rc = HGPU_BGZF_ERR_HEADER;
+        else {
+            Prof pf;
+            pf.start();
+            rc = inflate_member(s, blk + hl, blen - (uint32_t)hl, dst, cap, got, mrec, pf, GZ_MREC);
+            if (rc == HGPU_OK) {
+                __syncwarp();
+                __threadfence_block();
+                const uint8_t *f = blk + blen - 8;
+                const uint32_t want = f[0] | f[1] << 8 | f[2] << 16 | (uint32_t)f[3] << 24;
+                const uint32_t isize = f[4] | f[5] << 8 | f[6] << 16 | (uint32_t)f[7] << 24;
+                const uint32_t crc = warp_crc32(crc_tab, dst, got);
+                if (crc != want || isize != got) rc = HGPU_BGZF_ERR_CRC;
+            }
+        }
+        __syncwarp();
+        if (lane == 0) { status[job] = rc; out_len[job] = rc == HGPU_OK ? got : 0; }
+    }
+}
 
 #include "bgzf_inflate_cta.cuh"
 
@@ -1252,6 +1319,37 @@ int hgpu_launch_bgzf_inflate(hgpu_ctx *ctx, const uint8_t *d_in, const uint64_t 
                                                             d_out_len, d_status, counter, mrec);
     hgpu_count_launch();
     return hgpu_check(cudaGetLastError(), "inflate launch");
+}
+
+// gzip members (device pointers): same calling shape as hgpu_launch_bgzf_inflate, no 64 KiB clamp
+int hgpu_launch_gzip_inflate(hgpu_ctx *ctx, const uint8_t *d_in, const uint64_t *d_in_off, const uint32_t *d_in_len, uint32_t n,
+                             uint8_t *d_out, const uint64_t *d_out_off, const uint32_t *d_out_cap, uint32_t *d_out_len,
+                             int32_t *d_status, cudaStream_t st)
+{
+    if (n == 0) return HGPU_OK;
+    if (hgpu_check(cudaSetDevice(ctx->device), "cudaSetDevice")) return HGPU_ERR_CUDA;
+    int rc = ensure_crc_tables(ctx, st);
+    if (rc) return rc;
+    static bool attr_set[64];
+    const int dv = ctx->device & 63;
+    const size_t dyn_w = 4096 + INFLATE_WARPS * sizeof(InflateSmem);
+    if (!attr_set[dv]) {
+        if (hgpu_check(cudaFuncSetAttribute(gzip_inflate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn_w), "gzip smem attr")) return HGPU_ERR_CUDA;
+        attr_set[dv] = true;
+    }
+    uint32_t grid = (n + INFLATE_WARPS - 1) / INFLATE_WARPS;
+    const uint32_t full = (uint32_t)ctx->sm_count;          // CRAM files hold a handful of GZIP blocks: one CTA per SM is plenty
+    if (grid > full) grid = full;
+    uint32_t *counter = hgpu_take_counter(ctx, st);
+    if (!counter) return HGPU_ERR_CUDA;
+    // match-record scratch: the BGZF layout (three rotating sets for the pipelined host path) in front, this kernel's slots behind it
+    const size_t bgzf_part = (size_t)ctx->sm_count * 4u * INFLATE_WARPS * MREC_CAP * sizeof(uint2) * 3;
+    rc = hgpu_ensure_mrec(ctx, bgzf_part + (size_t)full * INFLATE_WARPS * GZ_MREC * sizeof(uint2));
+    if (rc) return rc;
+    uint2 *mrec = reinterpret_cast<uint2 *>(ctx->d_mrec + bgzf_part);
+    gzip_inflate_kernel<<<grid, 32 * INFLATE_WARPS, dyn_w, st>>>(d_in, d_in_off, d_in_len, n, d_out, d_out_off, d_out_cap, d_out_len, d_status, counter, mrec);
+    hgpu_count_launch();
+    return hgpu_check(cudaGetLastError(), "gzip inflate launch");
 }
 
 extern "C" int hgpu_debug_p2(int job, unsigned int *out)

@@ -5,8 +5,8 @@
 // hgpu_cram_scan_blocks goes to the device: one upload of the file image, one CRC-32 launch over every
 // block's header+payload (:1585-1592), one batch launch per entropy codec (method 4 rANS 4x8, 5 rANS
 // Nx16, 6 adaptive arithmetic, 8 tok3 names), one download of all payloads.  RAW blocks are host copies.
-// Method 7 (fqzcomp) blocks go through hgpu_fqz_decode_batch_host.  GZIP / BZIP2 / LZMA blocks are reported
-// HGPU_CRAM_UNSUPPORTED and stay with the host library.
+// Method 7 (fqzcomp) blocks go through hgpu_fqz_decode_batch_host.  GZIP blocks (whole gzip members of any size) take
+// gzip_inflate_kernel; BZIP2 / LZMA blocks are reported HGPU_CRAM_UNSUPPORTED and stay with the host library.
 #include "hgpu_internal.h"
 #include <vector>
 #include <new>
@@ -42,7 +42,7 @@ static int cram_uncompress_impl(hgpu_ctx *ctx, const uint8_t *file, uint64_t fil
         status[i] = b.method <= 8 ? HGPU_OK : HGPU_CRAM_ERR_DECODE;           // default: -1 (cram_io.c:1749)
         if (b.uncomp_size > MAX_BLOCK) { status[i] = HGPU_CRAM_ERR_DECODE; continue; }
         if (b.method <= 8) idx[b.method].push_back(i);
-        if (b.uncomp_size && (b.method == 4 || b.method == 5 || b.method == 6)) {
+        if (b.uncomp_size && (b.method == 1 || b.method == 4 || b.method == 5 || b.method == 6)) {
             if (out_off[i] < out_lo) out_lo = out_off[i];
             if (out_off[i] + b.uncomp_size > out_hi) out_hi = out_off[i] + b.uncomp_size;
         }
@@ -99,38 +99,6 @@ static int cram_uncompress_impl(hgpu_ctx *ctx, const uint8_t *file, uint64_t fil
         }
     }
 
-    // ---- GZIP blocks (method 1, zlib_mem_inflate cram_io.c:1068-1157) that fit one BGZF block: a gzip member with the
-    // plain 10-byte header is header + raw DEFLATE + CRC32 + ISIZE, and CRC32 + ISIZE is exactly the BGZF footer, so
-    // swapping the header for the 18-byte BGZF one hands it to the BGZF inflate kernel.  Larger or unusual members
-    // (FEXTRA / FNAME ..., > 64 KiB) stay HGPU_CRAM_UNSUPPORTED.
-    std::vector<uint32_t> gz_idx;
-    std::vector<uint8_t> gz_in, gz_out;
-    std::vector<uint64_t> g_in_off, g_out_off;
-    std::vector<uint32_t> g_in_len, g_cap, g_got;
-    std::vector<int32_t> g_st;
-    for (uint32_t i : idx[1]) {
-        const hgpu_cram_block &b = blocks[i];
-        const uint8_t *c = file + b.data_off;
-        if (b.uncomp_size == 0 || b.uncomp_size > 65536 || b.comp_size < 18 || (uint64_t)b.comp_size + 8 > 65536) continue;
-        if (c[0] != 0x1f || c[1] != 0x8b || c[2] != 8 || c[3] != 0) continue;
-        const uint32_t total = b.comp_size + 8;
-        static const uint8_t hdr[16] = {0x1f, 0x8b, 8, 4, 0, 0, 0, 0, 0, 0xff, 6, 0, 'B', 'C', 2, 0};
-        g_in_off.push_back(gz_in.size()); g_in_len.push_back(total);
-        g_out_off.push_back((uint64_t)gz_idx.size() * 65536); g_cap.push_back(65536);
-        gz_in.insert(gz_in.end(), hdr, hdr + 16);
-        gz_in.push_back((uint8_t)((total - 1) & 0xff)); gz_in.push_back((uint8_t)((total - 1) >> 8));
-        gz_in.insert(gz_in.end(), c + 10, c + b.comp_size);              // DEFLATE payload and the CRC32 + ISIZE trailer
-        gz_idx.push_back(i);
-    }
-    if (!gz_idx.empty()) {
-        gz_in.resize(gz_in.size() + 16);
-        gz_out.resize((size_t)gz_idx.size() * 65536);
-        g_got.resize(gz_idx.size()); g_st.resize(gz_idx.size());
-        int rc = hgpu_bgzf_inflate_blocks_host(ctx, gz_in.data(), g_in_off.data(), g_in_len.data(), (uint32_t)gz_idx.size(),
-                                               gz_out.data(), g_out_off.data(), g_cap.data(), g_got.data(), g_st.data());
-        if (rc) return rc;
-    }
-
     // ---- device staging: file image, the output span (same layout as the caller's), job arrays
     std::vector<uint32_t> order;                                              // job order: 4x8, Nx16, arith
     uint32_t big5 = 0, big6 = 0;                                              // blocks launched on their own, at the end of their group
@@ -138,6 +106,9 @@ static int cram_uncompress_impl(hgpu_ctx *ctx, const uint8_t *file, uint64_t fil
         for (uint32_t i : idx[m]) if (blocks[i].uncomp_size && (m == 4 || blocks[i].uncomp_size <= BIG_BLOCK)) order.push_back(i);
         if (m != 4) for (uint32_t i : idx[m]) if (blocks[i].uncomp_size > BIG_BLOCK) { order.push_back(i); (m == 5 ? big5 : big6)++; }
     }
+    // GZIP blocks (method 1, zlib_mem_inflate cram_io.c:1068-1157): whole gzip members of any size, one warp each
+    uint32_t n1 = 0;
+    for (uint32_t i : idx[1]) if (blocks[i].uncomp_size && blocks[i].comp_size >= 18) { order.push_back(i); n1++; }
     const uint32_t nj = (uint32_t)order.size();
     uint32_t n4 = 0, n5 = 0, n6 = 0, max5 = 0, max6 = 0;
     std::vector<uint64_t> jio(nj), joo(nj), coff(n);
@@ -145,6 +116,7 @@ static int cram_uncompress_impl(hgpu_ctx *ctx, const uint8_t *file, uint64_t fil
     for (uint32_t k = 0; k < nj; k++) {
         const hgpu_cram_block &b = blocks[order[k]];
         jio[k] = b.data_off; jil[k] = b.comp_size; joo[k] = out_off[order[k]] - out_lo; jol[k] = b.uncomp_size;
+        if (b.method == 1) continue;
         if (b.method == 4) n4++;
         else if (b.method == 5) { n5++; if (b.uncomp_size > max5 && b.uncomp_size <= BIG_BLOCK) max5 = b.uncomp_size; }
         else { n6++; if (b.uncomp_size > max6 && b.uncomp_size <= BIG_BLOCK) max6 = b.uncomp_size; }
@@ -194,9 +166,14 @@ static int cram_uncompress_impl(hgpu_ctx *ctx, const uint8_t *file, uint64_t fil
                                          d_jol + n4 + n5, d_got + n4 + n5, d_st + n4 + n5, max6, s);
         if (rc) return rc;
     }
-    for (uint32_t k = n4 + n5 + n6 - big6; k < nj; k++) {
+    for (uint32_t k = n4 + n5 + n6 - big6; k < n4 + n5 + n6; k++) {
         rc = hgpu_arith_decode_batch_dev(ctx, base + o_file, d_jio + k, d_jil + k, 1, base + o_out, d_joo + k, d_jol + k, d_got + k, d_st + k, jol[k], s);
         if (rc == HGPU_ERR_NOMEM) nomem.push_back(k); else if (rc) return rc;
+    }
+    if (n1) {
+        const uint32_t k0 = n4 + n5 + n6;
+        rc = hgpu_launch_gzip_inflate(ctx, base + o_file, d_jio + k0, d_jil + k0, n1, base + o_out, d_joo + k0, d_jol + k0, d_got + k0, d_st + k0, s);
+        if (rc) return rc;
     }
     std::vector<uint32_t> jgot(nj), crc(n);
     std::vector<int32_t> jst(nj);
@@ -212,8 +189,11 @@ static int cram_uncompress_impl(hgpu_ctx *ctx, const uint8_t *file, uint64_t fil
     // ---- results, in the reference's order of checks: CRC first, then the codec, then the size
     for (uint32_t k = 0; k < nj; k++) {
         const uint32_t i = order[k];
-        if (jst[k] != HGPU_OK || jgot[k] != blocks[i].uncomp_size) status[i] = HGPU_CRAM_ERR_DECODE;   // usize != usize2
-        else got_len[i] = jgot[k];
+        // a gzip member the device decoder declines (a deflate block beyond its match-record limit, a zlib wrapper) goes back
+        // to the host library rather than being called corrupt
+        if (blocks[i].method == 1 && (jst[k] == HGPU_BGZF_ERR_ZLIB || jst[k] == HGPU_BGZF_ERR_HEADER || jst[k] == HGPU_BGZF_ERR_SPACE)) status[i] = HGPU_CRAM_UNSUPPORTED;
+        else if (jst[k] != HGPU_OK || jgot[k] != blocks[i].uncomp_size) status[i] = HGPU_CRAM_ERR_DECODE;   // usize != usize2
+        else { got_len[i] = jgot[k]; status[i] = HGPU_OK; }
     }
     for (uint32_t i : idx[0]) {                                               // RAW: the payload is the data
         const hgpu_cram_block &b = blocks[i];
@@ -221,12 +201,8 @@ static int cram_uncompress_impl(hgpu_ctx *ctx, const uint8_t *file, uint64_t fil
         memcpy(out + out_off[i], file + b.data_off, m);
         got_len[i] = m;
     }
-    for (int m : {1, 2, 3}) for (uint32_t i : idx[m]) status[i] = blocks[i].uncomp_size ? HGPU_CRAM_UNSUPPORTED : HGPU_OK;
-    for (size_t t = 0; t < gz_idx.size(); t++) {                              // the GZIP blocks that went through the BGZF kernel
-        const uint32_t i = gz_idx[t];
-        if (g_st[t] != HGPU_OK || g_got[t] != blocks[i].uncomp_size) status[i] = HGPU_CRAM_ERR_DECODE;
-        else { memcpy(out + out_off[i], gz_out.data() + g_out_off[t], g_got[t]); got_len[i] = g_got[t]; status[i] = HGPU_OK; }
-    }
+    for (int m : {2, 3}) for (uint32_t i : idx[m]) status[i] = blocks[i].uncomp_size ? HGPU_CRAM_UNSUPPORTED : HGPU_OK;
+    for (uint32_t i : idx[1]) if (blocks[i].uncomp_size && blocks[i].comp_size < 18) status[i] = HGPU_CRAM_UNSUPPORTED;
     {
         size_t t = 0;
         for (uint32_t i : idx[7]) {

@@ -49,6 +49,9 @@ int hgpu_launch_bgzf_inflate(hgpu_ctx *ctx, const uint8_t *d_in, const uint64_t 
                              const uint32_t *d_in_len, uint32_t n, uint8_t *d_out,
                              const uint64_t *d_out_off, const uint32_t *d_out_cap,
                              uint32_t *d_out_len, int32_t *d_status, cudaStream_t st);
+int hgpu_launch_gzip_inflate(hgpu_ctx *ctx, const uint8_t *d_in, const uint64_t *d_in_off, const uint32_t *d_in_len, uint32_t n,
+                             uint8_t *d_out, const uint64_t *d_out_off, const uint32_t *d_out_cap, uint32_t *d_out_len,
+                             int32_t *d_status, cudaStream_t st);
 int hgpu_launch_crc32(hgpu_ctx *ctx, const uint8_t *d_buf, size_t len, uint32_t *d_partial,
                       uint32_t *h_result, uint32_t crc0, cudaStream_t st);
 

@@ -195,3 +195,52 @@ def test_cram_write_blocks_reproduce_every_fixture_block(ctx):
             assert out[int(off[i]):end].tobytes() == img[lo:hi].tobytes(), (os.path.basename(path), i)
         total_blocks += n
     assert total_blocks > 100
+
+
+def test_cram_gzip_blocks_of_any_size(ctx):
+    """cram_uncompress_block's GZIP arm (zlib_mem_inflate, cram_io.c:1068-1157, :1600-1616): whole gzip members larger than a
+    BGZF block, with optional header fields, several deflate blocks, stored blocks — and a corrupted one"""
+    import gzip as gz
+    rng = random.Random(21)
+    names = b"".join(b"@HS25_%05d:%d:%d:%d:%d#%d\n" % (rng.randrange(99999), rng.randrange(8), 1100 + rng.randrange(1200), rng.randrange(20000), rng.randrange(200000), rng.randrange(96)) for _ in range(9000))
+    pays = [names,                                                         # 300+ KB of read names: several dynamic blocks
+            bytes(rng.randrange(256) for _ in range(200000)),              # incompressible: stored blocks
+            b"ACGT" * 50000,                                               # long runs: overlapping matches
+            b"x"]
+    def member(p, level, extra=False):
+        c = zlib.compressobj(level, zlib.DEFLATED, -15, 9)
+        raw = c.compress(p) + c.flush()
+        hdr = bytes([0x1f, 0x8b, 8, 0x18 if extra else 0, 0, 0, 0, 0, 0, 3]) + (b"name.txt\0a comment\0" if extra else b"")
+        return hdr + raw + struct.pack("<II", zlib.crc32(p), len(p) & 0xffffffff)
+    import struct
+    comps = [member(pays[0], 6), member(pays[1], 6, True), member(pays[2], 9), member(pays[3], 1), member(pays[0], 1, True)]
+    want = [pays[0], pays[1], pays[2], pays[3], pays[0]]
+    bad = bytearray(comps[0]); bad[len(bad) // 2] ^= 0x40
+    comps.append(bytes(bad)); want.append(None)
+    n = len(comps)
+    dt = np.dtype([("data_off", "<u8"), ("comp_size", "<u4"), ("uncomp_size", "<u4"), ("content_id", "<i4"), ("method", "u1"),
+                   ("content_type", "u1"), ("hdr_len", "<u2"), ("container", "<u4"), ("pad2", "<u4")])     # hgpu_cram_block: 32 bytes
+    assert dt.itemsize == 32
+    blocks = np.zeros(n, dtype=dt)
+    for i, (c, w) in enumerate(zip(comps, want)):
+        blocks[i]["method"] = 1; blocks[i]["content_type"] = 4; blocks[i]["content_id"] = 10 + i
+        blocks[i]["comp_size"] = len(c); blocks[i]["uncomp_size"] = len(w if w is not None else pays[0])
+    L = H.lib()
+    L.hgpu_cram_write_blocks_host.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p]
+    bufs = [np.frombuffer(c, dtype=np.uint8).copy() for c in comps]
+    ptrs = (C.c_void_p * n)(*[b.ctypes.data for b in bufs])
+    img = np.zeros(sum(len(c) for c in comps) + 32 * n, dtype=np.uint8)
+    off = np.zeros(n, dtype=np.uint64); tot = C.c_uint64(0)
+    assert L.hgpu_cram_write_blocks_host(ctx.h, blocks.ctypes.data, ptrs, n, img.ctypes.data, img.size, off.ctypes.data, C.byref(tot)) == 0
+    img = img[:tot.value].copy()
+    scanned = blocks.copy()
+    for i in range(n):                                                  # where the payloads sit in the image we just wrote
+        hl = 2 + sum(1 if v < 0x80 else 2 if v < 0x4000 else 3 if v < 0x200000 else 4 if v < 0x10000000 else 5
+                     for v in (10 + i, len(comps[i]), int(blocks[i]["uncomp_size"])))
+        scanned[i]["hdr_len"] = hl; scanned[i]["data_off"] = int(off[i]) + hl
+    _, res = H.cram_uncompress_blocks(ctx, img, scanned)
+    for i, ((st, data), w) in enumerate(zip(res, want)):
+        if w is None:
+            assert st != 0, i                                           # corrupt: an error or "left to the host", never wrong bytes
+        else:
+            assert st == 0 and data == w, (i, st, len(data))
