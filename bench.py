@@ -48,9 +48,13 @@ def parse():
 def ncu_traffic(kernel_tag):
     """dram__bytes_read+write of one launch from the committed ncu --set full capture (profiles/),
     with the algorithmic bytes of THAT captured launch, so the ratio can be applied honestly."""
-    p = os.path.join(ROOT, "profiles", "r1_%s_ncu_summary.txt" % kernel_tag)
+    p = os.path.join(ROOT, "profiles", "r2_%s_ncu_summary.txt" % kernel_tag)
     if not os.path.exists(p):
         return None
+    alg = None
+    tp = os.path.join(ROOT, "profiles", "r2_traffic.json")
+    if os.path.exists(tp):
+        alg = json.load(open(tp)).get(kernel_tag, {}).get("algorithmic_bytes")
     rd = wr = None
     for line in open(p):
         f = line.split()
@@ -59,7 +63,8 @@ def ncu_traffic(kernel_tag):
     if not rd or not wr:
         return None
     scale = {"Gbyte": 1e9, "Mbyte": 1e6, "Kbyte": 1e3, "byte": 1.0}
-    return {"dram_bytes": rd[0] * scale.get(rd[1], 1) + wr[0] * scale.get(wr[1], 1), "source": os.path.relpath(p, ROOT)}
+    return {"dram_bytes": rd[0] * scale.get(rd[1], 1) + wr[0] * scale.get(wr[1], 1), "algorithmic_bytes": alg,
+            "source": os.path.relpath(p, ROOT)}
 
 
 def peaks():
@@ -499,6 +504,10 @@ def run_ours(args):
         return
     hbm, how = peaks()
     achieved = (U + Cb) / ms_step / 1e6
+    # roofline.traffic: the ncu --set full capture of this kernel on this very workload (same seeds, same launch shape);
+    # only quoted per launch when the captured launch moved the same algorithmic bytes as the timed one
+    cap = ncu_traffic("inflate")
+    traffic = cap["dram_bytes"] if cap and cap.get("algorithmic_bytes") and abs(cap["algorithmic_bytes"] - (U + Cb)) <= 0.01 * (U + Cb) else None
     out = {
         "metric": "BGZF inflate + CRAM rANS decode GB/s at 1/2/4/8 B200 vs reference CPU",
         "value": U * world / ms_step / 1e6, "unit": "GB/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
@@ -513,11 +522,13 @@ def run_ours(args):
                                    "%.2f GB unique per GPU repeated %dx at distinct addresses (host cores shared by %d generators)"
                                    % (U / 1e9 / corpus["tile"], corpus["tile"], world)},
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": hbm, "unit": "GB/s", "frac": achieved / hbm,
-                     "traffic": None, "kernel": "bgzf_inflate_kernel", "algorithmic_bytes_per_launch": U + Cb,
+                     "traffic": traffic, "kernel": "bgzf_inflate_kernel", "algorithmic_bytes_per_launch": U + Cb,
                      "peak_source": how,
-                     "traffic_note": "ncu --set full was captured on the same kernel at --gb 1 (profiles/r1_inflate_ncu_summary.txt): "
-                                     "dram read+write per launch there is in traffic_capture; a 10 GB launch was not captured (null above)",
-                     "traffic_capture": ncu_traffic("inflate")},
+                     "traffic_note": "dram__bytes_read.sum + dram__bytes_write.sum of one launch from the committed ncu --set full capture of "
+                                     "`python bench.py --gb 10` (profiles/r2_inflate_ncu_summary.txt); null when this run's launch is a different size. "
+                                     "3.2x the algorithmic bytes: the 8-byte match records make a DRAM round trip (~14 GB) and the CRC pass re-reads "
+                                     "the output (~9.7 GB) because 16 warps/SM x (64 KiB window + records) exceeds the 126 MB L2 (DESIGN.md 6)",
+                     "traffic_capture": cap},
         "gpu_launches": int(launches),
         "clocks": clocks,
     }

@@ -441,19 +441,15 @@ __device__ __forceinline__ void exec_batch(uint8_t *out, InflateSmem &s, uint2 r
             const int k = __ffs(m) - 1;
             const uint32_t d0 = __shfl_sync(0xffffffffu, dst, k), ln = __shfl_sync(0xffffffffu, len, k);
             const uint32_t di = __shfl_sync(0xffffffffu, dist, k);
-            uint8_t w[9];
-            // i % di for i = lane, lane+32, ...: one division pair, then add-and-wrap
+            // i % di for i = lane, lane+32, ...: one division pair, then add-and-wrap.  The source bytes lie in
+            // front of the destination and are never overwritten here, so loads and stores need no phases.
             const uint32_t stepm = 32u % di;
             uint32_t r = lane % di;
-#pragma unroll
-            for (int t = 0; t < 9; t++) {
-                uint32_t i = lane + 32 * t;
-                if (i < ln) w[t] = out[d0 - di + r];
+            for (uint32_t i = lane; i < ln; i += 32) {
+                out[d0 + i] = out[d0 - di + r];
                 r += stepm;
                 if (r >= di) r -= di;
             }
-#pragma unroll
-            for (int t = 0; t < 9; t++) { uint32_t i = lane + 32 * t; if (i < ln) out[d0 + i] = w[t]; }
         }
         __syncwarp();                               // next round reads what other lanes just stored
         done |= R;

@@ -119,7 +119,7 @@ __device__ int read_alphabet(const uint8_t *p, const uint8_t *end, uint32_t *F)
 //            the record's range (one step in the common case: 64 buckets for at most a few dozen symbols).
 //            A 40-symbol order-1 table is 9 KiB instead of 47 KiB (shift 10) / 170 KiB (shift 12), so
 //            it stays in shared memory; rows no valid stream enters ("null rows") only exist in full form.
-constexpr uint32_t COMPACT_LB = 6;
+constexpr uint32_t COMPACT_LB = 6, COMPACT_LB_BIG = 8;
 struct Table {
     uint8_t *lut;      // [rows][1<<lb]
     uint32_t *fb;      // [rows][ncol]  byte | start<<8 | (f-1)<<20
@@ -455,10 +455,15 @@ __device__ Table place_table(uint8_t *smem, const WarpScratch &ws, uint32_t rows
 {
     Table t;
     (void)smem;
-    const uint32_t need_f = table_bytes(rows, ncol, shift), need_c = table_bytes(rows, ncol, COMPACT_LB);
+    // compact form: 256 buckets when they fit (the walk is then almost always one step: ncu showed the 64-bucket walk
+    // at 40 % of rans_tile4_kernel's instructions on 150-symbol alphabets), else 64
+    const uint32_t need_f = table_bytes(rows, ncol, shift);
     uint32_t lb = shift;
-    if (!full_only && need_c <= ws.tab_cap && (ws.compact || need_f > ws.tab_cap)) lb = COMPACT_LB;
-    const uint32_t need = lb == shift ? need_f : need_c;
+    if (!full_only && (ws.compact || need_f > ws.tab_cap)) {
+        if (shift > COMPACT_LB_BIG && table_bytes(rows, ncol, COMPACT_LB_BIG) <= ws.tab_cap) lb = COMPACT_LB_BIG;
+        else if (table_bytes(rows, ncol, COMPACT_LB) <= ws.tab_cap) lb = COMPACT_LB;
+    }
+    const uint32_t need = table_bytes(rows, ncol, lb);
     if (need > ws.tab_cap && !ws.gtab) ws.defer = true;                 // caller bails out
     uint8_t *base = need <= ws.tab_cap ? ws.tab_base : ws.gtab;
     t.in_smem = need <= ws.tab_cap;

@@ -435,6 +435,16 @@ int hgpu_bam_layout_dev(hgpu_ctx *ctx, const uint8_t *d_stream, uint64_t len,
 unsigned char *rans_uncompress_to_4x16(unsigned char *in, unsigned int in_size,
                                        unsigned char *out, unsigned int *out_size);
 unsigned char *rans_uncompress_4x16(unsigned char *in, unsigned int in_size, unsigned int *out_size);
+/* the byte transforms cram/cram_codecs.c binds directly (XPACK / XRLE) and the version string cram_external.c prints
+ * (xform.cu; pack.h:52-80, rle.h:69-91, htscodecs.h:53): same signatures, ownership and bytes as the reference */
+uint8_t *hts_pack(uint8_t *data, int64_t len, uint8_t *out_meta, int *out_meta_len, uint64_t *out_len);
+uint8_t hts_unpack_meta(uint8_t *data, uint32_t data_len, uint64_t udata_len, uint8_t *map, int *nsym);
+uint8_t *hts_unpack(uint8_t *data, int64_t len, uint8_t *out, uint64_t out_len, int nsym, uint8_t *map);
+uint8_t *hts_rle_encode(uint8_t *data, uint64_t data_len, uint8_t *run, uint64_t *run_len, uint8_t *rle_syms, int *rle_nsyms,
+                        uint8_t *out, uint64_t *out_len);
+uint8_t *hts_rle_decode(uint8_t *lit, uint64_t lit_len, uint8_t *run, uint64_t run_len, uint8_t *rle_syms, int rle_nsyms,
+                        uint8_t *out, uint64_t *out_len);
+const char *htscodecs_version(void);
 /* the rest of the libhtscodecs seam (shims.cu): one stream per call through the batch kernels.
  * rANS 4x8 (rANS_static.h:40-43) — encoder byte-identical to the reference */
 unsigned char *rans_uncompress(unsigned char *in, unsigned int in_size, unsigned int *out_size);

@@ -8,8 +8,9 @@
 #   * the htscodecs entropy coders (rANS 4x8 / Nx16, arith_dynamic, tok3, fqzcomp) are NOT compiled:
 #     cram/cram_io.c resolves rans_uncompress_4x16, tok3_decode_names, ... to libhtsgpu.so, which is
 #     what ./configure --with-external-htscodecs (configure.ac:278-282) does with -lhtscodecs.
-#     pack.c / rle.c / utils.c / htscodecs.c — the part of libhtscodecs libhtsgpu does not replace —
-#     are compiled from the reference as they stand.
+#     hts_pack / hts_unpack(_meta) / hts_rle_encode / hts_rle_decode / htscodecs_version (bound by cram_codecs.c and
+#     cram_external.c) come from libhtsgpu.so as well (xform.cu); only utils.c (thread-local scratch) is compiled from
+#     the reference as it stands.
 #   * everything else is compiled from /root/reference where it lies, exactly as oracle/build_ref.sh
 #     does for the stock build.
 #
@@ -34,7 +35,7 @@ patch -s -p0 "$OUT/src/bgzf.c" < "$HERE/htsgpu_bgzf.patch"
 CFLAGS="-O2 -g0 -fPIC -fvisibility=default -w -I$G -I$REF -I$REF/htscodecs/htscodecs -I$ROOT/include"
 SRCS="kfunc kstring bcf_sr_sort errmod faidx header hfile hts hts_expr hts_os md5 multipart probaln realn regidx region sam sam_mods simd synced_bcf_reader vcf_sweep tbx textutils thread_pool vcf vcfutils
 cram/cram_codecs cram/cram_decode cram/cram_encode cram/cram_external cram/cram_index cram/cram_io cram/cram_stats cram/mFILE cram/open_trace_file cram/pooled_alloc cram/string_alloc
-htscodecs/htscodecs/htscodecs htscodecs/htscodecs/pack htscodecs/htscodecs/rle htscodecs/htscodecs/utils"
+htscodecs/htscodecs/utils"
 pids=()
 OBJS="$OUT/obj/bgzf.o"
 gcc $CFLAGS -DHAVE_HTSGPU -I"$REF" -c "$OUT/src/bgzf.c" -o "$OUT/obj/bgzf.o" &
@@ -62,4 +63,4 @@ if [ -f "$ROOT/oracle/_ref/libhts_ref.so" ]; then
   done
 fi
 echo "built $OUT/libhts_gpu.so"
-nm -D "$OUT/libhts_gpu.so" | grep -E " U (rans_|arith_|tok3_|fqz_|hgpu_)" | awk '{print "  from libhtsgpu.so:", $2}'
+nm -D "$OUT/libhts_gpu.so" | grep -E " U (rans_|arith_|tok3_|fqz_|hgpu_|hts_pack|hts_unpack|hts_rle_|htscodecs_version)" | awk '{print "  from libhtsgpu.so:", $2}'
