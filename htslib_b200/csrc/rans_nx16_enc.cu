@@ -1,5 +1,5 @@
 // rANS Nx16 ("RANS_PR", CRAM 3.1 method 5) ENCODER for sm_100a — order 0 / order 1, 4-way or
-// 32-way (X32), with the CAT fallback; one warp per stream.
+// 32-way (X32), PACK, RLE, STRIPE (with the per-part method trial) and the CAT fallback; one warp per stream.
 //
 // Stands where rans_compress_to_4x16 -> rans_compress_O0/O1_4x16 / _32x16 stand in the reference
 // (htscodecs rANS_static4x16pr.c:1203-1579, :112-211, :402-497; rANS_static32x16pr.c:67-252,
@@ -14,12 +14,26 @@
 // histograms (__match_any_sync), normalised to 2^12 (order 0) or 2^10 / 2^12 per context
 // (order 1) so that every present symbol keeps f >= 1.
 #include "hgpu_internal.h"
+#include "xform_dev.cuh"
 
 namespace {
 
 constexpr uint32_t RANS_L = 1u << 15;
 constexpr uint32_t ENC_TAB_SMEM = 16 * 1024;          // {f,start} table: smem when A*A*4 fits
-constexpr uint32_t ENC_SCRATCH = 256 * 256 * 4 + 256 * 1024;   // per-warp: full table + table text
+constexpr uint32_t ENC_NEST_TBL = 256 * 256 * 4 + 256 * 1024;   // table text of the nested order-0 coder (compressed order-1 tables)
+constexpr uint32_t ENC_NEST_OUT = ENC_NEST_TBL + 2048, ENC_NEST_CAP = 160 * 1024;
+constexpr uint32_t ENC_SCRATCH = ENC_NEST_OUT + ENC_NEST_CAP;     // per-warp: full table + table text + nested coder
+
+constexpr uint32_t F_ORDER = 1, F_X32 = 4, F_STRIPE = 8, F_NOSZ = 0x10, F_CAT = 0x20, F_RLE = 0x40, F_PACK = 0x80,
+                   F_STRIPE_NO0 = 1u << 16;                            // rANS_static4x16.h:75-100
+constexpr uint32_t ENC_FAIL = 0xffffffffu;
+
+// Per-warp transform buffers (global memory, carved by the launcher when a job asks for PACK / RLE / STRIPE):
+// P packed bytes, R run-length literals, M run-length meta-data, S the transposed input of a STRIPE job followed by
+// its part lengths, B the best candidate of the part being tried.  X = bytes each can take (0: none were carved).
+struct XBuf { uint8_t *P, *R, *M, *S, *B; uint32_t X; };
+constexpr uint32_t XB_PAD_M = 1024, XB_PAD_S = 2048, XB_PAD_B = 4096;
+__host__ __device__ inline size_t xbuf_bytes(uint32_t X) { return X ? 5 * (size_t)X + XB_PAD_M + XB_PAD_S + XB_PAD_B : 0; }
 
 struct EncSmem {
     uint32_t cnt[256];        // order-0 histogram / row scratch
@@ -114,18 +128,16 @@ __device__ __forceinline__ uint32_t enc_put(uint32_t x, uint32_t f, uint32_t sta
     return ((x / f) << shift) + (x % f) + start;
 }
 
-// One stream.  Returns bytes written, or 0 on failure (capacity).
-__device__ uint32_t encode_stream(EncSmem &s, uint8_t *scratch, const uint8_t *in, uint32_t U, uint32_t want,
-                                  uint8_t *out, uint32_t cap)
+// The entropy coder proper (rans_enc_func(do_simd, order): rans_compress_O0/O1_4x16, _32x16): frequency table,
+// N states, 16-bit words; no format byte, no size.  U > 0.  Returns the bytes written at out, or ENC_FAIL when they
+// do not fit in cap.
+template <bool nested = false>
+__device__ uint32_t encode_core(EncSmem &s, uint8_t *scratch, const uint8_t *in, uint32_t U, uint32_t order, uint32_t N,
+                                uint8_t *out, uint32_t cap)
 {
     const uint32_t lane = hgpu_lane();
-    const uint32_t N = (want & 4) ? 32 : 4;
-    const uint32_t order = want & 1;
-    if (cap < 16) return 0;
-    uint32_t hdr = 0;
-    if (lane == 0) { out[0] = (uint8_t)((want & 5)); hdr = 1 + vput(out + 1, U); }
-    hdr = __shfl_sync(0xffffffffu, hdr, 0);
-    if (U == 0) return hdr;                                         // empty stream: format byte + size only
+    const uint32_t hdr = 0;
+    if (cap < 16) return ENC_FAIL;
     // ---- alphabet (order-0 histogram, warp-aggregated) ----
     __syncwarp();
     for (int j = lane; j < 256; j += 32) s.cnt[j] = 0;
@@ -138,14 +150,14 @@ __device__ uint32_t encode_stream(EncSmem &s, uint8_t *scratch, const uint8_t *i
         if (act && (peers & hgpu_lanemask_lt()) == 0) atomicAdd(&s.cnt[b], __popc(peers));
     }
     __syncwarp();
-    uint8_t *tbl = scratch + 256 * 256 * 4;                          // table text
+    uint8_t *tbl = scratch + (nested ? ENC_NEST_TBL : 256 * 256 * 4);   // table text
     uint32_t tlen = 0;
     uint32_t shift = 12;
     uint32_t *tab = nullptr;
     uint32_t A = 0;
     const uint32_t seg = U / N;
     if (order == 0) {
-        if (!normalise_row(s.cnt, 256, 4096)) return 0;
+        if (!normalise_row(s.cnt, 256, 4096)) return ENC_FAIL;
         if (lane == 0) {
             int n = put_alphabet(tbl, s.cnt);
             for (int j = 0; j < 256; j++) if (s.cnt[j]) n += vput(tbl + n, s.cnt[j]);
@@ -196,7 +208,7 @@ __device__ uint32_t encode_stream(EncSmem &s, uint8_t *scratch, const uint8_t *i
         tlen = __shfl_sync(0xffffffffu, tlen, 0);
         for (uint32_t r = 0; r < A; r++) {
             uint32_t *row = tab + r * A;
-            if (!normalise_row(row, (int)A, 1u << shift)) return 0;
+            if (!normalise_row(row, (int)A, 1u << shift)) return ENC_FAIL;
             __syncwarp();
             if (lane == 0) {
                 uint8_t *cp = tbl + tlen;
@@ -218,12 +230,25 @@ __device__ uint32_t encode_stream(EncSmem &s, uint8_t *scratch, const uint8_t *i
             __syncwarp();
         }
         __threadfence_block();
+        // a long table is itself order-0 coded when that is smaller (encode_freq1, rANS_static16_int.h:397-411)
+        if constexpr (!nested) if (tlen > 1000 && tlen - 1 <= ENC_NEST_CAP - 4096) {     // (the nested instantiation has no such call: no recursion)
+            __syncwarp();
+            uint8_t *tmp = scratch + ENC_NEST_OUT;
+            const uint32_t c = encode_core<true>(s, scratch, tbl + 1, tlen - 1, 0, 4, tmp, ENC_NEST_CAP);
+            __syncwarp();
+            if (c != ENC_FAIL && c + 6 < tlen) {
+                uint32_t at = 0;
+                if (lane == 0) { tbl[0] |= 1; at = 1 + vput(tbl + 1, tlen - 1); at += vput(tbl + at, c); }
+                at = __shfl_sync(0xffffffffu, at, 0);
+                for (uint32_t i = lane; i < c; i += 32) tbl[at + i] = tmp[i];
+                tlen = at + c;
+                __syncwarp();
+                __threadfence_block();
+            }
+        }
     }
     const uint32_t body = hdr + tlen + 4 * N;                         // first byte after the states
-    if ((uint64_t)body + 2ull * U + 64 > cap) {
-        // not enough room to encode safely in place: the caller's bound is too small
-        if ((uint64_t)hdr + U > cap) return 0;
-    }
+    if (body + 2u > cap) return ENC_FAIL;
     // ---- encode backwards; words are laid downwards from the end of the slot ----
     uint32_t wp = cap & ~1u;                                          // byte offset of the lowest word written so far
     uint32_t x = RANS_L;
@@ -275,16 +300,8 @@ __device__ uint32_t encode_stream(EncSmem &s, uint8_t *scratch, const uint8_t *i
         }
     }
 #undef ENC_EMIT
-    uint32_t total = 0;
-    if (!overflow) total = body + ((cap & ~1u) - wp);
-    if (overflow || total >= hdr + U) {
-        // CAT fallback (rANS_static4x16pr.c:1539-1553): format byte | 0x20, raw payload
-        if ((uint64_t)hdr + U > cap) return 0;
-        __syncwarp();
-        if (lane == 0) out[0] = (uint8_t)((want & 4) | 0x20);
-        for (uint32_t i = lane; i < U; i += 32) out[hdr + i] = in[i];
-        return hdr + U;
-    }
+    if (overflow) return ENC_FAIL;
+    const uint32_t total = body + ((cap & ~1u) - wp);
     // table, states, then the words moved up behind them
     __syncwarp();
     for (uint32_t i = lane; i < tlen; i += 32) out[hdr + i] = tbl[i];
@@ -304,23 +321,293 @@ __device__ uint32_t encode_stream(EncSmem &s, uint8_t *scratch, const uint8_t *i
     return total;
 }
 
+// Forward copy by the warp; dst may overlap src from below (dst <= src): strides never overtake.
+__device__ void warp_move_down(uint8_t *dst, const uint8_t *src, uint32_t n)
+{
+    const uint32_t lane = hgpu_lane();
+    if (dst == src) return;
+    for (uint32_t i0 = 0; i0 < n; i0 += 32) {
+        const uint32_t i = i0 + lane;
+        const uint8_t v = i < n ? src[i] : 0;
+        __syncwarp();
+        if (i < n) dst[i] = v;
+        __syncwarp();
+    }
+}
+
+// hts_pack (pack.c:56-150) by the warp.  meta gets [nsym][symbols...]; returns nsym (> 16: not packable, nothing
+// else written) and the packed length in plen.
+__device__ uint32_t warp_pack(EncSmem &s, const uint8_t *in, uint32_t n, uint8_t *meta, uint8_t *packed, uint32_t &plen)
+{
+    const uint32_t lane = hgpu_lane();
+    __syncwarp();
+    for (int j = lane; j < 256; j += 32) s.cnt[j] = 0;
+    __syncwarp();
+    for (uint32_t i = lane; i < n; i += 32) s.cnt[in[i]] = 1;            // same value from every writer
+    __syncwarp();
+    uint32_t nsym = 0;
+#pragma unroll
+    for (int k = 0; k < 8; k++) {
+        const uint32_t j = k * 32 + lane, pr = s.cnt[j];
+        const uint32_t bal = __ballot_sync(0xffffffffu, pr != 0);
+        if (pr) { const uint32_t c = nsym + __popc(bal & hgpu_lanemask_lt()); s.idxof[j] = (uint8_t)c; if (c < 16) s.symof[c] = (uint8_t)j; }
+        nsym += __popc(bal);
+    }
+    __syncwarp();
+    if (nsym > 16) return nsym;
+    if (lane == 0) meta[0] = (uint8_t)nsym;
+    if (lane < nsym) meta[1 + lane] = s.symof[lane];
+    const uint32_t per = nsym > 4 ? 2 : nsym > 2 ? 4 : nsym > 1 ? 8 : 0, bits = per ? 8 / per : 0;
+    plen = per ? (n + per - 1) / per : 0;
+    for (uint32_t j = lane; j < plen; j += 32) {
+        uint32_t v = 0;
+        for (uint32_t k = 0; k < per; k++) {
+            const uint32_t i = j * per + k;
+            if (i < n) v |= (uint32_t)s.idxof[in[i]] << (bits * k);
+        }
+        packed[j] = (uint8_t)v;
+    }
+    __syncwarp();
+    return nsym;
+}
+
+// rle_find_syms (rle.c:48-98) + hts_rle_encode (:100-140) by the warp.  meta gets [nsyms][symbols...][run lengths...]
+// (the layout rans_compress_to_4x16 :1462-1465 assembles), lit the literals.
+__device__ void warp_rle(EncSmem &s, const uint8_t *in, uint32_t n, uint8_t *meta, uint8_t *lit, uint32_t &rmeta_len, uint32_t &nlit)
+{
+    const uint32_t lane = hgpu_lane();
+    int *saved = reinterpret_cast<int *>(s.cum);
+    __syncwarp();
+    for (int j = lane; j < 256; j += 32) saved[j] = 0;
+    __syncwarp();
+    for (uint32_t base = 0; base < n; base += 32) {
+        const uint32_t i = base + lane;
+        if (i < n) { const uint8_t b = in[i]; atomicAdd(&saved[b], (i > 0 && in[i - 1] == b) ? 1 : -1); }
+    }
+    __syncwarp();
+    uint32_t nsyms = 0;
+#pragma unroll
+    for (int k = 0; k < 8; k++) {
+        const uint32_t j = k * 32 + lane;
+        const bool in_set = saved[j] > 0;
+        const uint32_t bal = __ballot_sync(0xffffffffu, in_set);
+        s.idxof[j] = in_set ? 1 : 0;
+        if (in_set) meta[1 + nsyms + __popc(bal & hgpu_lanemask_lt())] = (uint8_t)j;
+        nsyms += __popc(bal);
+    }
+    if (lane == 0) meta[0] = (uint8_t)nsyms;                              // 256 wraps to 0 like the reference's store
+    __syncwarp();
+    uint64_t k64, j64;
+    warp_rle_encode(in, n, s.idxof, lit, meta + 1 + nsyms, k64, j64);
+    __syncwarp();
+    nlit = (uint32_t)k64;
+    rmeta_len = (uint32_t)j64 + nsyms + 1;
+}
+
+// rans_compress_to_4x16 without STRIPE (rANS_static4x16pr.c:1378-1565).  Returns bytes written, 0 on failure.
+__device__ uint32_t encode_flat(EncSmem &s, uint8_t *scratch, const XBuf &xb, const uint8_t *in, uint32_t U, uint32_t want,
+                                uint8_t *out, uint32_t cap)
+{
+    const uint32_t lane = hgpu_lane();
+    if (cap < 32) return 0;
+    if (U <= 1000) want &= ~F_X32;                                        // :1239-1242
+    if (U > xb.X) want &= ~(F_PACK | F_RLE);                              // no transform buffers carved for this size
+    uint32_t fmt = want & (F_ORDER | F_X32 | F_NOSZ | F_RLE | F_PACK);
+    uint32_t cm = 1;
+    if (!(want & F_NOSZ)) {
+        if (lane == 0) cm += vput(out + 1, U);
+        cm = __shfl_sync(0xffffffffu, cm, 0);
+    }
+    if (U == 0) {
+        if (lane == 0) out[0] = (uint8_t)(fmt & (F_ORDER | F_X32 | F_NOSZ));
+        return cm;
+    }
+    const uint8_t *cur = in;
+    uint32_t n = U;
+    if (fmt & F_PACK) {
+        if (cm + 280 > cap) return 0;
+        uint32_t plen = 0;
+        const uint32_t nsym = warp_pack(s, cur, n, out + cm, xb.P, plen);
+        if (nsym > 16) fmt &= ~F_PACK;
+        else {
+            cm += nsym + 1;
+            cur = xb.P; n = plen;
+            uint32_t sz = 0;
+            if (lane == 0) sz = vput(out + cm, n);
+            cm += __shfl_sync(0xffffffffu, sz, 0);
+            if ((fmt & F_X32) && n < 32) fmt &= ~F_X32;
+        }
+    }
+    if ((fmt & F_RLE) && n) {
+        uint32_t rmeta = 0, nlit = 0;
+        warp_rle(s, cur, n, xb.M, xb.R, rmeta, nlit);
+        if ((double)nlit + (double)rmeta >= 0.99 * (double)n) fmt &= ~F_RLE;     // not worth it (:1467)
+        else {
+            uint32_t sz = 0;
+            if (lane == 0) { sz = vput(out + cm, rmeta * 2); sz += vput(out + cm + sz, nlit); }
+            sz = __shfl_sync(0xffffffffu, sz, 0);
+            if ((uint64_t)cm + sz + 5 + 64 > cap) return 0;
+            if ((fmt & F_X32) && (rmeta < 32 || nlit < 32)) fmt &= ~F_X32;
+            __syncwarp();
+            __threadfence_block();
+            const uint32_t c = encode_core(s, scratch, xb.M, rmeta, 0, (fmt & F_X32) ? 32 : 4, out + cm + sz + 5, cap - (cm + sz + 5));
+            __syncwarp();
+            if (c != ENC_FAIL && c < rmeta) {
+                uint32_t sz2 = 0;
+                if (lane == 0) sz2 = vput(out + cm + sz, c);
+                sz2 = __shfl_sync(0xffffffffu, sz2, 0);
+                __syncwarp();
+                warp_move_down(out + cm + sz + sz2, out + cm + sz + 5, c);
+                cm += sz + sz2 + c;
+            } else {
+                // run lengths kept as they are: odd length field (:1501-1507)
+                uint32_t sz2 = 0;
+                if (lane == 0) { sz = vput(out + cm, rmeta * 2 + 1); sz2 = vput(out + cm + sz, nlit); }
+                sz = __shfl_sync(0xffffffffu, sz, 0);
+                sz2 = __shfl_sync(0xffffffffu, sz2, 0);
+                if ((uint64_t)cm + sz + sz2 + rmeta > cap) return 0;
+                for (uint32_t i = lane; i < rmeta; i += 32) out[cm + sz + sz2 + i] = xb.M[i];
+                cm += sz + sz2 + rmeta;
+            }
+            cur = xb.R; n = nlit;
+        }
+    } else
+        fmt &= ~F_RLE;
+    uint32_t order = fmt & F_ORDER;
+    if (order && n < 8) { fmt &= ~F_ORDER; order = 0; }                  // :1526-1529
+    if (cm + 4 > cap) return 0;
+    __syncwarp();
+    __threadfence_block();
+    uint32_t c = n ? encode_core(s, scratch, cur, n, order, (fmt & F_X32) ? 32 : 4, out + cm, cap - cm) : ENC_FAIL;
+    __syncwarp();
+    if (c == ENC_FAIL || c >= n) {
+        // CAT fallback (:1539-1553): the (possibly transformed) bytes as they are
+        if ((uint64_t)cm + n > cap) return 0;
+        fmt = (fmt & ~3u) | F_CAT;
+        for (uint32_t i = lane; i < n; i += 32) out[cm + i] = cur[i];
+        c = n;
+    }
+    if (lane == 0) out[0] = (uint8_t)fmt;
+    __syncwarp();
+    return cm + c;
+}
+
+// The STRIPE branch (:1244-1376): N interleaved sub-streams, each coded by the smallest of the methods the caller's
+// order admits (order 1, RLE, PACK, order 0).
+__device__ uint32_t encode_stripe(EncSmem &s, uint8_t *scratch, const XBuf &xb, const uint8_t *in, uint32_t U, uint32_t want,
+                                  uint8_t *out, uint32_t cap)
+{
+    const uint32_t lane = hgpu_lane();
+    uint32_t N = (want >> 8) & 0xff;
+    if (N == 0) N = 4;
+    if (N > U) N = U;
+    const uint32_t q = U / N, r = U % N;
+    if ((uint64_t)7 + 5 * N + 64 > cap) return 0;
+    // transpose: part j takes in[j], in[j + N], ...
+    for (uint32_t i = lane; i < U; i += 32) {
+        const uint32_t j = i % N, x = i / N;
+        xb.S[j * q + min(j, r) + x] = in[i];
+    }
+    uint32_t *lens = reinterpret_cast<uint32_t *>(xb.S + ((U + 3u) & ~3u));
+    uint32_t cm = 0;
+    if (lane == 0) {
+        out[0] = (uint8_t)(want & 0xff & ~F_NOSZ);
+        cm = 1 + vput(out + 1, U);
+        out[cm++] = (uint8_t)N;
+    }
+    cm = __shfl_sync(0xffffffffu, cm, 0);
+    __syncwarp();
+    __threadfence_block();
+    const uint32_t start2 = 7 + 5 * N;
+    uint32_t o2 = start2;
+    const uint32_t methods[4] = {1, 64, 128, 0};
+    XBuf sub = xb;
+    sub.S = nullptr; sub.B = nullptr;
+    for (uint32_t j = 0; j < N; j++) {
+        const uint32_t plen = q + (r > j ? 1u : 0u);
+        const uint8_t *part = xb.S + j * q + min(j, r);
+        uint32_t best = ENC_FAIL;
+        bool in_place = false;
+        for (int t = 0; t < 4; t++) {
+            const uint32_t m = methods[t];
+            if ((want & m) != m) continue;
+            if ((want & F_STRIPE_NO0) && !(m & 1)) continue;
+            if (o2 >= cap) continue;
+            const uint32_t c = encode_flat(s, scratch, sub, part, plen, m | F_NOSZ | (want & F_X32), out + o2, cap - o2);
+            __syncwarp();
+            if (c && c < best && c <= xb.X + XB_PAD_B) {
+                best = c;
+                in_place = true;
+                for (uint32_t i = lane; i < c; i += 32) xb.B[i] = out[o2 + i];
+                __syncwarp();
+            } else
+                in_place = false;
+        }
+        if (best == ENC_FAIL) return 0;
+        if (!in_place) { for (uint32_t i = lane; i < best; i += 32) out[o2 + i] = xb.B[i]; __syncwarp(); }
+        if (lane == 0) lens[j] = best;
+        o2 += best;
+    }
+    __syncwarp();
+    if (lane == 0) for (uint32_t j = 0; j < N; j++) cm += vput(out + cm, lens[j]);
+    cm = __shfl_sync(0xffffffffu, cm, 0);
+    __syncwarp();
+    warp_move_down(out + cm, out + start2, o2 - start2);
+    return cm + (o2 - start2);
+}
+
+__device__ uint32_t encode_stream(EncSmem &s, uint8_t *scratch, const XBuf &xb, const uint8_t *in, uint32_t U, uint32_t want,
+                                  uint8_t *out, uint32_t cap)
+{
+    if (U <= 1000) want &= ~F_X32;
+    if (U <= 20 || U > xb.X) want &= ~F_STRIPE;                          // :1237-1238
+    if (want & F_STRIPE) return encode_stripe(s, scratch, xb, in, U, want, out, cap);
+    if (want & F_CAT) {                                                   // :1378-1392
+        if ((uint64_t)6 + U > cap) return 0;
+        uint32_t cm = 0;
+        if (hgpu_lane() == 0) { out[0] = (uint8_t)F_CAT; cm = 1 + vput(out + 1, U); }
+        cm = __shfl_sync(0xffffffffu, cm, 0);
+        for (uint32_t i = hgpu_lane(); i < U; i += 32) out[cm + i] = in[i];
+        return cm + U;
+    }
+    return encode_flat(s, scratch, xb, in, U, want & ~F_NOSZ, out, cap);
+}
+
 __global__ void __launch_bounds__(32)
 rans_nx16_encode_kernel(const uint8_t *__restrict__ in, const uint64_t *__restrict__ in_off,
                         const uint32_t *__restrict__ in_len, const uint32_t *__restrict__ order, uint32_t n,
                         uint8_t *out, const uint64_t *__restrict__ out_off, const uint32_t *__restrict__ out_cap,
-                        uint32_t *out_len, int32_t *status, uint8_t *scratch, uint32_t *counter)
+                        uint32_t *out_len, int32_t *status, uint8_t *scratch, uint32_t *counter, uint32_t X)
 {
     __shared__ EncSmem s;
-    uint8_t *my = scratch + (size_t)blockIdx.x * ENC_SCRATCH;
+    const size_t per_warp = ENC_SCRATCH + xbuf_bytes(X);
+    uint8_t *my = scratch + (size_t)blockIdx.x * per_warp;
+    XBuf xb;
+    xb.X = X;
+    xb.P = my + ENC_SCRATCH;
+    xb.R = xb.P + X;
+    xb.M = xb.R + X;
+    xb.S = xb.M + X + XB_PAD_M;
+    xb.B = xb.S + X + XB_PAD_S;
     for (;;) {
         uint32_t job = 0;
         if (hgpu_lane() == 0) job = atomicAdd(counter, 1u);
         job = __shfl_sync(0xffffffffu, job, 0);
         if (job >= n) break;
-        uint32_t got = encode_stream(s, my, in + in_off[job], in_len[job], order[job], out + out_off[job], out_cap[job]);
+        uint32_t got = encode_stream(s, my, xb, in + in_off[job], in_len[job], order[job], out + out_off[job], out_cap[job]);
         __syncwarp();
         if (hgpu_lane() == 0) { out_len[job] = got; status[job] = got ? HGPU_OK : HGPU_RANS_ERR; }
     }
+}
+
+// longest input among the jobs that ask for a transform: sizes the per-warp transform buffers
+__global__ void rans_nx16_enc_survey_kernel(const uint32_t *__restrict__ in_len, const uint32_t *__restrict__ order, uint32_t n, uint32_t *res)
+{
+    uint32_t m = 0;
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
+        if (order[i] & (F_PACK | F_RLE | F_STRIPE)) m = max(m, in_len[i]);
+    for (int d = 16; d > 0; d >>= 1) m = max(m, __shfl_xor_sync(0xffffffffu, m, d));
+    if ((threadIdx.x & 31) == 0 && m) atomicMax(res, m);
 }
 
 } // namespace
@@ -329,8 +616,11 @@ extern "C" uint32_t hgpu_rans_nx16_compress_bound(uint32_t size, int order)
 {
     // same shape as rans_compress_bound_4x16 (rANS_static4x16pr.c:1203): payload slack + table + states
     uint64_t b = (uint64_t)(1.05 * size) + 257 * 3 + 4 + 64;
-    if (order & 1) b += 257 * 257 * 3;
+    if (order & 0xff) b += 257 * 257 * 3 + 257 * 3 + 4;               // the reference takes this branch for any flag (:98-100)
     b += (order & 4) ? 32 * 4 : 4 * 4;
+    if (order & 0x80) b += 1 + 280;
+    if (order & 0x40) b += 1 + 257 * 3 + 4 + 64;
+    if (order & 0x08) { uint32_t N = (order >> 8) & 0xff; if (!N) N = 4; b += 7 + 5 * N + (uint64_t)N * 1100; }
     b += 20;
     return b > 0xffffffffull ? 0xffffffffu : (uint32_t)b;
 }
@@ -348,12 +638,26 @@ extern "C" int hgpu_rans_nx16_encode_batch_dev(hgpu_ctx *ctx, const uint8_t *d_i
     if (per_sm < 1) per_sm = 1;
     uint32_t grid = (uint32_t)ctx->sm_count * (uint32_t)per_sm;
     if (grid > n) grid = n;
-    int rc = hgpu_ensure_scratch(ctx, (size_t)grid * ENC_SCRATCH);
+    // PACK / RLE / STRIPE need per-warp buffers as long as the longest such input: the job list lives on the device,
+    // so one word comes back (the only synchronisation of this call)
+    uint32_t *res = hgpu_take_counter(ctx, st);
+    if (!res) return HGPU_ERR_CUDA;
+    rans_nx16_enc_survey_kernel<<<(n + 255) / 256 < 64u ? (n + 255) / 256 : 64u, 256, 0, st>>>(d_in_len, d_order, n, res);
+    hgpu_count_launch();
+    uint32_t maxlen = 0;
+    if (hgpu_check(cudaMemcpyAsync(&maxlen, res, 4, cudaMemcpyDeviceToHost, st), "enc survey copy")) return HGPU_ERR_CUDA;
+    if (hgpu_check(cudaStreamSynchronize(st), "enc survey sync")) return HGPU_ERR_CUDA;
+    const uint32_t X = maxlen ? ((maxlen + 255u) & ~255u) + 256u : 0u;
+    const size_t per_warp = ENC_SCRATCH + xbuf_bytes(X);
+    const size_t budget = (size_t)4 << 30;
+    if ((size_t)grid * per_warp > budget) grid = (uint32_t)(budget / per_warp);
+    if (grid < 1) grid = 1;
+    int rc = hgpu_ensure_scratch(ctx, (size_t)grid * per_warp);
     if (rc) return rc;
     uint32_t *counter = hgpu_take_counter(ctx, st);
     if (!counter) return HGPU_ERR_CUDA;
     rans_nx16_encode_kernel<<<grid, 32, 0, st>>>(d_in, d_in_off, d_in_len, d_order, n, d_out, d_out_off, d_out_cap,
-                                                d_out_len, d_status, ctx->d_scratch, counter);
+                                                d_out_len, d_status, ctx->d_scratch, counter, X);
     hgpu_count_launch();
     return hgpu_check(cudaGetLastError(), "rans encode launch");
 }

@@ -160,8 +160,8 @@ unsigned char *arith_compress(unsigned char *in, unsigned int in_size, unsigned 
     return arith_compress_to(in, in_size, nullptr, out_size, order);
 }
 
-// ---- rANS Nx16 encode (method 5), rANS_static4x16pr.c:1203-1584.  PACK / RLE / STRIPE bits of `order` are not
-// acted on (the stream is coded without those transforms, which every decoder reads); bit 0 and bit 2 are.
+// ---- rANS Nx16 encode (method 5), rANS_static4x16pr.c:1203-1584: every bit of `order` means what it means there
+// (PACK / RLE / STRIPE / CAT / X32 / STRIPE_NO0 in rans_nx16_encode_kernel, SIMD_AUTO here, :1234-1237).
 unsigned int rans_compress_bound_4x16(unsigned int size, int order) { return hgpu_rans_nx16_compress_bound(size, order); }
 
 unsigned char *rans_compress_to_4x16(unsigned char *in, unsigned int in_size, unsigned char *out, unsigned int *out_size, int order)
@@ -173,7 +173,9 @@ unsigned char *rans_compress_to_4x16(unsigned char *in, unsigned int in_size, un
         alloc = out = (unsigned char *)malloc(*out_size);
         if (!out) { *out_size = 0; return nullptr; }
     }
-    const long got = one_stream(ENC_NX16, in, in_size, out, *out_size, (uint32_t)order & 5u);
+    uint32_t ord = (uint32_t)order & 0x1ffffu;
+    if ((order & (1 << 17)) && in_size >= 50000 && !(order & 8)) ord |= 4;          // RANS_ORDER_SIMD_AUTO
+    const long got = one_stream(ENC_NX16, in, in_size, out, *out_size, ord);
     if (got <= 0) { free(alloc); *out_size = 0; return nullptr; }
     *out_size = (unsigned int)got;
     return out;

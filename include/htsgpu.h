@@ -337,11 +337,16 @@ void hgpu_tok3_last_ms(float *ms2);
 uint8_t *tok3_decode_names(uint8_t *in, uint32_t sz, uint32_t *out_len);
 
 /* rANS Nx16 ENCODE — stands where rans_compress_to_4x16 stands (rANS_static4x16pr.c:1203-1579) for
- * a batch of streams, one warp per stream.  order[i]: bit 0 = order-1, bit 2 (value 4) = 32-way
- * (RANS_ORDER_X32); other transform bits are not produced yet.  out_cap[i] >=
- * hgpu_rans_nx16_compress_bound(in_len[i], order[i]).  The output is a complete RANS_PR stream
- * (format byte, size, table, states, words; CAT fallback when that is smaller) that the reference's
- * rans_uncompress_to_4x16 decodes; bytes need not equal the reference encoder's. */
+ * a batch of streams, one warp per stream.  order[i] is the reference's `order` argument
+ * (rANS_static4x16.h:75-103): bit 0 order-1, 0x04 X32 (32-way; dropped for inputs <= 1000 bytes as the
+ * reference does), 0x80 PACK, 0x40 RLE (kept only when it saves >= 1 %, run lengths order-0 coded when
+ * that is smaller), 0x20 CAT, 0x08 STRIPE with N = bits 8-15 (0 = 4; every part coded by the smallest of
+ * the methods the order admits, 1<<16 = never order 0).  out_cap[i] >=
+ * hgpu_rans_nx16_compress_bound(in_len[i], order[i]).  The output is a complete RANS_PR stream that the
+ * reference's rans_uncompress_to_4x16 decodes; the transform decisions follow the reference's rules, the
+ * frequency normalisation is this library's, so bytes need not equal the reference encoder's.  The call
+ * synchronises the stream once (it reads back the longest input that asks for a transform, to size the
+ * per-warp transform buffers). */
 uint32_t hgpu_rans_nx16_compress_bound(uint32_t size, int order);
 int hgpu_rans_nx16_encode_batch_dev(hgpu_ctx *ctx,
         const uint8_t *d_in, const uint64_t *d_in_off, const uint32_t *d_in_len, const uint32_t *d_order,
@@ -456,8 +461,8 @@ unsigned char *arith_compress_to(unsigned char *in, unsigned int in_size, unsign
 unsigned char *arith_compress(unsigned char *in, unsigned int in_size, unsigned int *out_size, int order);
 unsigned char *arith_uncompress_to(unsigned char *in, unsigned int in_size, unsigned char *out, unsigned int *out_size);
 unsigned char *arith_uncompress(unsigned char *in, unsigned int in_size, unsigned int *out_size);
-/* rANS Nx16 encode (rANS_static4x16.h:41-50, :64): order bit 0 (order-1) and bit 2 (32-way) are honoured,
- * the PACK / RLE / STRIPE bits are not acted on; streams decode with any rans_uncompress_to_4x16 */
+/* rANS Nx16 encode (rANS_static4x16.h:41-50, :64): order-1, X32, SIMD_AUTO,
+ * PACK / RLE / STRIPE / CAT follow the reference's rules; streams decode with any rans_uncompress_to_4x16 */
 unsigned int   rans_compress_bound_4x16(unsigned int size, int order);
 unsigned char *rans_compress_to_4x16(unsigned char *in, unsigned int in_size, unsigned char *out, unsigned int *out_size, int order);
 unsigned char *rans_compress_4x16(unsigned char *in, unsigned int in_size, unsigned int *out_size, int order);
