@@ -357,6 +357,90 @@ def cram_scan_blocks(file_np):
     return arr, (maj.value, mnr.value)
 
 
+class CramRefs(C.Structure):
+    _fields_ = [("bases", C.c_void_p), ("off", C.c_void_p), ("n_ref", C.c_int32)]
+
+
+class CramRecords(C.Structure):
+    _fields_ = [("n_records", C.c_uint64), ("data_bytes", C.c_uint64), ("n_slices", C.c_uint32), ("pad", C.c_uint32),
+                ("core", C.c_void_p), ("data", C.c_void_p), ("data_off", C.c_void_p),
+                ("rec_status", C.c_void_p), ("slice_status", C.c_void_p), ("slice_rec0", C.c_void_p)]
+
+
+BAM1_CORE_DT = [("pos", "<i8"), ("tid", "<i4"), ("bin", "<u2"), ("qual", "u1"), ("l_extranul", "u1"), ("flag", "<u2"), ("l_qname", "<u2"),
+                ("n_cigar", "<u4"), ("l_qseq", "<i4"), ("mtid", "<i4"), ("mpos", "<i8"), ("isize", "<i8")]
+
+
+def cram_sq_names(blocks, udata, udata_off):
+    """@SQ SN names of a CRAM file, from its (uncompressed) file header block."""
+    import struct
+    i = [k for k in range(len(blocks)) if int(blocks[k]["content_type"]) == 0][0]
+    o = int(udata_off[i])
+    n = struct.unpack("<i", udata[o:o + 4].tobytes())[0]
+    text = udata[o + 4:o + 4 + n].tobytes()
+    return [[f[3:] for f in line.split(b"\t") if f.startswith(b"SN:")][0] for line in text.split(b"\n") if line.startswith(b"@SQ\t")]
+
+
+def load_fasta_upper(path, names=None):
+    """Reference sequences of a FASTA file, upper case (what cram_get_ref hands the decoder, cram/cram_io.c:3270-3310), in file
+    order or in the order of `names` (the header's @SQ lines; a name the file lacks gets an empty sequence):
+    returns (bases uint8 array, offsets uint64 array of n + 1)."""
+    import numpy as np
+    seqs, cur, order = {}, None, []
+    for line in open(path, "rb"):
+        if line.startswith(b">"):
+            cur = []
+            nm = line[1:].split()[0]
+            seqs[nm] = cur
+            order.append(nm)
+        elif cur is not None:
+            cur.append(line.strip())
+    flat = [np.frombuffer(b"".join(seqs.get(nm, [])), dtype=np.uint8) & 0xdf for nm in (names if names is not None else order)]
+    off = np.zeros(len(flat) + 1, dtype=np.uint64)
+    off[1:] = np.cumsum([len(f) for f in flat])
+    return (np.concatenate(flat) if flat else np.zeros(0, dtype=np.uint8)), off
+
+
+def cram_decode_records(ctx, file_np, blocks, udata, udata_off, fasta=None, prefix=b"", decode_md=0, _entry=None):
+    """Every record of a CRAM 3.x image as bam1_t (hgpu_cram_decode_records_host).  udata / udata_off: the blocks
+    uncompressed (cram_uncompress_blocks).  fasta: (bases, offsets) from load_fasta_upper, or None.
+    Returns dict: core (structured array), data (list of bytes), rec_status, slice_status, slice_rec0."""
+    import numpy as np
+    L = lib()
+    refs = CramRefs()
+    keep = None
+    if fasta is not None:
+        keep = (np.ascontiguousarray(fasta[0]), np.ascontiguousarray(fasta[1]))
+        refs.bases = keep[0].ctypes.data; refs.off = keep[1].ctypes.data; refs.n_ref = len(keep[1]) - 1
+    out = CramRecords()
+    if _entry is None:
+        L.hgpu_cram_decode_records_host.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p,
+                                                    C.c_void_p, C.c_char_p, C.c_int, C.c_void_p]
+        rc = L.hgpu_cram_decode_records_host(ctx.h, file_np.ctypes.data, file_np.size, blocks.ctypes.data, len(blocks), udata.ctypes.data,
+                                             udata_off.ctypes.data, C.byref(refs) if fasta is not None else None, prefix, decode_md, C.byref(out))
+        free, err = L.hgpu_cram_records_free, last_error
+    else:
+        fn, free, err = _entry
+        rc = fn(file_np.ctypes.data, file_np.size, blocks.ctypes.data, len(blocks), udata.ctypes.data, udata_off.ctypes.data,
+                C.byref(refs) if fasta is not None else None, prefix, decode_md, C.byref(out))
+    if rc != 0:
+        raise HgpuError("cram_decode_records: %d %s" % (rc, err()))
+    n, ns = out.n_records, out.n_slices
+    def arr(ptr, count, dt):
+        if not count:
+            return np.zeros(0, dtype=dt)
+        return np.frombuffer((C.c_uint8 * (count * np.dtype(dt).itemsize)).from_address(ptr), dtype=dt).copy()
+    core = arr(out.core, n, np.dtype(BAM1_CORE_DT))
+    doff = arr(out.data_off, n + 1, np.uint64)
+    blob = arr(out.data, out.data_bytes, np.uint8).tobytes()
+    res = {"core": core, "data": [blob[int(doff[i]):int(doff[i + 1])] for i in range(n)], "rec_status": arr(out.rec_status, n, np.int32),
+           "slice_status": arr(out.slice_status, ns, np.int32), "slice_rec0": arr(out.slice_rec0, ns + 1, np.uint64)}
+    free.argtypes = [C.c_void_p]
+    free(C.byref(out))
+    return res
+
+
+
 def bgzf_scan(file_np):
     """BSIZE-chain walk: returns (off u64[n], len u32[n], isize u32[n]) or raises on a bad block."""
     import numpy as np

@@ -21,6 +21,13 @@
 #endif
 #endif
 
+#if defined(HGPU_HOSTSIM) && defined(CRAMREC_TRACE_ON)
+#include <stdio.h>
+#define CRAMREC_TRACE(...) fprintf(stderr, __VA_ARGS__)
+#else
+#define CRAMREC_TRACE(...) ((void)0)
+#endif
+
 namespace cramrec {
 
 enum DS { DS_BF, DS_CF, DS_RI, DS_RL, DS_AP, DS_RG, DS_RN, DS_MF, DS_NS, DS_NP, DS_TS, DS_NF, DS_TL, DS_FN, DS_FC, DS_FP, DS_DL,
@@ -207,7 +214,25 @@ struct SliceDec {
         default: return -1;
         }
     }
-    // type BYTE / BYTE_ARRAY value codecs: n items to out (may be null: consume only)
+    // one item of a BYTE series, returned to every lane (FC, BS, single BA / QS)
+    CRAMREC_HD int get_byte(const Codec &c, uint8_t &out)
+    {
+        switch (c.kind) {
+        case K_EXTERNAL: {
+            if (ext[c.a].size == 0xffffffffu) return -1;
+            const uint8_t *p = ext_take(c.a, 1);
+            if (!p) return -1;
+            out = *p;
+            return 0; }
+        case K_HUFFMAN: { int32_t s2 = 0; if (huff_one(c, s2)) return -1; out = (uint8_t)s2; return 0; }
+        case K_BETA:
+            if (c.b) { if (not_enough_bits(c.b)) return -1; out = (uint8_t)(get_bits(c.b) - c.a); }
+            else out = (uint8_t)(-c.a);
+            return 0;
+        default: return -1;
+        }
+    }
+    // type BYTE / BYTE_ARRAY value codecs: n items to out in memory (may be null: consume only)
     CRAMREC_HD int get_bytes(const Codec &c, uint8_t *out, int32_t n)
     {
         switch (c.kind) {
@@ -236,7 +261,7 @@ struct SliceDec {
     }
     CRAMREC_HD bool append(uint8_t *&base, uint32_t &size, uint32_t cap, const uint8_t *src, uint32_t n)
     {
-        if ((uint64_t)size + n > cap) { err = ERR_SPACE; return false; }
+        if ((uint64_t)size + n > cap) { CRAMREC_TRACE("append: %u + %u > %u\n", size, n, cap); err = ERR_SPACE; return false; }
         W::copy(base + size, src, n);
         size += n;
         return true;
@@ -270,19 +295,8 @@ struct SliceDec {
         return -1;
     }
     // E_BYTE_ARRAY_BLOCK series (RN, tags): appended to an arena
-    CRAMREC_HD int get_array_block(const Codec &c, uint8_t *&base, uint32_t &size, uint32_t cap, int32_t &out_sz)
+    CRAMREC_HD int block_leaf(const Codec &c, uint8_t *&base, uint32_t &size, uint32_t cap, int32_t &out_sz)
     {
-        if (c.kind == K_BYTE_ARRAY_LEN) {
-            int32_t len = 0;
-            const Codec &vc = P.cpool[c.b];
-            const int r = get_int(P.cpool[c.a], len);
-            if (len < 0 || (len > out_sz && vc.kind != K_EXTERNAL)) return -1;
-            if (r) return -1;
-            int32_t l2 = len;
-            const int r2 = get_array_block(vc, base, size, cap, l2);
-            out_sz = len;
-            return r2;
-        }
         if (c.kind == K_EXTERNAL) {                                         // cram_external_decode_block
             if (ext[c.a].size == 0xffffffffu) return out_sz ? -1 : 0;
             const uint8_t *p = ext_take(c.a, out_sz);
@@ -303,9 +317,24 @@ struct SliceDec {
         }
         return -1;
     }
+    CRAMREC_HD int get_array_block(const Codec &c, uint8_t *&base, uint32_t &size, uint32_t cap, int32_t &out_sz)
+    {
+        if (c.kind == K_BYTE_ARRAY_LEN) {
+            int32_t len = 0;
+            const Codec &vc = P.cpool[c.b];
+            const int r = get_int(P.cpool[c.a], len);
+            if (len < 0 || (len > out_sz && vc.kind != K_EXTERNAL)) return -1;
+            if (r) return -1;
+            int32_t l2 = len;
+            const int r2 = block_leaf(vc, base, size, cap, l2);            // the tables only admit EXTERNAL / BYTE_ARRAY_STOP here
+            out_sz = len;
+            return r2;
+        }
+        return block_leaf(c, base, size, cap, out_sz);
+    }
 
     // ---- small appenders for MD / cigar ----
-    CRAMREC_HD bool aux_char(uint8_t c) { if (aux_size >= aux_cap) { err = ERR_SPACE; return false; } aux[aux_size++] = c; return true; }
+    CRAMREC_HD bool aux_char(uint8_t c) { if (aux_size >= aux_cap) { CRAMREC_TRACE("aux_char full %u\n", aux_cap); err = ERR_SPACE; return false; } aux[aux_size++] = c; return true; }
     CRAMREC_HD bool aux_uint(uint32_t v)                                    // BLOCK_APPEND_UINT: decimal
     {
         uint8_t tmp[10]; int n = 0;
@@ -321,7 +350,7 @@ struct SliceDec {
     }
     CRAMREC_HD bool cig_push(uint32_t len, uint32_t op)
     {
-        if (ncigar >= cig_cap) { err = ERR_SPACE; return false; }
+        if (ncigar >= cig_cap) { CRAMREC_TRACE("cigar full %u\n", cig_cap); err = ERR_SPACE; return false; }
         cigar[ncigar++] = (len << 4) + op;
         return true;
     }
@@ -359,8 +388,7 @@ struct SliceDec {
             int32_t pos = 0;
             uint8_t op = 0;
             if (ncigar + 2 >= cig_cap) { err = ERR_SPACE; return -1; }
-            if (get_bytes(C[DS_FC], &op, 1)) return -1;
-            W::sync();
+            if (get_byte(C[DS_FC], op)) return -1;
             if (get_int(C[DS_FP], pos)) return -1;
             pos += prev_pos;
             if (pos <= 0) return -1;
@@ -417,8 +445,7 @@ struct SliceDec {
                 uint8_t base = 0;
                 if (cig_len && cig_op != CIG_M) { if (!cig_push(cig_len, cig_op)) return -1; cig_len = 0; }
                 if (C[DS_BS].kind == K_NONE) return -1;
-                if (get_bytes(C[DS_BS], &base, 1)) return -1;
-                W::sync();
+                if (get_byte(C[DS_BS], base)) return -1;
                 if (cr.ref_id < 0 || ref_pos >= sq_len(cr.ref_id) || !ref) {
                     if (pos - 1 < cr.len) seq[pos - 1] = T->sub[4][base & 3];
                     if (decode_md || decode_nm) {
@@ -478,7 +505,7 @@ struct SliceDec {
             case 'i': {
                 if (cig_len && cig_op != CIG_I) { if (!cig_push(cig_len, cig_op)) return -1; cig_len = 0; }
                 if (C[DS_BA].kind == K_NONE) return -1;
-                if (get_bytes(C[DS_BA], cr.len ? &seq[pos - 1] : nullptr, 1)) return -1;
+                { uint8_t b1 = 0; if (get_byte(C[DS_BA], b1)) return -1; if (cr.len) seq[pos - 1] = b1; }
                 cig_op = CIG_I;
                 cig_len++; seq_pos++; nm++;
                 break; }
@@ -515,7 +542,9 @@ struct SliceDec {
             case 'B': {
                 if (cig_len && cig_op != CIG_M) { if (!cig_push(cig_len, cig_op)) return -1; cig_len = 0; }
                 if (C[DS_BA].kind == K_NONE) return -1;
-                const int rb = get_bytes(C[DS_BA], cr.len ? &seq[pos - 1] : nullptr, 1);
+                uint8_t b1 = 0, q1 = 0;
+                const int rb = get_byte(C[DS_BA], b1);
+                if (!rb && cr.len) seq[pos - 1] = b1;
                 if (decode_md || decode_nm) {
                     if (md_dist >= 0 && decode_md) { if (!aux_uint((uint32_t)md_dist)) return -1; }
                     if (ref_pos >= sq_len(cr.ref_id) || !ref) md_dist = -1;
@@ -530,7 +559,8 @@ struct SliceDec {
                 }
                 if (C[DS_QS].kind == K_NONE) return -1;
                 if (!pres_q && cr.len > 0 && qual[0] == 255) W::fill(qual, 30, (uint32_t)cr.len);
-                const int rq = get_bytes(C[DS_QS], cr.len ? &qual[pos - 1] : nullptr, 1);
+                const int rq = get_byte(C[DS_QS], q1);
+                if (!rq && cr.len) qual[pos - 1] = q1;
                 if (rb | rq) return -1;                                    // the reference ORs r and fails the record at the end
                 cig_op = CIG_M;
                 cig_len++; seq_pos++; ref_pos++;
@@ -538,7 +568,7 @@ struct SliceDec {
             case 'Q': {
                 if (C[DS_QS].kind == K_NONE) return -1;
                 if (!pres_q && cr.len > 0 && qual[0] == 255) W::fill(qual, 30, (uint32_t)cr.len);
-                if (get_bytes(C[DS_QS], cr.len ? &qual[pos - 1] : nullptr, 1)) return -1;
+                { uint8_t q1 = 0; if (get_byte(C[DS_QS], q1)) return -1; if (cr.len) qual[pos - 1] = q1; }
                 break; }
             case 'H': case 'P': case 'N': {
                 const uint32_t cop = op == 'H' ? CIG_H : op == 'P' ? CIG_P : CIG_N;
@@ -778,7 +808,7 @@ struct SliceDec {
             cr.aux = aux_size; cr.aux_size = 0;
             if (decode_aux(cr, has_MD, has_NM)) return err ? err : ERR_DECODE;
 
-            if ((uint64_t)sq_size + (uint32_t)cr.len > sq_cap) return ERR_SPACE;
+            if ((uint64_t)sq_size + (uint32_t)cr.len > sq_cap) { CRAMREC_TRACE("seq full %u + %d > %u\n", sq_size, cr.len, sq_cap); return ERR_SPACE; }
             cr.seq = cr.qual = sq_size;
             uint8_t *seq = seqs + sq_size, *qual = quals + sq_size;
             sq_size += (uint32_t)cr.len;

@@ -431,6 +431,35 @@ int hgpu_bam_layout_dev(hgpu_ctx *ctx, const uint8_t *d_stream, uint64_t len,
                         const uint64_t *d_rec_off, uint64_t n,
                         uint64_t *d_data_off, uint64_t *d_seq_off, void *stream);
 
+/* CRAM 3.x record decode on the device — cram_decode_slice's record loop (cram/cram_decode.c:2340-3015), cram_decode_seq
+ * (:1096-1917), cram_decode_aux (:2008-2137), cram_decode_slice_xref (:2140-2304) and cram_to_bam (:3100-3211) for every
+ * slice of a file image at once: one warp per slice walks the data series (EXTERNAL / HUFFMAN / BETA / SUBEXP / GAMMA /
+ * BYTE_ARRAY_LEN / BYTE_ARRAY_STOP, CORE bit stream included), rebuilds SEQ from the reference and the read features,
+ * CIGAR, MD/NM when asked, mate cross references and template lengths; one warp per record then lays down bam1_t.
+ *   file / blocks: the CRAM image and what hgpu_cram_scan_blocks listed; udata + udata_off[i]: block i uncompressed
+ *   (hgpu_cram_uncompress_blocks_host's `out` / `out_off`).  @SQ lengths and @RG ids are read from the file header block.
+ *   refs: the reference sequences in @SQ order, upper case, back to back (NULL or bases == NULL: only slices that
+ *   need no external reference decode; the others come back HGPU_CRAM_ERR_NOREF).  The slice MD5 is not checked.
+ *   name_prefix: the reference's fd->prefix (file base name) for generated read names.  decode_md: CRAM_OPT_DECODE_MD.
+ * Result (host arrays, malloc'd; hgpu_cram_records_free): record r of the file, in file order, is core[r] +
+ * data[data_off[r] .. data_off[r+1]) exactly as sam_read1 / cram_get_bam_seq returns it; rec_status[r] != 0 where
+ * cram_to_bam fails.  slice_status[s]: HGPU_OK; HGPU_CRAM_ERR_DECODE (the reference fails on this slice);
+ * HGPU_CRAM_UNSUPPORTED (an encoding the device tables do not model) / HGPU_CRAM_ERR_SPACE (an arena bound computed
+ * from the container header was too small) / HGPU_CRAM_ERR_NOREF: the slice's records are empty and stay with the
+ * host library.  slice_rec0[s]: first record of slice s (n_slices + 1 entries). */
+#define HGPU_CRAM_ERR_NOREF (-7)
+typedef struct hgpu_cram_refs { const uint8_t *bases; const uint64_t *off; int32_t n_ref; } hgpu_cram_refs;
+typedef struct hgpu_cram_records {
+    uint64_t n_records, data_bytes;
+    uint32_t n_slices, pad;
+    hgpu_bam1_core *core; uint8_t *data; uint64_t *data_off;
+    int32_t *rec_status, *slice_status; uint64_t *slice_rec0;
+} hgpu_cram_records;
+int hgpu_cram_decode_records_host(hgpu_ctx *ctx, const uint8_t *file, uint64_t file_len,
+        const hgpu_cram_block *blocks, uint32_t n_blocks, const uint8_t *udata, const uint64_t *udata_off,
+        const hgpu_cram_refs *refs, const char *name_prefix, int decode_md, hgpu_cram_records *out);
+void hgpu_cram_records_free(hgpu_cram_records *r);
+
 /* ------------------------------------------------------------------------------------------
  * Reference-named shims (link seam B1: `./configure --with-external-htscodecs`, configure.ac:278).
  * Same signatures, same malloc/free ownership, same NULL-on-error as htscodecs

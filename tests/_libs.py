@@ -461,3 +461,78 @@ def orc_arith_decode(comp, cap):
     n = C.c_uint32(cap)
     rc = o.orc_arith_decode(buf(comp), C.c_uint32(len(comp)), out, C.byref(n))
     return None if rc != 0 else bytes(out[: n.value])
+
+
+def ref_cram_read_all(path, fasta=None, decode_md=0):
+    """Every record of a CRAM file through the compiled reference: hts_open + sam_hdr_read + sam_read1 (-> cram_get_bam_seq).
+    Returns list of (core tuple, data bytes)."""
+    r = ref()
+    r.hts_open.restype = C.c_void_p
+    r.hts_open.argtypes = [C.c_char_p, C.c_char_p]
+    r.hts_close.argtypes = [C.c_void_p]
+    r.sam_hdr_read.restype = C.c_void_p
+    r.sam_hdr_read.argtypes = [C.c_void_p]
+    r.sam_hdr_destroy.argtypes = [C.c_void_p]
+    r.sam_read1.argtypes = [C.c_void_p, C.c_void_p, C.POINTER(Bam1)]
+    r.bam_init1.restype = C.POINTER(Bam1)
+    r.bam_destroy1.argtypes = [C.POINTER(Bam1)]
+    fp = r.hts_open(path.encode(), b"r")
+    assert fp, path
+    if fasta:
+        r.hts_set_fai_filename.argtypes = [C.c_void_p, C.c_char_p]
+        assert r.hts_set_fai_filename(fp, fasta.encode()) == 0
+    r.hts_set_opt.argtypes = [C.c_void_p, C.c_int, C.c_int]
+    r.hts_set_opt(fp, 0, int(decode_md))                       # CRAM_OPT_DECODE_MD, hts.h:297
+    hdr = r.sam_hdr_read(fp)
+    assert hdr
+    b = r.bam_init1()
+    out = []
+    while True:
+        rc = r.sam_read1(fp, hdr, b)
+        if rc < 0:
+            assert rc == -1, rc
+            break
+        out.append((b.contents.core.astuple(), bytes(b.contents.data[: b.contents.l_data])))
+    r.bam_destroy1(b)
+    r.sam_hdr_destroy(hdr)
+    r.hts_close(fp)
+    return out
+
+
+def ref_write_cram(sam_path, fasta, out_path, version="3.0", int_opts=()):
+    """SAM -> CRAM through the compiled reference (hts_open "wc", sam_write1).  int_opts: (hts_fmt_option, int) pairs."""
+    r = ref()
+    r.hts_open.restype = C.c_void_p
+    r.hts_open.argtypes = [C.c_char_p, C.c_char_p]
+    r.hts_close.argtypes = [C.c_void_p]
+    r.sam_hdr_read.restype = C.c_void_p
+    r.sam_hdr_read.argtypes = [C.c_void_p]
+    r.sam_hdr_write.argtypes = [C.c_void_p, C.c_void_p]
+    r.sam_hdr_destroy.argtypes = [C.c_void_p]
+    r.sam_read1.argtypes = [C.c_void_p, C.c_void_p, C.POINTER(Bam1)]
+    r.sam_write1.argtypes = [C.c_void_p, C.c_void_p, C.POINTER(Bam1)]
+    r.bam_init1.restype = C.POINTER(Bam1)
+    r.bam_destroy1.argtypes = [C.POINTER(Bam1)]
+    fo = r.hts_open(out_path.encode(), b"wc")
+    assert fo
+    r.hts_set_opt.argtypes = [C.c_void_p, C.c_int, C.c_char_p]
+    assert r.hts_set_opt(fo, 6, version.encode()) == 0                 # CRAM_OPT_VERSION
+    if fasta:
+        assert r.hts_set_opt(fo, 9, fasta.encode()) == 0               # CRAM_OPT_REFERENCE
+    r.hts_set_opt.argtypes = [C.c_void_p, C.c_int, C.c_int]
+    for opt, val in int_opts:
+        assert r.hts_set_opt(fo, opt, val) == 0
+    fi = r.hts_open(sam_path.encode(), b"r")
+    assert fi
+    h = r.sam_hdr_read(fi)
+    assert h and r.sam_hdr_write(fo, h) == 0
+    b = r.bam_init1()
+    n = 0
+    while r.sam_read1(fi, h, b) >= 0:
+        assert r.sam_write1(fo, h, b) >= 0
+        n += 1
+    r.bam_destroy1(b)
+    r.hts_close(fi)
+    assert r.hts_close(fo) == 0
+    r.sam_hdr_destroy(h)
+    return n

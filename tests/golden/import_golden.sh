@@ -16,4 +16,5 @@ cp -r $REF/test/bgzf_boundaries $D/htslib/
 cp $REF/test/ce#1.sam $REF/test/ce#1000.sam $REF/test/ce.fa $REF/test/ce.fa.fai $D/htslib/ 2>/dev/null || true
 cp $REF/test/range.bam $REF/test/colons.bam $D/htslib/ 2>/dev/null || true
 cp $REF/test/range.cram $REF/test/*_java.cram $D/htslib/ 2>/dev/null || true   # foreign-writer CRAM 3.0 files
+cp $REF/test/xx.fa $REF/test/xx.fa.fai $REF/test/auxf.fa $REF/test/auxf.fa.fai $D/htslib/ 2>/dev/null || true   # their references
 chmod -R u+w $D
