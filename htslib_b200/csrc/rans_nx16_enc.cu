@@ -208,7 +208,21 @@ __device__ uint32_t encode_core(EncSmem &s, uint8_t *scratch, const uint8_t *in,
         tlen = __shfl_sync(0xffffffffu, tlen, 0);
         for (uint32_t r = 0; r < A; r++) {
             uint32_t *row = tab + r * A;
-            if (!normalise_row(row, (int)A, 1u << shift)) return ENC_FAIL;
+            // a row that totals well under 2^shift is stored normalised to a smaller power of two and shifted up on both
+            // sides (rans_compute_shift :376-387, normalise_freq_shift): smaller varints in the table text
+            uint32_t trow = 0, ns = 0;
+            for (uint32_t k = lane; k < A; k += 32) { trow += row[k]; ns += row[k] != 0; }
+            for (int d = 16; d > 0; d >>= 1) { trow += __shfl_xor_sync(0xffffffffu, trow, d); ns += __shfl_xor_sync(0xffffffffu, ns, d); }
+            uint32_t max_val = 1u << shift, up = 0;
+            if (trow) {
+                uint32_t m2 = 1;
+                while (m2 < trow) m2 <<= 1;                          // round2
+                if (ns < 64 && m2 > 128) m2 >>= 1;
+                if (m2 > 1024) m2 >>= 1;
+                while (m2 < ns) m2 <<= 1;
+                if (m2 < max_val) { max_val = m2; while ((max_val << up) < (1u << shift)) up++; }
+            }
+            if (!normalise_row(row, (int)A, max_val)) return ENC_FAIL;
             __syncwarp();
             if (lane == 0) {
                 uint8_t *cp = tbl + tlen;
@@ -224,7 +238,7 @@ __device__ uint32_t encode_core(EncSmem &s, uint8_t *scratch, const uint8_t *in,
                 tlen = (uint32_t)(cp - tbl);
                 // row -> {f | start<<16}
                 uint32_t x = 0;
-                for (uint32_t k = 0; k < A; k++) { uint32_t f = row[k]; row[k] = f | (x << 16); x += f; }
+                for (uint32_t k = 0; k < A; k++) { uint32_t f = row[k] << up; row[k] = f | (x << 16); x += f; }
             }
             tlen = __shfl_sync(0xffffffffu, tlen, 0);
             __syncwarp();

@@ -134,3 +134,89 @@ def test_gpu_written_by_reference(tmp_path, shape):
             assert len(got["data"]) == n
             compare(sam, fa, got, decode_md, path=out)
     ctx.close()
+
+
+def _synthetic_sam(path, n=10000, seed=3):
+    """A coordinate-sorted paired-end SAM over CHROMOSOME_I of ce.fa: matches, substitutions, insertions, deletions, reference skips,
+    soft / hard clips, unmapped mates, several read groups and aux tag types — every read feature code the writer emits."""
+    import random
+    rng = random.Random(seed)
+    fa = H.load_fasta_upper(os.path.join(HT, "ce.fa"))
+    chrom = fa[0][:int(fa[1][1])].tobytes()
+    recs = []
+    shapes = [[(100, "M")], [(5, "S"), (95, "M")], [(40, "M"), (2, "I"), (58, "M")], [(50, "M"), (3, "D"), (50, "M")], [(30, "M"), (200, "N"), (70, "M")],
+              [(10, "H"), (90, "M"), (10, "S")], [(100, "M")], [(100, "M")], [(60, "M"), (1, "I"), (20, "M"), (1, "D"), (19, "M")]]
+    pos = 1000
+    for i in range(n // 2):
+        pos += rng.randrange(1, 150)
+        ends = []
+        for which in (0, 1):
+            p = pos + which * rng.randrange(150, 400)
+            sh = rng.choice(shapes)
+            seq, rp = [], p - 1
+            for l, op in sh:
+                if op in "M":
+                    seq.append(chrom[rp:rp + l].decode()); rp += l
+                elif op in "IS":
+                    seq.append("".join(rng.choice("ACGT") for _ in range(l)))
+                elif op in "DN":
+                    rp += l
+            s = list("".join(seq))
+            for _ in range(rng.choice([0, 0, 1, 2, 5])):
+                s[rng.randrange(len(s))] = rng.choice("ACGTN")
+            q = "".join(chr(33 + rng.choice([2, 12, 23, 37])) for _ in s)
+            ends.append((p, "".join("%d%s" % t for t in sh), "".join(s), q, rp))
+        unm = rng.random() < 0.03
+        for which in (0, 1):
+            p, cig, s, q, rp = ends[which]
+            mp = ends[1 - which][0]
+            flag = 1 | (64 if which == 0 else 128) | (16 if which else 32)
+            if unm and which == 1:
+                flag = 1 | 128 | 4 | 32; cig = "*"; p = ends[0][0]
+            if unm and which == 0:
+                flag |= 8
+            lo, hi = min(ends[0][0], ends[1][0]), max(ends[0][4], ends[1][4])
+            tlen = 0 if unm else (hi - lo + 1) * (1 if p == lo and which == 0 else -1 if which == 1 else 1)
+            tags = ["RG:Z:g%d" % rng.randrange(3), "NH:i:%d" % rng.randrange(1, 300), "XA:A:%s" % rng.choice("xyz")]
+            if rng.random() < 0.3: tags.append("XB:B:s,%d,%d,-7" % (rng.randrange(100), rng.randrange(40000) - 20000))
+            if rng.random() < 0.2: tags.append("XZ:Z:" + "".join(rng.choice("abc:;") for _ in range(rng.randrange(0, 20))))
+            recs.append((p, "r%06d\t%d\tCHROMOSOME_I\t%d\t%d\t%s\t=\t%d\t%d\t%s\t%s\t%s" % (i, flag, p, rng.randrange(0, 61), cig, mp if not (unm and which == 0) else p, tlen, s, q, "\t".join(tags))))
+    recs.sort(key=lambda t: t[0])
+    with open(path, "w") as f:
+        f.write("@HD\tVN:1.4\tSO:coordinate\n@SQ\tSN:CHROMOSOME_I\tLN:1009800\n@RG\tID:g0\tSM:a\n@RG\tID:g1\tSM:a\n@RG\tID:g2\tSM:b\n")
+        for _, line in recs:
+            f.write(line + "\n")
+    return len(recs)
+
+
+def _synthetic_case(tmp_path, entry_ctx, version, opts):
+    sam = str(tmp_path / "syn.sam")
+    n = _synthetic_sam(sam)
+    out = str(tmp_path / "syn.cram")
+    assert ref_write_cram(sam, os.path.join(HT, "ce.fa"), out, version, opts) == n
+    img = np.fromfile(out, dtype=np.uint8)
+    blocks, udata, off = cpu_blocks(img)
+    fasta = H.load_fasta_upper(os.path.join(HT, "ce.fa"), H.cram_sq_names(blocks, udata, off))
+    for decode_md in (0, 1):
+        if entry_ctx is None:
+            got = H.cram_decode_records(None, img, blocks, udata, off, fasta, b"syn.cram", decode_md, _entry=hostsim())
+        else:
+            got = H.cram_decode_records(entry_ctx, img, blocks, udata, off, fasta, b"syn.cram", decode_md)
+        assert len(got["data"]) == n
+        compare("syn", "ce.fa", got, decode_md, path=out)
+    return len(got["slice_status"])
+
+
+@pytest.mark.skipif(ref() is None, reason="oracle/_ref not built")
+def test_hostsim_synthetic_10000_read_slice(tmp_path):
+    assert _synthetic_case(tmp_path, None, "3.1", []) == 1
+    assert _synthetic_case(tmp_path, None, "3.0", [(SEQS, 700), (LOSSY, 1)]) == 15
+
+
+@pytest.mark.gpu
+@pytest.mark.skipif(ref() is None, reason="oracle/_ref not built")
+def test_gpu_synthetic_10000_read_slice(tmp_path):
+    ctx = H.Context(0)
+    assert _synthetic_case(tmp_path, ctx, "3.1", []) == 1
+    assert _synthetic_case(tmp_path, ctx, "3.0", [(SEQS, 700), (LOSSY, 1)]) == 15
+    ctx.close()
