@@ -401,6 +401,40 @@ def load_fasta_upper(path, names=None):
     return (np.concatenate(flat) if flat else np.zeros(0, dtype=np.uint8)), off
 
 
+def _records_out(out, free):
+    import numpy as np
+    n, ns = out.n_records, out.n_slices
+    def arr(ptr, count, dt):
+        if not count:
+            return np.zeros(0, dtype=dt)
+        return np.frombuffer((C.c_uint8 * (count * np.dtype(dt).itemsize)).from_address(ptr), dtype=dt).copy()
+    core = arr(out.core, n, np.dtype(BAM1_CORE_DT))
+    doff = arr(out.data_off, n + 1, np.uint64)
+    blob = arr(out.data, out.data_bytes, np.uint8).tobytes()
+    res = {"core": core, "data": [blob[int(doff[i]):int(doff[i + 1])] for i in range(n)], "rec_status": arr(out.rec_status, n, np.int32),
+           "slice_status": arr(out.slice_status, ns, np.int32), "slice_rec0": arr(out.slice_rec0, ns + 1, np.uint64)}
+    free.argtypes = [C.c_void_p]
+    free(C.byref(out))
+    return res
+
+
+def cram_decode_file(ctx, file_np, fasta=None, prefix=b"", decode_md=0):
+    """hgpu_cram_decode_file_host: scan + uncompress + record decode of a CRAM file image in one call."""
+    import numpy as np
+    L = lib()
+    refs = CramRefs()
+    keep = None
+    if fasta is not None:
+        keep = (np.ascontiguousarray(fasta[0]), np.ascontiguousarray(fasta[1]))
+        refs.bases = keep[0].ctypes.data; refs.off = keep[1].ctypes.data; refs.n_ref = len(keep[1]) - 1
+    out = CramRecords()
+    L.hgpu_cram_decode_file_host.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p, C.c_char_p, C.c_int, C.c_void_p]
+    rc = L.hgpu_cram_decode_file_host(ctx.h, file_np.ctypes.data, file_np.size, C.byref(refs) if fasta is not None else None, prefix, decode_md, C.byref(out))
+    if rc != 0:
+        raise HgpuError("cram_decode_file: %d %s" % (rc, last_error()))
+    return _records_out(out, L.hgpu_cram_records_free)
+
+
 def cram_decode_records(ctx, file_np, blocks, udata, udata_off, fasta=None, prefix=b"", decode_md=0, _entry=None):
     """Every record of a CRAM 3.x image as bam1_t (hgpu_cram_decode_records_host).  udata / udata_off: the blocks
     uncompressed (cram_uncompress_blocks).  fasta: (bases, offsets) from load_fasta_upper, or None.
@@ -425,19 +459,7 @@ def cram_decode_records(ctx, file_np, blocks, udata, udata_off, fasta=None, pref
                 C.byref(refs) if fasta is not None else None, prefix, decode_md, C.byref(out))
     if rc != 0:
         raise HgpuError("cram_decode_records: %d %s" % (rc, err()))
-    n, ns = out.n_records, out.n_slices
-    def arr(ptr, count, dt):
-        if not count:
-            return np.zeros(0, dtype=dt)
-        return np.frombuffer((C.c_uint8 * (count * np.dtype(dt).itemsize)).from_address(ptr), dtype=dt).copy()
-    core = arr(out.core, n, np.dtype(BAM1_CORE_DT))
-    doff = arr(out.data_off, n + 1, np.uint64)
-    blob = arr(out.data, out.data_bytes, np.uint8).tobytes()
-    res = {"core": core, "data": [blob[int(doff[i]):int(doff[i + 1])] for i in range(n)], "rec_status": arr(out.rec_status, n, np.int32),
-           "slice_status": arr(out.slice_status, ns, np.int32), "slice_rec0": arr(out.slice_rec0, ns + 1, np.uint64)}
-    free.argtypes = [C.c_void_p]
-    free(C.byref(out))
-    return res
+    return _records_out(out, free)
 
 
 

@@ -489,6 +489,7 @@ CRAMREC_HD void fill_body(const Args &A, uint64_t g)
 }
 
 #ifndef HGPU_HOSTSIM
+float g_last_ms[2] = {0, 0};                    // device time of the two kernels of the last call (bench.py reads it)
 __global__ void __launch_bounds__(32) cram_slice_decode_kernel(Args A)
 {
     if (blockIdx.x < A.n_slices) slice_body<WarpW>(A, blockIdx.x, threadIdx.x & 31, 32);
@@ -722,7 +723,16 @@ int decode_impl(hgpu_ctx *ctx, const uint8_t *file, uint64_t file_len, const hgp
 #else
     if (cudaMemsetAsync(base + s_cur.off, 0, ext.size() * 4 + 4, st) != cudaSuccess) up_fail = true;
     if (up_fail) { hgpu_set_error("cram records: upload failed: %s", cudaGetErrorString(cudaGetLastError())); return HGPU_ERR_CUDA; }
+    struct Events {                                  // destroyed on every return path
+        cudaEvent_t e[4]; int n = 0;
+        bool make() { for (; n < 4; n++) if (cudaEventCreate(&e[n]) != cudaSuccess) return false; return true; }
+        ~Events() { for (int k = 0; k < n; k++) cudaEventDestroy(e[k]); }
+    } evs;
+    if (!evs.make()) return HGPU_ERR_CUDA;
+    cudaEvent_t *ev = evs.e;
+    cudaEventRecord(ev[0], st);
     cram_slice_decode_kernel<<<ns, 32, 0, st>>>(A);
+    cudaEventRecord(ev[1], st);
     hgpu_count_launch();
     if (hgpu_check(cudaGetLastError(), "cram slice decode launch")) return HGPU_ERR_CUDA;
     if (hgpu_check(cudaMemcpyAsync(sbytes.data(), A.slice_bytes, (size_t)ns * 8, cudaMemcpyDeviceToHost, st), "D2H")) return HGPU_ERR_CUDA;
@@ -751,7 +761,9 @@ int decode_impl(hgpu_ctx *ctx, const uint8_t *file, uint64_t file_len, const hgp
     if (rc1) { hgpu_cram_records_free(out); return rc1; }
     A.data = ctx->d_bam;
     if (hgpu_check(cudaMemcpyAsync(base + s_sbase.off, sbase.data(), sbase.size() * 8, cudaMemcpyHostToDevice, st), "H2D")) return HGPU_ERR_CUDA;
+    cudaEventRecord(ev[2], st);
     cram_bam_fill_kernel<<<(unsigned)((n_records + 3) / 4), 128, 0, st>>>(A);
+    cudaEventRecord(ev[3], st);
     hgpu_count_launch();
     if (hgpu_check(cudaGetLastError(), "cram bam fill launch")) return HGPU_ERR_CUDA;
     if (hgpu_check(cudaMemcpyAsync(out->core, A.core, n_records * sizeof(BamCore), cudaMemcpyDeviceToHost, st), "D2H")) return HGPU_ERR_CUDA;
@@ -759,6 +771,8 @@ int decode_impl(hgpu_ctx *ctx, const uint8_t *file, uint64_t file_len, const hgp
     if (hgpu_check(cudaMemcpyAsync(out->rec_status, A.rec_status, n_records * 4, cudaMemcpyDeviceToHost, st), "D2H")) return HGPU_ERR_CUDA;
     if (data_bytes && hgpu_check(cudaMemcpyAsync(out->data, A.data, data_bytes, cudaMemcpyDeviceToHost, st), "D2H")) return HGPU_ERR_CUDA;
     if (hgpu_check(cudaStreamSynchronize(st), "cram bam fill")) return HGPU_ERR_CUDA;
+    cudaEventElapsedTime(&g_last_ms[0], ev[0], ev[1]);
+    cudaEventElapsedTime(&g_last_ms[1], ev[2], ev[3]);
 #endif
 #undef UP
     return HGPU_OK;
@@ -781,6 +795,47 @@ extern "C" int hostsim_cram_decode_records(const uint8_t *file, uint64_t file_le
     catch (...) { hgpu_set_error("internal error"); return HGPU_ERR_NOMEM; }
 }
 #else
+extern "C" long hgpu_cram_scan_blocks(const uint8_t *file, uint64_t len, hgpu_cram_block *blocks, long cap, int *major, int *minor);
+extern "C" int hgpu_cram_uncompress_blocks_host(hgpu_ctx *ctx, const uint8_t *file, uint64_t file_len, const hgpu_cram_block *blocks, uint32_t n,
+                                                 uint8_t *out, const uint64_t *out_off, uint32_t *got_len, int32_t *status);
+
+// scan + cram_uncompress_block for every block + record decode: a CRAM file image in, bam1_t records out
+static int decode_file_impl(hgpu_ctx *ctx, const uint8_t *file, uint64_t file_len, const hgpu_cram_refs *refs, const char *name_prefix,
+                            int decode_md, hgpu_cram_records *out)
+{
+    if (!out) { hgpu_set_error("cram file: null argument"); return HGPU_ERR_ARG; }
+    memset(out, 0, sizeof *out);
+    int maj = 0, mnr = 0;
+    const long nb = hgpu_cram_scan_blocks(file, file_len, nullptr, 0, &maj, &mnr);
+    if (nb < 0) return HGPU_ERR_ARG;
+    std::vector<hgpu_cram_block> blocks((size_t)nb + 1);
+    hgpu_cram_scan_blocks(file, file_len, blocks.data(), nb, &maj, &mnr);
+    std::vector<uint64_t> off((size_t)nb + 1, 0);
+    for (long i = 0; i < nb; i++) off[(size_t)i + 1] = off[(size_t)i] + (((uint64_t)blocks[(size_t)i].uncomp_size + 15) & ~15ull);
+    std::vector<uint8_t> udata(off[(size_t)nb] + 16);
+    std::vector<uint32_t> got((size_t)nb + 1);
+    std::vector<int32_t> st((size_t)nb + 1);
+    int rc = hgpu_cram_uncompress_blocks_host(ctx, file, file_len, blocks.data(), (uint32_t)nb, udata.data(), off.data(), got.data(), st.data());
+    if (rc) return rc;
+    for (long i = 0; i < nb; i++)
+        if (st[(size_t)i] != HGPU_OK) { hgpu_set_error("cram file: block %ld (method %d) did not uncompress: status %d", i, blocks[(size_t)i].method, st[(size_t)i]); return st[(size_t)i]; }
+    return decode_impl(ctx, file, file_len, blocks.data(), (uint32_t)nb, udata.data(), off.data(), refs, name_prefix, decode_md, out);
+}
+
+extern "C" void hgpu_cram_records_last_ms(float *slice_decode_ms, float *bam_fill_ms)
+{
+    if (slice_decode_ms) *slice_decode_ms = g_last_ms[0];
+    if (bam_fill_ms) *bam_fill_ms = g_last_ms[1];
+}
+
+extern "C" int hgpu_cram_decode_file_host(hgpu_ctx *ctx, const uint8_t *file, uint64_t file_len, const hgpu_cram_refs *refs,
+                                          const char *name_prefix, int decode_md, hgpu_cram_records *out)
+{
+    try { return decode_file_impl(ctx, file, file_len, refs, name_prefix, decode_md, out); }
+    catch (const std::bad_alloc &) { hgpu_set_error("out of host memory"); return HGPU_ERR_NOMEM; }
+    catch (...) { hgpu_set_error("internal error"); return HGPU_ERR_NOMEM; }
+}
+
 extern "C" int hgpu_cram_decode_records_host(hgpu_ctx *ctx, const uint8_t *file, uint64_t file_len, const hgpu_cram_block *blocks, uint32_t n_blocks,
         const uint8_t *udata, const uint64_t *udata_off, const hgpu_cram_refs *refs, const char *name_prefix, int decode_md, hgpu_cram_records *out)
 {

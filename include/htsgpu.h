@@ -459,6 +459,13 @@ int hgpu_cram_decode_records_host(hgpu_ctx *ctx, const uint8_t *file, uint64_t f
         const hgpu_cram_block *blocks, uint32_t n_blocks, const uint8_t *udata, const uint64_t *udata_off,
         const hgpu_cram_refs *refs, const char *name_prefix, int decode_md, hgpu_cram_records *out);
 void hgpu_cram_records_free(hgpu_cram_records *r);
+/* The whole read side of a CRAM file in one call: hgpu_cram_scan_blocks + hgpu_cram_uncompress_blocks_host +
+ * hgpu_cram_decode_records_host — what a loop of sam_read1 over the file returns.  A block the device cannot uncompress
+ * (BZIP2 / LZMA) fails the call with that block's status. */
+int hgpu_cram_decode_file_host(hgpu_ctx *ctx, const uint8_t *file, uint64_t file_len, const hgpu_cram_refs *refs,
+                               const char *name_prefix, int decode_md, hgpu_cram_records *out);
+/* device time (CUDA events) of cram_slice_decode_kernel and cram_bam_fill_kernel in the last record-decode call: measurement only */
+void hgpu_cram_records_last_ms(float *slice_decode_ms, float *bam_fill_ms);
 
 /* ------------------------------------------------------------------------------------------
  * Reference-named shims (link seam B1: `./configure --with-external-htscodecs`, configure.ac:278).

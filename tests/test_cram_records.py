@@ -148,7 +148,7 @@ def _synthetic_sam(path, n=10000, seed=3):
               [(10, "H"), (90, "M"), (10, "S")], [(100, "M")], [(100, "M")], [(60, "M"), (1, "I"), (20, "M"), (1, "D"), (19, "M")]]
     pos = 1000
     for i in range(n // 2):
-        pos += rng.randrange(1, 150)
+        pos += rng.randrange(1, max(2, min(150, 1_700_000 // n)))
         ends = []
         for which in (0, 1):
             p = pos + which * rng.randrange(150, 400)
@@ -219,4 +219,18 @@ def test_gpu_synthetic_10000_read_slice(tmp_path):
     ctx = H.Context(0)
     assert _synthetic_case(tmp_path, ctx, "3.1", []) == 1
     assert _synthetic_case(tmp_path, ctx, "3.0", [(SEQS, 700), (LOSSY, 1)]) == 15
+    ctx.close()
+
+
+@pytest.mark.gpu
+@pytest.mark.skipif(ref() is None, reason="oracle/_ref not built")
+@pytest.mark.parametrize("name,fa", [("ce#1000.v31.cram", "ce.fa"), ("ce#1000.v31arith.cram", "ce.fa"), ("range.cram", "ce.fa")])
+def test_gpu_file_in_records_out(name, fa):
+    """hgpu_cram_decode_file_host: the image goes in, every block is uncompressed and every record decoded on the device."""
+    img = np.fromfile(os.path.join(HT, name), dtype=np.uint8)
+    blocks, udata, off = cpu_blocks(img)                       # only to learn the @SQ order of the header
+    fasta = H.load_fasta_upper(os.path.join(HT, fa), H.cram_sq_names(blocks, udata, off))
+    ctx = H.Context(0)
+    got = H.cram_decode_file(ctx, img, fasta, name.encode(), 1)
+    compare(name, fa, got, 1)
     ctx.close()
