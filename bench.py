@@ -39,7 +39,7 @@ def parse():
     ap.add_argument("--quals", default="novaseq")
     ap.add_argument("--rans-slices", type=int, default=-2, help="CRAM slices for the rANS leg (0 = skip)")
     ap.add_argument("--tok3-blocks", type=int, default=9472, help="read-name blocks for the tok3 leg (0 = skip)")
-    ap.add_argument("--cram-tiles", type=int, default=40, help="CRAM record-decode leg: the reference-written 100k-read file tiled this many times (0 = skip)")
+    ap.add_argument("--cram-tiles", type=int, default=120, help="CRAM record-decode leg: the reference-written 100k-read file tiled this many times (0 = skip)")
     ap.add_argument("--cpu-sample-gb", type=float, default=4.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")

@@ -1076,9 +1076,27 @@ constexpr uint32_t DEFL_HASH_BITS = 12;
 constexpr uint32_t DEFL_MAX_IN = 0xff00 + 256;      // htslib never exceeds 0xff00; allow the full 64 KiB - 280
 constexpr uint32_t DEFL_TOK_CAP = 65536;
 
-struct DeflateSmem {
-    uint16_t htab[1u << DEFL_HASH_BITS];
+// pass 1 uses the hash table; pass 2 (dynamic Huffman) reuses the same bytes for histograms, code tables and the
+// code-length sequence
+struct DeflateDyn {
+    uint32_t freq[288 + 32];          // lit/len then distance counts; reused as sort keys
+    uint16_t code_ll[288], code_d[32];
+    uint8_t  len_ll[288], len_d[32];
+    uint16_t order[288];              // symbols sorted by count
+    uint8_t  cl_sym[320], cl_ext[320];  // code-length alphabet symbols and their extra-bit values
+    uint32_t cl_freq[19];
+    uint16_t cl_code[19];
+    uint8_t  cl_len[19];
+    uint32_t n_cl;
+    uint32_t w[576];                  // build_lengths work space: node weights, parents, depths
+    uint16_t par[576];
+    uint8_t  depth[576];
 };
+union DeflateSmem {
+    uint16_t htab[1u << DEFL_HASH_BITS];
+    DeflateDyn d;
+};
+static_assert(sizeof(DeflateDyn) <= (sizeof(uint16_t) << DEFL_HASH_BITS), "pass-2 tables fit the hash table's bytes");
 
 __device__ __forceinline__ uint32_t fixed_lit_code(uint32_t sym, uint32_t &nbits)
 {
@@ -1108,6 +1126,86 @@ __device__ __forceinline__ uint32_t token_bits(uint32_t tok, uint32_t &nbits)
     uint32_t dx = c_dst_xtra[ds];
     bits |= (__brev(ds) >> 27) << n1; n1 += 5;
     bits |= (dist - c_dst_base[ds]) << n1; n1 += dx;
+    nbits = n1;
+    return bits;
+}
+
+// ---- dynamic Huffman (RFC 1951 3.2.7): code lengths from the token histogram ----
+__device__ __forceinline__ uint32_t len_symbol(uint32_t len) { uint32_t ls = 28; while (ls > 0 && c_len_base[ls] > len) ls--; return ls; }
+__device__ __forceinline__ uint32_t dist_symbol(uint32_t dist) { uint32_t ds = 29; while (ds > 0 && c_dst_base[ds] > dist) ds--; return ds; }
+
+// One thread: optimal prefix-code lengths for n symbols with counts freq[] (0 = unused), limited to max_bits, into len[].
+// order[] is scratch.  Sorted leaves + the two-queue merge give the depths (Huffman's algorithm without a heap); lengths over
+// the limit are folded back by moving codes between length classes until the Kraft sum is exact.  A lone used symbol gets
+// length 1 (inflaters accept the incomplete one-code set).
+__device__ void build_lengths(const uint32_t *freq, int n, int max_bits, uint8_t *len, uint16_t *order, uint32_t *w, uint16_t *par, uint8_t *depth)
+{
+    int used = 0;
+    for (int i = 0; i < n; i++) { len[i] = 0; if (freq[i]) order[used++] = (uint16_t)i; }
+    if (used == 0) return;
+    if (used == 1) { len[order[0]] = 1; return; }
+    // insertion sort by count (ties by symbol): used <= 286
+    for (int i = 1; i < used; i++) {
+        const uint16_t v = order[i];
+        const uint32_t fv = freq[v];
+        int j = i - 1;
+        while (j >= 0 && (freq[order[j]] > fv)) { order[j + 1] = order[j]; j--; }
+        order[j + 1] = v;
+    }
+    // two-queue Huffman on the sorted leaves: node weights in w[], parent links in par[] (local arrays, 2*286 entries)
+    for (int i = 0; i < used; i++) w[i] = freq[order[i]];
+    int leaf = 0, inode = used, next = used;            // leaf queue [leaf, used), internal queue [inode, next)
+    for (int k = 0; k < used - 1; k++) {
+        int a, b;
+        if (leaf < used && (inode >= next || w[leaf] <= w[inode])) a = leaf++; else a = inode++;
+        if (leaf < used && (inode >= next || w[leaf] <= w[inode])) b = leaf++; else b = inode++;
+        w[next] = w[a] + w[b];
+        par[a] = par[b] = (uint16_t)next;
+        next++;
+    }
+    const int root = next - 1;
+    depth[root] = 0;
+    for (int i = root - 1; i >= 0; i--) depth[i] = (uint8_t)(depth[par[i]] + 1);
+    // length classes, folded to max_bits
+    int cnt[32];
+    for (int i = 0; i < 32; i++) cnt[i] = 0;
+    for (int i = 0; i < used; i++) cnt[depth[i] > max_bits ? max_bits : depth[i]]++;
+    uint32_t total = 0;
+    for (int i = 1; i <= max_bits; i++) total += (uint32_t)cnt[i] << (max_bits - i);
+    while (total > (1u << max_bits)) {                    // over-subscribed: lengthen the shallowest code that can give way
+        cnt[max_bits]--;
+        for (int i = max_bits - 1; i > 0; i--) if (cnt[i]) { cnt[i]--; cnt[i + 1] += 2; break; }
+        total--;
+    }
+    // the most frequent symbols get the shortest lengths: walk the sorted order from the back
+    int idx = used - 1;
+    for (int l = 1; l <= max_bits; l++)
+        for (int c = 0; c < cnt[l]; c++) len[order[idx--]] = (uint8_t)l;
+}
+
+// canonical codes (RFC 1951 3.2.2), bit-reversed for the LSB-first stream
+__device__ void assign_codes(const uint8_t *len, int n, int max_bits, uint16_t *code)
+{
+    uint32_t bl_count[16], next_code[16];
+    for (int i = 0; i < 16; i++) bl_count[i] = 0;
+    for (int i = 0; i < n; i++) bl_count[len[i]]++;
+    bl_count[0] = 0;
+    uint32_t c = 0;
+    for (int b = 1; b <= max_bits; b++) { c = (c + bl_count[b - 1]) << 1; next_code[b] = c; }
+    for (int i = 0; i < n; i++) if (len[i]) code[i] = (uint16_t)(__brev(next_code[len[i]]++) >> (32 - len[i]));
+}
+
+// token -> (bits, nbits <= 48) with the block's own codes
+__device__ __forceinline__ uint64_t token_bits_dyn(const DeflateDyn &d, uint32_t tok, uint32_t &nbits)
+{
+    if (!(tok >> 31)) { const uint32_t sym = tok & 0xff; nbits = d.len_ll[sym]; return d.code_ll[sym]; }
+    const uint32_t len = (tok & 0xff) + 3, dist = ((tok >> 8) & 0x7fff) + 1;
+    const uint32_t ls = len_symbol(len), ds = dist_symbol(dist);
+    uint64_t bits = d.code_ll[257 + ls];
+    uint32_t n1 = d.len_ll[257 + ls];
+    bits |= (uint64_t)(len - c_len_base[ls]) << n1; n1 += c_len_xtra[ls];
+    bits |= (uint64_t)d.code_d[ds] << n1; n1 += d.len_d[ds];
+    bits |= (uint64_t)(dist - c_dst_base[ds]) << n1; n1 += c_dst_xtra[ds];
     nbits = n1;
     return bits;
 }
@@ -1182,35 +1280,140 @@ __device__ uint32_t deflate_block_warp(DeflateSmem &s, const uint32_t (*crc_tab)
         }
         __syncwarp();
         __threadfence_block();
-        // ---- pass 2: bits ----
+        // ---- pass 2: code construction + bits ----
+        // the hash table is dead: its bytes now hold the histograms and code tables (DeflateDyn)
+        DeflateDyn &d = s.d;
+        bool overflow = ntok > DEFL_TOK_CAP;
+        for (uint32_t i = lane; i < 320; i += 32) d.freq[i] = 0;
+        __syncwarp();
+        uint32_t xbits = 0;                                   // extra bits of all matches (the same under any code)
+        for (uint32_t t = lane; t < ntok && !overflow; t += 32) {
+            const uint32_t tok = toks[t];
+            if (!(tok >> 31)) atomicAdd(&d.freq[tok & 0xff], 1u);
+            else {
+                const uint32_t ls = len_symbol((tok & 0xff) + 3), ds = dist_symbol(((tok >> 8) & 0x7fff) + 1);
+                atomicAdd(&d.freq[257 + ls], 1u);
+                atomicAdd(&d.freq[288 + ds], 1u);
+                xbits += c_len_xtra[ls] + c_dst_xtra[ds];
+            }
+        }
+        for (int dd = 16; dd > 0; dd >>= 1) xbits += __shfl_xor_sync(0xffffffffu, xbits, dd);
+        __syncwarp();
+        uint32_t use_dyn = 0, hlit = 257, hdist = 1, hclen = 4;
+        if (lane == 0 && !overflow) {
+            d.freq[256] = 1;                                  // end of block
+            uint64_t fixed_bits = 3 + xbits, dyn_bits = 3 + 14 + xbits;
+            for (int i = 0; i < 288; i++) fixed_bits += (uint64_t)d.freq[i] * (i < 144 ? 8 : i < 256 ? 9 : i < 280 ? 7 : 8);
+            for (int i = 0; i < 30; i++) fixed_bits += (uint64_t)d.freq[288 + i] * 5;
+            build_lengths(d.freq, 286, 15, d.len_ll, d.order, d.w, d.par, d.depth);
+            build_lengths(d.freq + 288, 30, 15, d.len_d, d.order, d.w, d.par, d.depth);
+            bool any_d = false;
+            for (int i = 0; i < 30; i++) any_d |= d.len_d[i] != 0;
+            if (!any_d) d.len_d[0] = 1;                       // "one distance code of one bit": a set every inflater accepts
+            for (int i = 286; i < 288; i++) d.len_ll[i] = 0;
+            d.len_d[30] = d.len_d[31] = 0;
+            assign_codes(d.len_ll, 286, 15, d.code_ll);
+            assign_codes(d.len_d, 30, 15, d.code_d);
+            for (int i = 285; i >= 257; i--) if (d.len_ll[i]) { hlit = (uint32_t)i + 1; break; }
+            for (int i = 29; i >= 1; i--) if (d.len_d[i]) { hdist = (uint32_t)i + 1; break; }
+            // the code lengths as one sequence, run-length coded with symbols 16 / 17 / 18 (3.2.7)
+            for (int i = 0; i < 19; i++) d.cl_freq[i] = 0;
+            uint32_t ncl = 0;
+            const uint32_t nseq = hlit + hdist;
+            uint32_t i = 0;
+            while (i < nseq) {
+                const uint32_t v = i < hlit ? d.len_ll[i] : d.len_d[i - hlit];
+                uint32_t run = 1;
+                while (i + run < nseq && (i + run < hlit ? d.len_ll[i + run] : d.len_d[i + run - hlit]) == v) run++;
+                i += run;
+                if (v == 0) {
+                    while (run >= 11) { const uint32_t r = run < 138 ? run : 138; d.cl_sym[ncl] = 18; d.cl_ext[ncl++] = (uint8_t)(r - 11); d.cl_freq[18]++; run -= r; }
+                    if (run >= 3) { d.cl_sym[ncl] = 17; d.cl_ext[ncl++] = (uint8_t)(run - 3); d.cl_freq[17]++; run = 0; }
+                } else {
+                    d.cl_sym[ncl] = (uint8_t)v; d.cl_ext[ncl++] = 0; d.cl_freq[v]++; run--;
+                    while (run >= 3) { const uint32_t r = run < 6 ? run : 6; d.cl_sym[ncl] = 16; d.cl_ext[ncl++] = (uint8_t)(r - 3); d.cl_freq[16]++; run -= r; }
+                }
+                while (run--) { d.cl_sym[ncl] = (uint8_t)v; d.cl_ext[ncl++] = 0; d.cl_freq[v]++; }
+            }
+            d.n_cl = ncl;
+            build_lengths(d.cl_freq, 19, 7, d.cl_len, d.order, d.w, d.par, d.depth);
+            {   // the code-length code must be complete (zlib rejects an incomplete CODES set even of one code): pair a lone code
+                int used = 0, only = 0;
+                for (int k = 0; k < 19; k++) if (d.cl_len[k]) { used++; only = k; }
+                if (used == 1) d.cl_len[only == 0 ? 1 : 0] = 1;
+            }
+            assign_codes(d.cl_len, 19, 7, d.cl_code);
+            for (int k = 18; k >= 4; k--) if (d.cl_len[c_cl_order[k]]) { hclen = (uint32_t)k + 1; break; }
+            dyn_bits += 3 * hclen;
+            for (int k = 0; k < 19; k++) dyn_bits += (uint64_t)d.cl_freq[k] * (d.cl_len[k] + (k == 16 ? 2 : k == 17 ? 3 : k == 18 ? 7 : 0));
+            for (int k = 0; k < 286; k++) dyn_bits += (uint64_t)d.freq[k] * d.len_ll[k];
+            for (int k = 0; k < 30; k++) dyn_bits += (uint64_t)d.freq[288 + k] * d.len_d[k];
+            use_dyn = dyn_bits < fixed_bits ? 1u : 0u;
+        }
+        use_dyn = __shfl_sync(0xffffffffu, use_dyn, 0);
+        hlit = __shfl_sync(0xffffffffu, hlit, 0); hdist = __shfl_sync(0xffffffffu, hdist, 0); hclen = __shfl_sync(0xffffffffu, hclen, 0);
+        __syncwarp();
         // zero the slot's deflate area first (bits are ORed in)
         uint32_t *ow = reinterpret_cast<uint32_t *>(out);          // out slots are 64 KiB aligned by contract (>= 4)
         for (uint32_t i = lane; i < 65536 / 4; i += 32) ow[i] = 0;
         __syncwarp();
         __threadfence_block();
         uint64_t bitpos = 18 * 8;
-        if (lane == 0) atomicOr(&ow[bitpos >> 5], 3u << (bitpos & 31));     // BFINAL=1, BTYPE=01
-        bitpos += 3;
-        bool overflow = ntok > DEFL_TOK_CAP;
+        if (lane == 0) {
+            // lane 0 alone writes the block header; the other lanes join after the barrier below
+            uint64_t bp = bitpos;
+            auto put = [&](uint32_t bits, uint32_t nb) {
+                if (!nb) return;
+                const uint32_t w = (uint32_t)(bp >> 5), sh = (uint32_t)(bp & 31);
+                ow[w] |= bits << sh;
+                if (sh + nb > 32) ow[w + 1] |= bits >> (32 - sh);
+                bp += nb;
+            };
+            if (!use_dyn) put(3u, 3);                              // BFINAL=1, BTYPE=01
+            else {
+                put(5u, 3);                                        // BFINAL=1, BTYPE=10
+                put(hlit - 257, 5); put(hdist - 1, 5); put(hclen - 4, 4);
+                for (uint32_t k = 0; k < hclen; k++) put(d.cl_len[c_cl_order[k]], 3);
+                for (uint32_t k = 0; k < d.n_cl; k++) {
+                    const uint32_t sy = d.cl_sym[k];
+                    put(d.cl_code[sy], d.cl_len[sy]);
+                    if (sy == 16) put(d.cl_ext[k], 2); else if (sy == 17) put(d.cl_ext[k], 3); else if (sy == 18) put(d.cl_ext[k], 7);
+                }
+            }
+            bitpos = bp;
+        }
+        bitpos = __shfl_sync(0xffffffffu, (unsigned long long)bitpos, 0);
+        __syncwarp();
+        __threadfence_block();
         const uint64_t limit = (uint64_t)(65536 - 8 - 4) * 8;       // keep room for EOB + footer
         for (uint32_t t0 = 0; t0 < ntok && !overflow; t0 += 32) {
-            uint32_t t = t0 + lane, nb = 0, bits = 0;
-            if (t < ntok) bits = token_bits(toks[t], nb);
+            uint32_t t = t0 + lane, nb = 0;
+            uint64_t bits = 0;
+            if (t < ntok) { if (use_dyn) bits = token_bits_dyn(d, toks[t], nb); else bits = token_bits(toks[t], nb); }
             uint32_t inc = nb;
 #pragma unroll
-            for (int d = 1; d < 32; d <<= 1) { uint32_t v = __shfl_up_sync(0xffffffffu, inc, d); if (lane >= (uint32_t)d) inc += v; }
+            for (int dd = 1; dd < 32; dd <<= 1) { uint32_t v = __shfl_up_sync(0xffffffffu, inc, dd); if (lane >= (uint32_t)dd) inc += v; }
             uint32_t tot = __shfl_sync(0xffffffffu, inc, 31);
             if (bitpos + tot > limit) { overflow = true; break; }
             if (nb) {
                 uint64_t bp = bitpos + inc - nb;
                 uint32_t w = (uint32_t)(bp >> 5), sh = (uint32_t)(bp & 31);
-                atomicOr(&ow[w], bits << sh);
-                if (sh + nb > 32) atomicOr(&ow[w + 1], bits >> (32 - sh));
+                atomicOr(&ow[w], (uint32_t)(bits << sh));                                   // up to 48 bits at any bit offset: three words
+                if (sh + nb > 32) atomicOr(&ow[w + 1], sh ? (uint32_t)(bits >> (32 - sh)) : (uint32_t)(bits >> 32));
+                if (sh + nb > 64) atomicOr(&ow[w + 2], (uint32_t)(bits >> (64 - sh)));
             }
             bitpos += tot;
         }
         if (!overflow) {
-            bitpos += 7;                                            // end-of-block: seven zero bits
+            // end-of-block code: seven zero bits under the fixed code, the block's own code otherwise
+            const uint32_t eob_n = use_dyn ? d.len_ll[256] : 7u;
+            if (use_dyn && lane == 0) {
+                const uint32_t w = (uint32_t)(bitpos >> 5), sh = (uint32_t)(bitpos & 31);
+                const uint32_t bits = d.code_ll[256];
+                atomicOr(&ow[w], bits << sh);
+                if (sh + eob_n > 32) atomicOr(&ow[w + 1], bits >> (32 - sh));
+            }
+            bitpos += eob_n;
             dlen = (uint32_t)((bitpos + 7) / 8) - 18;
             if (dlen >= n + 5) overflow = true;                    // stored would be smaller
         }

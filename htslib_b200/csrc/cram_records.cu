@@ -409,6 +409,26 @@ CRAMREC_HD void slice_body(const Args &A, uint32_t si, uint32_t lane, uint32_t n
     D.T = A.P.tables + S.table;
     D.ext = A.P.ext + S.ext_off;
     D.cur = A.P.cur + S.ext_off;
+#if defined(__CUDA_ARCH__)
+    // every series read is table entry -> block descriptor -> cursor -> bytes, a chain of dependent loads: the first three
+    // links live in shared memory (one warp per CTA), only the stream bytes come from L2 / HBM
+    constexpr uint32_t SM_EXT = 96;
+    __shared__ __align__(16) Table s_T;
+    __shared__ __align__(16) Ext s_ext[SM_EXT];
+    __shared__ uint32_t s_cur[SM_EXT];
+    {
+        const uint32_t *src = reinterpret_cast<const uint32_t *>(D.T);
+        uint32_t *dst = reinterpret_cast<uint32_t *>(&s_T);
+        for (uint32_t i = lane; i < sizeof(Table) / 4; i += 32) dst[i] = src[i];
+        const uint32_t ne = D.T->n_ext + 1;
+        if (ne <= SM_EXT) {
+            for (uint32_t i = lane; i < ne; i += 32) { s_ext[i] = D.ext[i]; s_cur[i] = 0; }
+            D.ext = s_ext; D.cur = s_cur;
+        }
+        __syncwarp();
+        D.T = &s_T;
+    }
+#endif
     D.core = A.P.udata + S.core_off; D.csize = S.core_size; D.cbyte = 0; D.cbit = 7;
     D.name = A.scratch + S.name_off; D.name_size = 0; D.name_cap = S.name_cap;
     D.aux = A.scratch + S.aux_off; D.aux_size = 0; D.aux_cap = S.aux_cap;

@@ -149,5 +149,5 @@ if __name__ == "__main__":
     torch.cuda.set_device(0)
     ctx = H.Context(0)
     reads = int(sys.argv[1]) if len(sys.argv) > 1 else 100000
-    tiles = int(sys.argv[2]) if len(sys.argv) > 2 else 20
+    tiles = int(sys.argv[2]) if len(sys.argv) > 2 else 120
     print(json.dumps(run(ctx, reads, tiles)))
