@@ -218,6 +218,19 @@ long hgpu_cram_scan_blocks(const uint8_t *file, uint64_t len, hgpu_cram_block *b
 int hgpu_cram_write_blocks_host(hgpu_ctx *ctx, const hgpu_cram_block *blocks, const uint8_t *const *payload, uint32_t n,
                                 uint8_t *out, uint64_t cap, uint64_t *out_off, uint64_t *out_len);
 
+/* The method trial of cram_compress_block2 / cram_compress_block3 (cram/cram_io.c:1912-2308) with cram_compress_by_method's
+ * mapping (:1697-1897) for a batch of blocks: block i (payload[i], payload_len[i] host bytes) is encoded with every
+ * method whose bit is set in method_mask[i] — bits numbered as enum cram_block_method_int (cram_structs.h:215-266):
+ * RANS0 4, RANS1 16 (rANS 4x8), RANS_PR0 5, RANS_PR1..RANS_PR193 17-23 (rANS Nx16 orders 1, 64, 9, 128, 129, 192, 193, with
+ * SIMD_AUTO), ARITH_PR0 6, ARITH_PR1..ARITH_PR193 25-31 — all candidates of all blocks in one launch per codec, the smallest
+ * stream kept, RAW when nothing beats the data; then framed as cram_write_block does (hgpu_cram_write_blocks_host: method,
+ * content type, ITF8 id / sizes, payload, CRC-32) back to back into out.  Stateless: no cram_metrics history.  GZIP*, BZIP2,
+ * LZMA, FQZ*, TOK3 / TOKA bits are ignored (see hgpu_fqz_encode_batch_host / hgpu_tok3_encode_batch_host).  chosen[i] (may be
+ * NULL) = the winning method.  HGPU_ERR_NOMEM with *out_len = the bytes needed when cap is too small. */
+int hgpu_cram_compress_blocks_host(hgpu_ctx *ctx, const uint8_t *const *payload, const uint32_t *payload_len,
+        const uint32_t *method_mask, const int32_t *content_id, const uint8_t *content_type, uint32_t n,
+        uint8_t *out, uint64_t cap, uint64_t *out_off, uint64_t *out_len, int32_t *chosen);
+
 /* CRAM 3.x compression header on the host: the record and tag encoding maps of a container
  * (cram_decode_compression_header, cram/cram_decode.c:144-538, and the *_decode_init parsers of
  * cram/cram_codecs.c) — which codec and which external block feed every data series; the table a device
