@@ -234,3 +234,58 @@ def test_gpu_file_in_records_out(name, fa):
     got = H.cram_decode_file(ctx, img, fasta, name.encode(), 1)
     compare(name, fa, got, 1)
     ctx.close()
+
+
+def _mutations(name, count, seed):
+    import random
+    rng = random.Random(seed)
+    fa = dict(CASES)[name]
+    img = np.fromfile(os.path.join(HT, name), dtype=np.uint8)
+    blocks, udata, off = cpu_blocks(img)
+    fasta = H.load_fasta_upper(os.path.join(HT, fa), H.cram_sq_names(blocks, udata, off))
+    for _ in range(count):
+        u2 = udata.copy()
+        for _ in range(rng.randrange(1, 5)):
+            i = rng.randrange(len(blocks))
+            if int(blocks[i]["content_type"]) == 0 or int(blocks[i]["uncomp_size"]) == 0:
+                continue
+            p = int(off[i]) + rng.randrange(int(blocks[i]["uncomp_size"]))
+            u2[p] = rng.randrange(256) if rng.random() < 0.7 else (int(u2[p]) ^ (1 << rng.randrange(8)))
+        yield img, blocks, u2, off, fasta, rng.randrange(2)
+
+
+@pytest.mark.parametrize("name", ["ce#5b_java.cram", "range.cram"])
+def test_hostsim_corrupt_series_never_run_wild(name):
+    """Random bytes flipped in compression headers, slice headers, CORE and external blocks: the decoder must come back with a
+    status (a malformed header fails the call; a bad slice is flagged -1; untouched slices still decode), never crash —
+    every cursor, bit read and arena append is bounds-checked (the same code runs on the device)."""
+    seen = set()
+    for img, blocks, u2, off, fasta, md in _mutations(name, 60, 5):
+        try:
+            got = H.cram_decode_records(None, img, blocks, u2, off, fasta, b"x", md, _entry=hostsim())
+            assert set(got["slice_status"].tolist()) <= {0, -1, -4, -6, -7}
+            for st, d in zip(got["rec_status"], got["data"]):
+                assert st == 0 or d == b""
+            seen |= set(got["slice_status"].tolist())
+        except H.HgpuError:
+            seen.add("call")
+    assert 0 in seen and (-1 in seen or "call" in seen)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", ["ce#5b_java.cram", "range.cram"])
+def test_gpu_corrupt_series_never_run_wild(name):
+    ctx = H.Context(0)
+    for img, blocks, u2, off, fasta, md in _mutations(name, 40, 6):
+        try:
+            got = H.cram_decode_records(ctx, img, blocks, u2, off, fasta, b"x", md)
+            assert set(got["slice_status"].tolist()) <= {0, -1, -4, -6, -7}
+        except H.HgpuError as e:
+            assert "CUDA" not in str(e) and "illegal" not in str(e), str(e)
+    # the context is still healthy: the clean file decodes
+    img = np.fromfile(os.path.join(HT, name), dtype=np.uint8)
+    blocks, udata, off = cpu_blocks(img)
+    fasta = H.load_fasta_upper(os.path.join(HT, dict(CASES)[name]), H.cram_sq_names(blocks, udata, off))
+    got = H.cram_decode_records(ctx, img, blocks, udata, off, fasta, name.encode(), 0)
+    compare(name, dict(CASES)[name], got, 0)
+    ctx.close()
