@@ -435,6 +435,35 @@ def cram_decode_file(ctx, file_np, fasta=None, prefix=b"", decode_md=0):
     return _records_out(out, L.hgpu_cram_records_free)
 
 
+class CramRecordsDev(C.Structure):
+    _fields_ = [("n_records", C.c_uint64), ("data_bytes", C.c_uint64), ("d_core", C.c_void_p), ("d_data", C.c_void_p),
+                ("d_data_off", C.c_void_p), ("d_rec_status", C.c_void_p)]
+
+
+def cram_decode_records_dev(ctx, file_np, blocks, udata, udata_off, fasta=None, prefix=b"", decode_md=0):
+    """hgpu_cram_decode_records_dev: the records stay in HBM.  Returns (CramRecordsDev with raw device pointers, slice_status)."""
+    import numpy as np
+    L = lib()
+    refs = CramRefs()
+    keep = None
+    if fasta is not None:
+        keep = (np.ascontiguousarray(fasta[0]), np.ascontiguousarray(fasta[1]))
+        refs.bases = keep[0].ctypes.data; refs.off = keep[1].ctypes.data; refs.n_ref = len(keep[1]) - 1
+    out, dev = CramRecords(), CramRecordsDev()
+    L.hgpu_cram_decode_records_dev.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p,
+                                               C.c_void_p, C.c_char_p, C.c_int, C.c_void_p, C.c_void_p]
+    rc = L.hgpu_cram_decode_records_dev(ctx.h, file_np.ctypes.data, file_np.size, blocks.ctypes.data, len(blocks), udata.ctypes.data,
+                                        udata_off.ctypes.data, C.byref(refs) if fasta is not None else None, prefix, decode_md,
+                                        C.byref(out), C.byref(dev))
+    if rc != 0:
+        raise HgpuError("cram_decode_records_dev: %d %s" % (rc, last_error()))
+    ns = out.n_slices
+    sst = np.frombuffer((C.c_uint8 * (ns * 4)).from_address(out.slice_status), dtype=np.int32).copy() if ns else np.zeros(0, dtype=np.int32)
+    L.hgpu_cram_records_free.argtypes = [C.c_void_p]
+    L.hgpu_cram_records_free(C.byref(out))
+    return dev, sst
+
+
 def cram_decode_records(ctx, file_np, blocks, udata, udata_off, fasta=None, prefix=b"", decode_md=0, _entry=None):
     """Every record of a CRAM 3.x image as bam1_t (hgpu_cram_decode_records_host).  udata / udata_off: the blocks
     uncompressed (cram_uncompress_blocks).  fasta: (bases, offsets) from load_fasta_upper, or None.

@@ -525,8 +525,9 @@ inline size_t up256(size_t x) { return (x + 255) & ~(size_t)255; }
 
 int decode_impl(hgpu_ctx *ctx, const uint8_t *file, uint64_t file_len, const hgpu_cram_block *blocks, uint32_t n_blocks,
                 const uint8_t *udata, const uint64_t *udata_off, const hgpu_cram_refs *refs, const char *name_prefix, int decode_md,
-                hgpu_cram_records *out)
+                hgpu_cram_records *out, hgpu_cram_records_dev *dev = nullptr)
 {
+    if (dev) memset(dev, 0, sizeof *dev);
     if (!file || !blocks || !udata || !udata_off || !out) { hgpu_set_error("cram records: null argument"); return HGPU_ERR_ARG; }
     memset(out, 0, sizeof *out);
     if (file_len < 26 || memcmp(file, "CRAM", 4) != 0 || file[4] != 3) { hgpu_set_error("cram records: CRAM 3.x only"); return HGPU_ERR_ARG; }
@@ -657,10 +658,12 @@ int decode_impl(hgpu_ctx *ctx, const uint8_t *file, uint64_t file_len, const hgp
     out->n_records = n_records; out->n_slices = ns;
     out->slice_status = (int32_t *)calloc(ns + 1, sizeof(int32_t));
     out->slice_rec0 = (uint64_t *)calloc((size_t)ns + 1, sizeof(uint64_t));
-    out->core = (hgpu_bam1_core *)calloc(n_records + 1, sizeof(hgpu_bam1_core));
-    out->data_off = (uint64_t *)calloc(n_records + 1, sizeof(uint64_t));
-    out->rec_status = (int32_t *)calloc(n_records + 1, sizeof(int32_t));
-    if (!out->slice_status || !out->slice_rec0 || !out->core || !out->data_off || !out->rec_status) { hgpu_cram_records_free(out); hgpu_set_error("out of host memory"); return HGPU_ERR_NOMEM; }
+    if (!dev) {
+        out->core = (hgpu_bam1_core *)calloc(n_records + 1, sizeof(hgpu_bam1_core));
+        out->data_off = (uint64_t *)calloc(n_records + 1, sizeof(uint64_t));
+        out->rec_status = (int32_t *)calloc(n_records + 1, sizeof(int32_t));
+    }
+    if (!out->slice_status || !out->slice_rec0 || (!dev && (!out->core || !out->data_off || !out->rec_status))) { hgpu_cram_records_free(out); hgpu_set_error("out of host memory"); return HGPU_ERR_NOMEM; }
     for (uint32_t s = 0; s < ns; s++) out->slice_rec0[s] = slices[s].rec0;
     out->slice_rec0[ns] = n_records;
     if (ns == 0 || n_records == 0) return HGPU_OK;
@@ -762,8 +765,8 @@ int decode_impl(hgpu_ctx *ctx, const uint8_t *file, uint64_t file_len, const hgp
     for (uint32_t s = 0; s < ns; s++) { if (sstat[s] != 0) sbytes[s] = 0; sbase[s + 1] = sbase[s] + sbytes[s]; }
     const uint64_t data_bytes = sbase[ns];
     out->data_bytes = data_bytes;
-    out->data = (uint8_t *)malloc(data_bytes + 16);
-    if (!out->data) { hgpu_cram_records_free(out); hgpu_set_error("out of host memory"); return HGPU_ERR_NOMEM; }
+    if (!dev) out->data = (uint8_t *)malloc(data_bytes + 16);
+    if (!dev && !out->data) { hgpu_cram_records_free(out); hgpu_set_error("out of host memory"); return HGPU_ERR_NOMEM; }
     for (uint32_t s = 0; s < ns; s++) out->slice_status[s] = sstat[s] == ERR_SPACE ? HGPU_CRAM_ERR_SPACE : sstat[s] == ERR_NOREF ? HGPU_CRAM_ERR_NOREF : sstat[s];
 
 #ifdef HGPU_HOSTSIM
@@ -777,19 +780,24 @@ int decode_impl(hgpu_ctx *ctx, const uint8_t *file, uint64_t file_len, const hgp
     memcpy(out->data, dbuf.data(), data_bytes);
 #else
     // the record bytes go where the (now dead) uploads of this call's inputs cannot be: a second staging area
-    int rc1 = hgpu_ensure_bam(ctx, data_bytes + 256);
+    int rc1 = hgpu_ensure_mrec(ctx, data_bytes + 256);            // (not d_bam: hgpu_sam_format_dev / hgpu_bam_pack_dev scan there)
     if (rc1) { hgpu_cram_records_free(out); return rc1; }
-    A.data = ctx->d_bam;
+    A.data = ctx->d_mrec;
     if (hgpu_check(cudaMemcpyAsync(base + s_sbase.off, sbase.data(), sbase.size() * 8, cudaMemcpyHostToDevice, st), "H2D")) return HGPU_ERR_CUDA;
     cudaEventRecord(ev[2], st);
     cram_bam_fill_kernel<<<(unsigned)((n_records + 3) / 4), 128, 0, st>>>(A);
     cudaEventRecord(ev[3], st);
     hgpu_count_launch();
     if (hgpu_check(cudaGetLastError(), "cram bam fill launch")) return HGPU_ERR_CUDA;
-    if (hgpu_check(cudaMemcpyAsync(out->core, A.core, n_records * sizeof(BamCore), cudaMemcpyDeviceToHost, st), "D2H")) return HGPU_ERR_CUDA;
-    if (hgpu_check(cudaMemcpyAsync(out->data_off, A.data_off, (n_records + 1) * 8, cudaMemcpyDeviceToHost, st), "D2H")) return HGPU_ERR_CUDA;
-    if (hgpu_check(cudaMemcpyAsync(out->rec_status, A.rec_status, n_records * 4, cudaMemcpyDeviceToHost, st), "D2H")) return HGPU_ERR_CUDA;
-    if (data_bytes && hgpu_check(cudaMemcpyAsync(out->data, A.data, data_bytes, cudaMemcpyDeviceToHost, st), "D2H")) return HGPU_ERR_CUDA;
+    if (dev) {
+        dev->n_records = n_records; dev->data_bytes = data_bytes;
+        dev->d_core = reinterpret_cast<hgpu_bam1_core *>(A.core); dev->d_data = A.data; dev->d_data_off = A.data_off; dev->d_rec_status = A.rec_status;
+    } else {
+        if (hgpu_check(cudaMemcpyAsync(out->core, A.core, n_records * sizeof(BamCore), cudaMemcpyDeviceToHost, st), "D2H")) return HGPU_ERR_CUDA;
+        if (hgpu_check(cudaMemcpyAsync(out->data_off, A.data_off, (n_records + 1) * 8, cudaMemcpyDeviceToHost, st), "D2H")) return HGPU_ERR_CUDA;
+        if (hgpu_check(cudaMemcpyAsync(out->rec_status, A.rec_status, n_records * 4, cudaMemcpyDeviceToHost, st), "D2H")) return HGPU_ERR_CUDA;
+        if (data_bytes && hgpu_check(cudaMemcpyAsync(out->data, A.data, data_bytes, cudaMemcpyDeviceToHost, st), "D2H")) return HGPU_ERR_CUDA;
+    }
     if (hgpu_check(cudaStreamSynchronize(st), "cram bam fill")) return HGPU_ERR_CUDA;
     cudaEventElapsedTime(&g_last_ms[0], ev[0], ev[1]);
     cudaEventElapsedTime(&g_last_ms[1], ev[2], ev[3]);
@@ -840,6 +848,16 @@ static int decode_file_impl(hgpu_ctx *ctx, const uint8_t *file, uint64_t file_le
     for (long i = 0; i < nb; i++)
         if (st[(size_t)i] != HGPU_OK) { hgpu_set_error("cram file: block %ld (method %d) did not uncompress: status %d", i, blocks[(size_t)i].method, st[(size_t)i]); return st[(size_t)i]; }
     return decode_impl(ctx, file, file_len, blocks.data(), (uint32_t)nb, udata.data(), off.data(), refs, name_prefix, decode_md, out);
+}
+
+extern "C" int hgpu_cram_decode_records_dev(hgpu_ctx *ctx, const uint8_t *file, uint64_t file_len, const hgpu_cram_block *blocks, uint32_t n_blocks,
+        const uint8_t *udata, const uint64_t *udata_off, const hgpu_cram_refs *refs, const char *name_prefix, int decode_md,
+        hgpu_cram_records *out, hgpu_cram_records_dev *dev)
+{
+    if (!dev) { hgpu_set_error("cram records: null argument"); return HGPU_ERR_ARG; }
+    try { return decode_impl(ctx, file, file_len, blocks, n_blocks, udata, udata_off, refs, name_prefix, decode_md, out, dev); }
+    catch (const std::bad_alloc &) { hgpu_set_error("out of host memory"); return HGPU_ERR_NOMEM; }
+    catch (...) { hgpu_set_error("internal error"); return HGPU_ERR_NOMEM; }
 }
 
 extern "C" void hgpu_cram_records_last_ms(float *slice_decode_ms, float *bam_fill_ms)

@@ -472,6 +472,18 @@ int hgpu_cram_decode_records_host(hgpu_ctx *ctx, const uint8_t *file, uint64_t f
         const hgpu_cram_block *blocks, uint32_t n_blocks, const uint8_t *udata, const uint64_t *udata_off,
         const hgpu_cram_refs *refs, const char *name_prefix, int decode_md, hgpu_cram_records *out);
 void hgpu_cram_records_free(hgpu_cram_records *r);
+/* The same with the records left in HBM, in exactly the layout hgpu_bam_unpack_dev produces (core[n], data blob,
+ * data_off[n + 1]) so that the BAM-side kernels take them as they are: hgpu_sam_format_dev (CRAM -> SAM text without the
+ * records visiting the host), hgpu_bam_pack_dev (CRAM -> BAM records).  `out` receives only the per-slice arrays
+ * (slice_status, slice_rec0; core / data / data_off / rec_status stay NULL).  The device pointers belong to the context
+ * and are valid until its next *_host / records call. */
+typedef struct hgpu_cram_records_dev {
+    uint64_t n_records, data_bytes;
+    hgpu_bam1_core *d_core; uint8_t *d_data; uint64_t *d_data_off; int32_t *d_rec_status;
+} hgpu_cram_records_dev;
+int hgpu_cram_decode_records_dev(hgpu_ctx *ctx, const uint8_t *file, uint64_t file_len,
+        const hgpu_cram_block *blocks, uint32_t n_blocks, const uint8_t *udata, const uint64_t *udata_off,
+        const hgpu_cram_refs *refs, const char *name_prefix, int decode_md, hgpu_cram_records *out, hgpu_cram_records_dev *dev);
 /* The whole read side of a CRAM file in one call: hgpu_cram_scan_blocks + hgpu_cram_uncompress_blocks_host +
  * hgpu_cram_decode_records_host — what a loop of sam_read1 over the file returns.  A block the device cannot uncompress
  * (BZIP2 / LZMA) fails the call with that block's status. */

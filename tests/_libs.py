@@ -536,3 +536,45 @@ def ref_write_cram(sam_path, fasta, out_path, version="3.0", int_opts=()):
     assert r.hts_close(fo) == 0
     r.sam_hdr_destroy(h)
     return n
+
+
+def ref_cram_sam_text(path, fasta=None, decode_md=0):
+    """SAM text of a CRAM file through the compiled reference: sam_read1 + sam_format1.  Returns (target names, [line bytes])."""
+    r = ref()
+    r.hts_open.restype = C.c_void_p
+    r.hts_open.argtypes = [C.c_char_p, C.c_char_p]
+    r.hts_close.argtypes = [C.c_void_p]
+    r.sam_hdr_read.restype = C.c_void_p
+    r.sam_hdr_read.argtypes = [C.c_void_p]
+    r.sam_hdr_destroy.argtypes = [C.c_void_p]
+    r.sam_hdr_nref.argtypes = [C.c_void_p]
+    r.sam_hdr_tid2name.restype = C.c_char_p
+    r.sam_hdr_tid2name.argtypes = [C.c_void_p, C.c_int]
+    r.sam_read1.argtypes = [C.c_void_p, C.c_void_p, C.POINTER(Bam1)]
+    r.sam_format1.argtypes = [C.c_void_p, C.POINTER(Bam1), C.POINTER(KString)]
+    r.bam_init1.restype = C.POINTER(Bam1)
+    r.bam_destroy1.argtypes = [C.POINTER(Bam1)]
+    fp = r.hts_open(path.encode(), b"r")
+    assert fp
+    if fasta:
+        r.hts_set_fai_filename.argtypes = [C.c_void_p, C.c_char_p]
+        assert r.hts_set_fai_filename(fp, fasta.encode()) == 0
+    r.hts_set_opt.argtypes = [C.c_void_p, C.c_int, C.c_int]
+    r.hts_set_opt(fp, 0, int(decode_md))
+    hdr = r.sam_hdr_read(fp)
+    assert hdr
+    names = [r.sam_hdr_tid2name(hdr, i) for i in range(r.sam_hdr_nref(hdr))]
+    b = r.bam_init1()
+    ks = KString(0, 0, None)
+    lines = []
+    while r.sam_read1(fp, hdr, b) >= 0:
+        n = r.sam_format1(hdr, b, C.byref(ks))
+        lines.append(C.string_at(ks.s, ks.l) if n >= 0 else None)
+    libc = C.CDLL(None)
+    libc.free.argtypes = [C.c_void_p]
+    if ks.s:
+        libc.free(ks.s)
+    r.bam_destroy1(b)
+    r.sam_hdr_destroy(hdr)
+    r.hts_close(fp)
+    return names, lines

@@ -289,3 +289,35 @@ def test_gpu_corrupt_series_never_run_wild(name):
     got = H.cram_decode_records(ctx, img, blocks, udata, off, fasta, name.encode(), 0)
     compare(name, dict(CASES)[name], got, 0)
     ctx.close()
+
+
+@pytest.mark.gpu
+@pytest.mark.skipif(ref() is None, reason="oracle/_ref not built")
+@pytest.mark.parametrize("name,fa", [("ce#1000.v31.cram", "ce.fa"), ("range.cram", "ce.fa"), ("ce#5b_java.cram", "ce.fa")])
+def test_gpu_cram_to_sam_text_without_leaving_the_device(name, fa):
+    """hgpu_cram_decode_records_dev leaves core / data / data_off in HBM in hgpu_bam_unpack_dev's layout; hgpu_sam_format_dev takes them
+    as they are: the SAM text must equal the reference's sam_read1 + sam_format1 on the same CRAM."""
+    import ctypes as C
+    import torch
+    from _libs import ref_cram_sam_text
+    img = np.fromfile(os.path.join(HT, name), dtype=np.uint8)
+    blocks, udata, off = cpu_blocks(img)
+    fasta = H.load_fasta_upper(os.path.join(HT, fa), H.cram_sq_names(blocks, udata, off))
+    ctx = H.Context(0)
+    dev, sst = H.cram_decode_records_dev(ctx, img, blocks, udata, off, fasta, name.encode(), 1)
+    assert sst.tolist() == [0] * len(sst)
+    n = int(dev.n_records)
+
+    class Raw:                                        # a device pointer with the two methods the wrapper uses
+        def __init__(self, p): self.p = p; self.device = torch.device("cuda", 0)
+        def data_ptr(self): return self.p
+    names, want = ref_cram_sam_text(os.path.join(HT, name), os.path.join(HT, fa), 1)
+    text, out_off, status = ctx.sam_format_dev(Raw(dev.d_core), Raw(dev.d_data), Raw(dev.d_data_off), n, names)
+    torch.cuda.synchronize()
+    t = text.cpu().numpy().tobytes(); oo = out_off.cpu().numpy(); stt = status.cpu().numpy()
+    assert n == len(want)
+    for i, w in enumerate(want):
+        if stt[i] == 1:
+            continue                                  # a floating-point aux value: left to the host by contract
+        assert stt[i] == 0 and t[int(oo[i]):int(oo[i + 1])] == w + b"\n", (i, t[int(oo[i]):int(oo[i + 1])][:120], w[:120])
+    ctx.close()
