@@ -578,3 +578,36 @@ def ref_cram_sam_text(path, fasta=None, decode_md=0):
     r.sam_hdr_destroy(hdr)
     r.hts_close(fp)
     return names, lines
+
+
+def ref_read_sam_records(path):
+    """(header text, [(core tuple, data bytes)]) of a SAM / BAM / CRAM file through the compiled reference (sam_hdr_read, sam_read1)."""
+    r = ref()
+    r.hts_open.restype = C.c_void_p
+    r.hts_open.argtypes = [C.c_char_p, C.c_char_p]
+    r.hts_close.argtypes = [C.c_void_p]
+    r.sam_hdr_read.restype = C.c_void_p
+    r.sam_hdr_read.argtypes = [C.c_void_p]
+    r.sam_hdr_destroy.argtypes = [C.c_void_p]
+    r.sam_hdr_str.restype = C.c_char_p
+    r.sam_hdr_str.argtypes = [C.c_void_p]
+    r.sam_read1.argtypes = [C.c_void_p, C.c_void_p, C.POINTER(Bam1)]
+    r.bam_init1.restype = C.POINTER(Bam1)
+    r.bam_destroy1.argtypes = [C.POINTER(Bam1)]
+    fp = r.hts_open(path.encode(), b"r")
+    assert fp, path
+    hdr = r.sam_hdr_read(fp)
+    assert hdr
+    text = r.sam_hdr_str(hdr) or b""
+    b = r.bam_init1()
+    out = []
+    while True:
+        rc = r.sam_read1(fp, hdr, b)
+        if rc < 0:
+            assert rc == -1, rc
+            break
+        out.append((b.contents.core.astuple(), bytes(b.contents.data[: b.contents.l_data])))
+    r.bam_destroy1(b)
+    r.sam_hdr_destroy(hdr)
+    r.hts_close(fp)
+    return bytes(text), out

@@ -21,9 +21,8 @@ CASES = [("ce#1000.v31.cram", "ce.fa"), ("ce#1000.v30.cram", "ce.fa"), ("ce#1000
 
 def hostsim():
     so = os.path.join(HERE, "hostsim", "_build", "libcramrec_hostsim.so")
-    src = os.path.join(HERE, "..", "htslib_b200", "csrc", "cram_records.cu")
-    hdr = os.path.join(HERE, "..", "htslib_b200", "csrc", "cram_records.cuh")
-    if not os.path.exists(so) or os.path.getmtime(so) < max(os.path.getmtime(src), os.path.getmtime(hdr)):
+    srcs = [os.path.join(HERE, "..", "htslib_b200", "csrc", f) for f in ("cram_records.cu", "cram_records.cuh", "cram_encode.cu", "cram_encode.cuh")]
+    if not os.path.exists(so) or os.path.getmtime(so) < max(os.path.getmtime(f) for f in srcs):
         subprocess.check_call(["bash", os.path.join(HERE, "hostsim", "build.sh")], stdout=subprocess.DEVNULL)
     l = C.CDLL(so)
     l.hostsim_cram_decode_records.argtypes = [C.c_void_p, C.c_uint64, C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_char_p, C.c_int, C.c_void_p]
