@@ -567,7 +567,7 @@ int decode_impl(hgpu_ctx *ctx, const uint8_t *file, uint64_t file_len, const hgp
             hgpu_cram_slice sh;
             std::vector<int32_t> ids(10000);
             if (hgpu_cram_parse_slice_header(pay, b.uncomp_size, 3, &sh, ids.data(), (long)ids.size()) < 0) return HGPU_CRAM_ERR_DECODE;
-            if (sh.n_blocks < 1 || (uint64_t)i + (uint64_t)sh.n_blocks >= (uint64_t)n_blocks + 1 || sh.n_records < 0) {
+            if (sh.n_blocks < 1 || (uint64_t)i + (uint64_t)sh.n_blocks >= (uint64_t)n_blocks + 1 || sh.n_records < 0 || sh.n_records > 50000000) {   // (a slice holds ~10^4 records; the clamp keeps a corrupt count from sizing arrays)
                 hgpu_set_error("cram records: slice header block count"); return HGPU_CRAM_ERR_DECODE;
             }
             const Table &T = B.tables[(size_t)cur_table];

@@ -10,8 +10,8 @@
 //   * tokens come from the text alone: letter runs (N_ALPHA), digit runs of up to 9 starting with '0'
 //     (N_DIGITS0 + N_DZLEN) or not (N_DIGITS), any other byte (N_CHAR); against the previous name's token
 //     at the same position they become N_MATCH, N_DDELTA / N_DDELTA0 (0 < delta < 256) or stay literal.
-//   * each token stream is entropy-coded by this library's rANS Nx16 encoder, order 0 and order 1 both
-//     tried, smaller kept (the reference also tries PACK/RLE/STRIPE variants per stream type).
+//   * each token stream is entropy-coded by this library's rANS Nx16 encoder: order 0, order 1 and the reference's level-3
+//     transform choices for its type (PACK / RLE / 4-way STRIPE, compress() :1299-1313), all tried, smallest kept.
 // Work split: tok3_tokenise_kernel<0> counts the bytes of every (position, type) stream, one THREAD per
 // block (a name's tokens depend on the previous name's, a serial chain); the host lays the streams out;
 // tok3_tokenise_kernel<1> writes them; one rANS encode launch covers all streams of all blocks; the
@@ -215,11 +215,21 @@ static int hgpu_tok3_encode_batch_host_impl(hgpu_ctx *ctx, const uint8_t *in, co
             const uint32_t c = cnt[(size_t)b * NSTREAM + id];
             if (!c) continue;
             soff[(size_t)b * NSTREAM + id] = o;
-            StreamRef r{b, id, (uint32_t)jio.size(), c >= 64 ? 2u : 1u};
+            // candidate orders: 0, 1 (>= 64 bytes), and what the reference tries for this stream type at CRAM's level 3
+            // (compress(), tokenise_name3.c:1299-1313: PACK / RLE for the type and alphabet streams, 4-way STRIPE for the
+            // 32-bit integer streams); the smallest stream wins below
+            static const int k_l3[13][2] = {{192, -1}, {129, -1}, {-1, -1}, {136, -1}, {-1, -1}, {200, -1}, {136, -1}, {200, -1}, {-1, -1}, {128, -1}, {-1, -1}, {-1, -1}, {-1, -1}};
+            uint32_t ords[4], no = 0;
+            ords[no++] = 0;
+            if (c >= 64) ords[no++] = 1;
+            const uint32_t ty = id & 15;
+            if (ty < 13 && c >= 16)
+                for (int q = 0; q < 2; q++) { const int m = k_l3[ty][q]; if (m > 1 && (!(m & 8) || c % 4 == 0)) ords[no++] = (uint32_t)m; }
+            StreamRef r{b, id, (uint32_t)jio.size(), no};
             for (uint32_t k = 0; k < r.njobs; k++) {
                 jio.push_back(fixed_end + aoff[b] + o);                          // relative to base + o_in (= base), the encoder's d_in
-                jil.push_back(c); jord.push_back(k);
-                const uint32_t cap = c + 96;
+                jil.push_back(c); jord.push_back(ords[k]);
+                const uint32_t cap = c + 256;                                    // every level of the coder falls back to CAT, so c + framing is enough
                 joo.push_back(comp_bytes); jcap.push_back(cap);
                 comp_bytes += (cap + 15) & ~15u;
             }
