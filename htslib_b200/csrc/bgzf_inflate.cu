@@ -895,12 +895,13 @@ __device__ int check_header(const uint8_t *h)
 }
 
 #ifndef HGPU_INFLATE_WARPS
-#define HGPU_INFLATE_WARPS 4
+#define HGPU_INFLATE_WARPS 7
 #endif
-constexpr int INFLATE_WARPS = HGPU_INFLATE_WARPS;      // warps per CTA; they share only the CRC tables (4 x 10 KB + 4 KB: four CTAs = 16 warps per SM)
+constexpr int INFLATE_WARPS = HGPU_INFLATE_WARPS;      // warps per CTA; they share only the CRC tables (7 x 10 KB + 4 KB per CTA: three CTAs = 21 warps per SM, 80 registers;
+                                                       // measured 16 -> 20 -> 21 -> 22 warps/SM: 214 / 229 / 232 / 233 GB/s, shared memory caps it at 22)
 
 #ifndef INFL_LB
-#define INFL_LB 4
+#define INFL_LB 3
 #endif
 __global__ void __launch_bounds__(32 * INFLATE_WARPS, INFL_LB)
 bgzf_inflate_kernel(const uint8_t *__restrict__ in, const uint64_t *__restrict__ in_off,
@@ -1479,8 +1480,8 @@ int hgpu_launch_bgzf_inflate(hgpu_ctx *ctx, const uint8_t *d_in, const uint64_t 
     if (hgpu_check(cudaSetDevice(ctx->device), "cudaSetDevice")) return HGPU_ERR_CUDA;
     int rc = ensure_crc_tables(ctx, st);
     if (rc) return rc;
-    // The product path is the warp-per-block kernel (20 blocks in flight per SM, LZ77 through L2 with
-    // per-lane word copies: 201 GB/s on sorted BAM).  HGPU_INFLATE_CTA=1 selects the CTA-per-block kernel
+    // The product path is the warp-per-block kernel (21 blocks in flight per SM, LZ77 through L2 with
+    // per-lane word copies: 232 GB/s on sorted BAM).  HGPU_INFLATE_CTA=1 selects the CTA-per-block kernel
     // (window in shared memory, 2 blocks per SM: 127 GB/s) for A/B measurements.
     static const bool use_warp = !(getenv("HGPU_INFLATE_CTA") && getenv("HGPU_INFLATE_CTA")[0] == '1');
     static bool attr_set[64];                          // function attributes are per device
