@@ -83,7 +83,7 @@ void frame_block(Buf &o, int method, int ctype, int32_t cid, const uint8_t *payl
 }
 
 const char *const k_keys[S_COUNT] = {"BF", "CF", "RI", "RL", "AP", "RG", "RN", "MF", "NS", "NP", "TS", "TL", "FN", "FC", "FP", "DL", "RS", "HC", "PD",
-                                     nullptr, "BB", nullptr, "SC", nullptr, "IN", "BA", "QS", "MQ", nullptr, nullptr};
+                                     nullptr, "BB", nullptr, "SC", nullptr, "IN", "BA", "QS", "MQ", nullptr, nullptr, "BS"};
 
 void enc_external(Buf &o, int id) { o.itf8(1); Buf t; t.itf8(id); o.itf8((int32_t)t.v.size()); o.bytes(t.v.data(), t.v.size()); }
 void enc_byte_array_len(Buf &o, int len_id, int val_id)
@@ -95,13 +95,13 @@ void enc_byte_array_len(Buf &o, int len_id, int val_id)
 }
 
 // cram_encode_compression_header :380-1030 for this writer's fixed layout
-void compression_header(Buf &o, const std::vector<std::string> &tag_lines, const std::vector<uint32_t> &tag_keys)
+void compression_header(Buf &o, const std::vector<std::string> &tag_lines, const std::vector<uint32_t> &tag_keys, bool ref_required)
 {
     Buf pm;                                                                // preservation map
     pm.itf8(5);
     pm.u8('R'); pm.u8('N'); pm.u8(1);
     pm.u8('A'); pm.u8('P'); pm.u8(0);
-    pm.u8('R'); pm.u8('R'); pm.u8(0);
+    pm.u8('R'); pm.u8('R'); pm.u8(ref_required ? 1 : 0);
     pm.u8('S'); pm.u8('M'); { const uint8_t sm[5] = {0x1b, 0x1b, 0x1b, 0x1b, 0x1b}; pm.bytes(sm, 5); }   // the default matrix (:165): CGTN AGTN ACTN ACGN ACGT
     pm.u8('T'); pm.u8('D');
     { Buf td; for (const std::string &l : tag_lines) { td.bytes(l.data(), l.size()); td.u8(0); } if (tag_lines.empty()) td.u8(0);
@@ -128,6 +128,7 @@ void compression_header(Buf &o, const std::vector<std::string> &tag_lines, const
 
 struct EArgs {
     const Core *core; const uint8_t *data; const uint64_t *data_off; const int32_t *tl;
+    const uint8_t *ref_bases; const uint64_t *ref_off; int32_t n_ref;      // reference sequences (ref_bases == nullptr: the no-reference shape)
     uint64_t n; uint32_t rps;               // records, records per slice
     uint32_t *cnt;                          // [slice][stream][rps]: counts, then exclusive offsets
     uint32_t *tot;                          // [slice][stream]
@@ -142,7 +143,9 @@ CRAMREC_HD inline void count_body(const EArgs &A, uint64_t g)
     uint32_t n[S_COUNT];
     for (int s = 0; s < S_COUNT; s++) n[s] = 0;
     Emit<false> E{n, nullptr};
-    const int rc = walk<false>(A.core[g], A.data + A.data_off[g], (uint32_t)(A.data_off[g + 1] - A.data_off[g]), A.tl[g], E);
+    const uint8_t *ref = nullptr; int64_t rl = 0;
+    if (A.ref_bases && A.core[g].tid >= 0 && A.core[g].tid < A.n_ref) { ref = A.ref_bases + A.ref_off[A.core[g].tid]; rl = (int64_t)(A.ref_off[A.core[g].tid + 1] - A.ref_off[A.core[g].tid]); }
+    const int rc = walk<false>(A.core[g], A.data + A.data_off[g], (uint32_t)(A.data_off[g + 1] - A.data_off[g]), A.tl[g], ref, rl, E);
     A.status[g] = rc;
     for (int s = 0; s < S_COUNT; s++) A.cnt[((size_t)sl * S_COUNT + s) * A.rps + r] = rc == ENC_OK ? n[s] : 0;
 }
@@ -155,7 +158,9 @@ CRAMREC_HD inline void write_body(const EArgs &A, uint64_t g)
     uint8_t *base[S_COUNT];
     for (int s = 0; s < S_COUNT; s++) { n[s] = A.cnt[((size_t)sl * S_COUNT + s) * A.rps + r]; base[s] = A.arena + A.base[(size_t)sl * S_COUNT + s]; }
     Emit<true> E{n, base};
-    walk<true>(A.core[g], A.data + A.data_off[g], (uint32_t)(A.data_off[g + 1] - A.data_off[g]), A.tl[g], E);
+    const uint8_t *ref = nullptr; int64_t rl = 0;
+    if (A.ref_bases && A.core[g].tid >= 0 && A.core[g].tid < A.n_ref) { ref = A.ref_bases + A.ref_off[A.core[g].tid]; rl = (int64_t)(A.ref_off[A.core[g].tid + 1] - A.ref_off[A.core[g].tid]); }
+    walk<true>(A.core[g], A.data + A.data_off[g], (uint32_t)(A.data_off[g + 1] - A.data_off[g]), A.tl[g], ref, rl, E);
 }
 
 #ifndef HGPU_HOSTSIM
@@ -193,8 +198,16 @@ __global__ void __launch_bounds__(128) cram_enc_write_kernel(EArgs A)
 inline size_t up256(size_t x) { return (x + 255) & ~(size_t)255; }
 
 int encode_impl(hgpu_ctx *ctx, const char *header_text, uint32_t header_len, const hgpu_bam1_core *core, const uint8_t *data,
-                const uint64_t *data_off, uint64_t n, uint32_t rps, int minor, uint8_t **out_file, uint64_t *out_len)
+                const uint64_t *data_off, uint64_t n, const hgpu_cram_refs *refs, uint32_t rps, int minor, uint8_t **out_file, uint64_t *out_len)
 {
+    // reference-based shape only when every mapped record's reference sequence was supplied (the reader will need them all)
+    bool use_ref = refs && refs->bases && refs->off && refs->n_ref > 0;
+    if (use_ref)
+        for (uint64_t g = 0; g < n && use_ref; g++) {
+            const int32_t t = core[g].tid;
+            if (!(core[g].flag & 4) && (t < 0 || t >= refs->n_ref || refs->off[t + 1] == refs->off[t])) use_ref = false;
+        }
+    const uint64_t ref_bytes = use_ref ? refs->off[refs->n_ref] : 0;
     if (!out_file || !out_len || (n && (!core || !data || !data_off)) || (header_len && !header_text)) { hgpu_set_error("cram encode: null argument"); return HGPU_ERR_ARG; }
     *out_file = nullptr; *out_len = 0;
     if (rps == 0) rps = 10000;
@@ -239,6 +252,7 @@ int encode_impl(hgpu_ctx *ctx, const char *header_text, uint32_t header_len, con
         struct Seg { size_t off, bytes; };
         size_t total = 0;
         auto seg = [&](size_t bytes) { Seg s{total, bytes}; total += up256(bytes + 16); return s; };
+        const Seg s_ref = seg(ref_bytes), s_roff = seg(use_ref ? ((size_t)refs->n_ref + 1) * 8 : 0);
         const Seg s_core = seg(n * 48), s_data = seg(data_bytes), s_doff = seg((n + 1) * 8), s_tl = seg(n * 4), s_cnt = seg(rows * rps * 4),
                   s_tot = seg(rows * 4), s_base = seg(rows * 8), s_st = seg(n * 4);
         // every series byte comes from the record data, ITF8 at most 5 bytes per value: bound the arena before the scan
@@ -250,6 +264,7 @@ int encode_impl(hgpu_ctx *ctx, const char *header_text, uint32_t header_len, con
         uint8_t *b0 = image.data();
         memcpy(b0 + s_core.off, core, n * 48); memcpy(b0 + s_data.off, data, data_bytes); memcpy(b0 + s_doff.off, data_off, (n + 1) * 8);
         memcpy(b0 + s_tl.off, tl.data(), n * 4);
+        if (use_ref) { memcpy(b0 + s_ref.off, refs->bases, ref_bytes); memcpy(b0 + s_roff.off, refs->off, ((size_t)refs->n_ref + 1) * 8); }
 #else
         if (!ctx) { hgpu_set_error("null context"); return HGPU_ERR_ARG; }
         if (cudaSetDevice(ctx->device) != cudaSuccess) return HGPU_ERR_CUDA;
@@ -261,10 +276,13 @@ int encode_impl(hgpu_ctx *ctx, const char *header_text, uint32_t header_len, con
             hgpu_check(cudaMemcpyAsync(b0 + s_data.off, data, data_bytes, cudaMemcpyHostToDevice, st), "H2D") ||
             hgpu_check(cudaMemcpyAsync(b0 + s_doff.off, data_off, (n + 1) * 8, cudaMemcpyHostToDevice, st), "H2D") ||
             hgpu_check(cudaMemcpyAsync(b0 + s_tl.off, tl.data(), n * 4, cudaMemcpyHostToDevice, st), "H2D")) return HGPU_ERR_CUDA;
+        if (use_ref && (hgpu_check(cudaMemcpyAsync(b0 + s_ref.off, refs->bases, ref_bytes, cudaMemcpyHostToDevice, st), "H2D") ||
+                        hgpu_check(cudaMemcpyAsync(b0 + s_roff.off, refs->off, ((size_t)refs->n_ref + 1) * 8, cudaMemcpyHostToDevice, st), "H2D"))) return HGPU_ERR_CUDA;
 #endif
         EArgs A;
         A.core = reinterpret_cast<const Core *>(b0 + s_core.off); A.data = b0 + s_data.off; A.data_off = reinterpret_cast<const uint64_t *>(b0 + s_doff.off);
         A.tl = reinterpret_cast<const int32_t *>(b0 + s_tl.off); A.n = n; A.rps = rps;
+        A.ref_bases = use_ref ? b0 + s_ref.off : nullptr; A.ref_off = reinterpret_cast<const uint64_t *>(b0 + s_roff.off); A.n_ref = use_ref ? refs->n_ref : 0;
         A.cnt = reinterpret_cast<uint32_t *>(b0 + s_cnt.off); A.tot = reinterpret_cast<uint32_t *>(b0 + s_tot.off);
         A.base = reinterpret_cast<const uint64_t *>(b0 + s_base.off); A.arena = b0 + s_arena.off; A.status = reinterpret_cast<int32_t *>(b0 + s_st.off);
 #ifdef HGPU_HOSTSIM
@@ -400,7 +418,7 @@ int encode_impl(hgpu_ctx *ctx, const char *header_text, uint32_t header_len, con
         const uint64_t a = (uint64_t)sl * rps, b = a + rps < n ? a + rps : n;
         int64_t bases = 0;
         for (uint64_t g = a; g < b; g++) bases += core[g].l_qseq;
-        Buf ch; compression_header(ch, lines[sl], keys[sl]);
+        Buf ch; compression_header(ch, lines[sl], keys[sl], use_ref);
         Buf body;
         frame_block(body, 0, 1, 0, ch.v.data(), (uint32_t)ch.v.size(), (uint32_t)ch.v.size());
         const int32_t landmark = (int32_t)body.v.size();
@@ -438,16 +456,17 @@ int encode_impl(hgpu_ctx *ctx, const char *header_text, uint32_t header_len, con
 
 #ifdef HGPU_HOSTSIM
 extern "C" int hostsim_cram_encode_records(const char *header_text, uint32_t header_len, const hgpu_bam1_core *core, const uint8_t *data,
-        const uint64_t *data_off, uint64_t n, uint32_t rps, int minor, uint8_t **out_file, uint64_t *out_len)
+        const uint64_t *data_off, uint64_t n, const hgpu_cram_refs *refs, uint32_t rps, int minor, uint8_t **out_file, uint64_t *out_len)
 {
-    try { return encode_impl(nullptr, header_text, header_len, core, data, data_off, n, rps, minor, out_file, out_len); }
+    try { return encode_impl(nullptr, header_text, header_len, core, data, data_off, n, refs, rps, minor, out_file, out_len); }
     catch (...) { hgpu_set_error("internal error"); return HGPU_ERR_NOMEM; }
 }
 #else
 extern "C" int hgpu_cram_encode_records_host(hgpu_ctx *ctx, const char *header_text, uint32_t header_len, const hgpu_bam1_core *core,
-        const uint8_t *data, const uint64_t *data_off, uint64_t n, uint32_t records_per_slice, int minor_version, uint8_t **out_file, uint64_t *out_len)
+        const uint8_t *data, const uint64_t *data_off, uint64_t n, const hgpu_cram_refs *refs, uint32_t records_per_slice, int minor_version,
+        uint8_t **out_file, uint64_t *out_len)
 {
-    try { return encode_impl(ctx, header_text, header_len, core, data, data_off, n, records_per_slice, minor_version, out_file, out_len); }
+    try { return encode_impl(ctx, header_text, header_len, core, data, data_off, n, refs, records_per_slice, minor_version, out_file, out_len); }
     catch (const std::bad_alloc &) { hgpu_set_error("out of host memory"); return HGPU_ERR_NOMEM; }
     catch (...) { hgpu_set_error("internal error"); return HGPU_ERR_NOMEM; }
 }

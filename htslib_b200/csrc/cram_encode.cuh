@@ -30,7 +30,7 @@
 namespace cramenc {
 
 enum Stream { S_BF, S_CF, S_RI, S_RL, S_AP, S_RG, S_RN, S_MF, S_NS, S_NP, S_TS, S_TL, S_FN, S_FC, S_FP, S_DL, S_RS, S_HC, S_PD,
-              S_BB_LEN, S_BB, S_SC_LEN, S_SC, S_IN_LEN, S_IN, S_BA, S_QS, S_MQ, S_TAG_LEN, S_TAG_VAL, S_COUNT };
+              S_BB_LEN, S_BB, S_SC_LEN, S_SC, S_IN_LEN, S_IN, S_BA, S_QS, S_MQ, S_TAG_LEN, S_TAG_VAL, S_BS, S_COUNT };
 
 struct Core { int64_t pos; int32_t tid; uint16_t bin; uint8_t qual, l_extranul; uint16_t flag, l_qname; uint32_t n_cigar; int32_t l_qseq, mtid; int64_t mpos, isize; };
 
@@ -92,9 +92,81 @@ struct Emit {
     }
 };
 
-// One record.  tl = its tag-line index (the host built the dictionary).  Returns ENC_OK or why the slice cannot be written here.
+CRAMREC_HD inline uint8_t base_at(const uint8_t *seq4, uint32_t q) { return (uint8_t)"=ACMGRSVTWYHKDBN"[(seq4[q >> 1] >> ((~q & 1) << 2)) & 15]; }
+CRAMREC_HD inline int l1_row(uint8_t c) { return c == 'A' ? 0 : c == 'C' ? 1 : c == 'G' ? 2 : c == 'T' ? 3 : 4; }
+// substitution code of read base sb against reference base rb under the default matrix (rows CGTN AGTN ACTN ACGN ACGT): -1 = not expressible
+CRAMREC_HD inline int bs_code(uint8_t rb, uint8_t sb)
+{
+    const char *row = l1_row(rb) == 0 ? "CGTN" : l1_row(rb) == 1 ? "AGTN" : l1_row(rb) == 2 ? "ACTN" : l1_row(rb) == 3 ? "ACGN" : "ACGT";
+    for (int k = 0; k < 4; k++) if ((uint8_t)row[k] == sb) return k;
+    return -1;
+}
+
+// CIGAR (+ SEQ, + reference) -> read features.  EMIT = false only counts them (FN is written before the features).
+// ref != nullptr: match operations are compared with the reference (ref[0] = base 1 of the record's reference sequence):
+// equal bases leave no feature, a different A/C/G/T/N is a substitution 'X' (BS = its code in the reference base's row),
+// anything else a one-base 'b'.  ref == nullptr: every match operation is a 'b' run with its bases.
+template <bool WRITE, bool EMIT>
+CRAMREC_HD inline int features(const Core &c, const uint8_t *cig, uint32_t nc, const uint8_t *seq4, int32_t ls, bool noseq,
+                               const uint8_t *ref, int64_t ref_len, Emit<WRITE> &E, uint32_t &nf)
+{
+    uint32_t spos = 1, prev = 0, qlen = 0;
+    int64_t rpos = c.pos;
+    nf = 0;
+    for (uint32_t k = 0; k < nc; k++) {
+        const uint32_t w = cig[4 * k] | cig[4 * k + 1] << 8 | cig[4 * k + 2] << 16 | (uint32_t)cig[4 * k + 3] << 24;
+        const uint32_t op = w & 15, len = w >> 4;
+        if (len == 0) return ENC_UNSUPPORTED;                                  // zero-length ops do not survive the feature form
+        uint8_t code;
+        switch (op) {
+        case 0: case 7: case 8: code = 'b'; break;
+        case 1: code = 'I'; break;
+        case 2: code = 'D'; break;
+        case 3: code = 'N'; break;
+        case 4: code = 'S'; break;
+        case 5: code = 'H'; break;
+        default: code = 'P'; break;
+        }
+        if (code == 'b' && noseq) { spos += len; qlen += len; rpos += len; continue; }       // implicit match
+        if (code == 'b' && ref) {
+            if ((uint64_t)spos - 1 + len > (uint64_t)ls) return ENC_BAD;
+            for (uint32_t i = 0; i < len; i++) {
+                const uint8_t rb = rpos + i < ref_len ? ref[rpos + i] : (uint8_t)'N', sb = base_at(seq4, spos - 1 + i);
+                if (rb == sb) continue;
+                const int bs = bs_code(rb, sb);
+                nf++;
+                if (EMIT) {
+                    E.put_byte(S_FC, bs >= 0 ? 'X' : 'b');
+                    E.put_int(S_FP, (int32_t)(spos + i - prev));
+                    prev = spos + i;
+                    if (bs >= 0) E.put_byte(S_BS, (uint8_t)bs);
+                    else { E.put_int(S_BB_LEN, 1); E.put_byte(S_BB, sb); }
+                }
+            }
+            spos += len; qlen += len; rpos += len;
+            continue;
+        }
+        nf++;
+        if (EMIT) { E.put_byte(S_FC, code); E.put_int(S_FP, (int32_t)(spos - prev)); prev = spos; }
+        if (code == 'b' || code == 'I' || code == 'S') {
+            if (!noseq && (uint64_t)spos - 1 + len > (uint64_t)ls) return ENC_BAD;              // CIGAR longer than SEQ
+            const int ln = code == 'b' ? S_BB_LEN : code == 'I' ? S_IN_LEN : S_SC_LEN;
+            if (EMIT) { E.put_int(ln, (int32_t)len); if (noseq) E.put_fill(ln + 1, 'N', len); else E.put_bases(ln + 1, seq4, spos - 1, len); }
+            spos += len; qlen += len;
+            if (code == 'b') rpos += len;
+        } else {
+            if (EMIT) E.put_int(code == 'D' ? S_DL : code == 'N' ? S_RS : code == 'H' ? S_HC : S_PD, (int32_t)len);
+            if (code == 'D' || code == 'N') rpos += len;
+        }
+    }
+    if (!noseq && qlen != (uint32_t)ls) return ENC_BAD;                        // bam_set1 would refuse what the decoder rebuilds
+    return ENC_OK;
+}
+
+// One record.  tl = its tag-line index (the host built the dictionary).  ref / ref_len: the record's reference sequence
+// (nullptr: none).  Returns ENC_OK or why the slice cannot be written here.
 template <bool WRITE>
-CRAMREC_HD inline int walk(const Core &c, const uint8_t *data, uint32_t l_data, int32_t tl, Emit<WRITE> &E)
+CRAMREC_HD inline int walk(const Core &c, const uint8_t *data, uint32_t l_data, int32_t tl, const uint8_t *ref, int64_t ref_len, Emit<WRITE> &E)
 {
     const uint32_t lq = c.l_qname, nc = c.n_cigar;
     const int32_t ls = c.l_qseq;
@@ -141,38 +213,12 @@ CRAMREC_HD inline int walk(const Core &c, const uint8_t *data, uint32_t l_data, 
         p += 3 + vlen;
     }
     if (!unmapped) {
-        // CIGAR -> read features.  prev: position (1-based, in the read) of the previous feature
         uint32_t nf = 0;
-        for (uint32_t k = 0; k < nc; k++) { const uint32_t op = cig[4 * k] & 15; if (!(noseq && (op == 0 || op == 7 || op == 8))) nf++; }
+        int rc = features<WRITE, false>(c, cig, nc, seq4, ls, noseq, ref, ref_len, E, nf);
+        if (rc != ENC_OK) return rc;
         E.put_int(S_FN, (int32_t)nf);
-        uint32_t spos = 1, prev = 0, qlen = 0;
-        for (uint32_t k = 0; k < nc; k++) {
-            const uint32_t w = cig[4 * k] | cig[4 * k + 1] << 8 | cig[4 * k + 2] << 16 | (uint32_t)cig[4 * k + 3] << 24;
-            const uint32_t op = w & 15, len = w >> 4;
-            if (len == 0) return ENC_UNSUPPORTED;                              // zero-length ops do not survive the feature form
-            uint8_t code;
-            switch (op) {
-            case 0: case 7: case 8: code = 'b'; break;
-            case 1: code = 'I'; break;
-            case 2: code = 'D'; break;
-            case 3: code = 'N'; break;
-            case 4: code = 'S'; break;
-            case 5: code = 'H'; break;
-            default: code = 'P'; break;
-            }
-            if (noseq && code == 'b') { spos += len; qlen += len; continue; }   // implicit match
-            E.put_byte(S_FC, code);
-            E.put_int(S_FP, (int32_t)(spos - prev));
-            prev = spos;
-            if (code == 'b' || code == 'I' || code == 'S') {
-                if (!noseq && (uint64_t)spos - 1 + len > (uint64_t)ls) return ENC_BAD;  // CIGAR longer than SEQ
-                const int ln = code == 'b' ? S_BB_LEN : code == 'I' ? S_IN_LEN : S_SC_LEN;
-                E.put_int(ln, (int32_t)len);
-                if (noseq) E.put_fill(ln + 1, 'N', len); else E.put_bases(ln + 1, seq4, spos - 1, len);
-                spos += len; qlen += len;
-            } else E.put_int(code == 'D' ? S_DL : code == 'N' ? S_RS : code == 'H' ? S_HC : S_PD, (int32_t)len);
-        }
-        if (!noseq && qlen != (uint32_t)ls) return ENC_BAD;                    // bam_set1 would refuse what the decoder rebuilds
+        rc = features<WRITE, true>(c, cig, nc, seq4, ls, noseq, ref, ref_len, E, nf);
+        if (rc != ENC_OK) return rc;
         E.put_int(S_MQ, c.qual);
     } else E.put_bases(S_BA, seq4, 0, (uint32_t)ls);
     if (has_qual) E.put_bytes(S_QS, qual, (uint32_t)ls);

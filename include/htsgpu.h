@@ -444,21 +444,26 @@ int hgpu_bam_layout_dev(hgpu_ctx *ctx, const uint8_t *d_stream, uint64_t len,
                         const uint64_t *d_rec_off, uint64_t n,
                         uint64_t *d_data_off, uint64_t *d_seq_off, void *stream);
 
+/* the reference sequences of a file, for the CRAM record decoder and encoder: upper case, @SQ order, back to back */
+typedef struct hgpu_cram_refs { const uint8_t *bases; const uint64_t *off; int32_t n_ref; } hgpu_cram_refs;
+
 /* bam1_t records -> a complete CRAM 3.0 / 3.1 file image: the write side of the CRAM path (cram_encode_container /
- * cram_encode_slice cram/cram_encode.c:1950-2420, cram_encode_compression_header :380-1030, container and file framing
- * cram_io.c:3958-4100, :4694, :4889, :5512).  core / data / data_off: n records in hgpu_bam_unpack_dev's layout (host
- * arrays); header_text: the SAM header.  One slice of records_per_slice records (0 = 10 000) per container.  On the device:
- * per-record byte counts for each of the 30 series, a scan per (slice, series), the series bytes; then every series block
- * through the method trial of hgpu_cram_compress_blocks_host (rANS Nx16 family for minor_version 1, rANS 4x8 for 0) and
- * read names through the tok3 encoder (3.1), framed with CRC-32.  The file needs no reference to decode (RR = 0: bases and
- * qualities explicit, CIGAR as read features, every mate detached, multi-reference slices), so it is larger than what the
- * reference writes against a reference sequence; what the reference's reader returns for it is the input records, except
- * what CRAM cannot hold ('=' / 'X' CIGAR ops come back as 'M', MAPQ of unmapped reads as 0, RNEXT of unpaired reads as '*').
- * HGPU_CRAM_UNSUPPORTED: a mapped read without SEQ or position, or a zero-length CIGAR op (left to the host library).
- * *out_file is malloc'd. */
+ * cram_encode_slice cram/cram_encode.c:1950-2420, process_one_read :3490-4010, cram_encode_compression_header :380-1030,
+ * container and file framing cram_io.c:3958-4100, :4694, :4889, :5512).  core / data / data_off: n records in
+ * hgpu_bam_unpack_dev's layout (host arrays); header_text: the SAM header.  One slice of records_per_slice records
+ * (0 = 10 000) per container.  On the device: per-record byte counts for each of the 31 series, a scan per (slice,
+ * series), the series bytes; then every series block through the method trial of hgpu_cram_compress_blocks_host (rANS
+ * Nx16 family for minor_version 1, rANS 4x8 for 0) and read names through the tok3 encoder (3.1), framed with CRC-32.
+ * refs (may be NULL): with the reference sequence of every mapped record supplied, match operations are coded against
+ * it — equal bases leave nothing, a differing base is a substitution feature — and the file needs that reference to
+ * decode (RR = 1), as the reference's writer does; otherwise bases are explicit and the file decodes without one
+ * (RR = 0).  Every mate is written detached, slices are multi-reference.  What the reference's reader returns for the
+ * file is the input records, except what CRAM cannot hold ('=' / 'X' CIGAR ops come back as 'M', MAPQ of unmapped reads
+ * as 0, RNEXT of unpaired reads as '*').  HGPU_CRAM_UNSUPPORTED: a mapped read at position 0 or a zero-length CIGAR op
+ * (left to the host library).  *out_file is malloc'd. */
 int hgpu_cram_encode_records_host(hgpu_ctx *ctx, const char *header_text, uint32_t header_len, const hgpu_bam1_core *core,
-        const uint8_t *data, const uint64_t *data_off, uint64_t n, uint32_t records_per_slice, int minor_version,
-        uint8_t **out_file, uint64_t *out_len);
+        const uint8_t *data, const uint64_t *data_off, uint64_t n, const hgpu_cram_refs *refs, uint32_t records_per_slice,
+        int minor_version, uint8_t **out_file, uint64_t *out_len);
 
 /* CRAM 3.x record decode on the device — cram_decode_slice's record loop (cram/cram_decode.c:2340-3015), cram_decode_seq
  * (:1096-1917), cram_decode_aux (:2008-2137), cram_decode_slice_xref (:2140-2304) and cram_to_bam (:3100-3211) for every
@@ -477,7 +482,6 @@ int hgpu_cram_encode_records_host(hgpu_ctx *ctx, const char *header_text, uint32
  * from the container header was too small) / HGPU_CRAM_ERR_NOREF: the slice's records are empty and stay with the
  * host library.  slice_rec0[s]: first record of slice s (n_slices + 1 entries). */
 #define HGPU_CRAM_ERR_NOREF (-7)
-typedef struct hgpu_cram_refs { const uint8_t *bases; const uint64_t *off; int32_t n_ref; } hgpu_cram_refs;
 typedef struct hgpu_cram_records {
     uint64_t n_records, data_bytes;
     uint32_t n_slices, pad;

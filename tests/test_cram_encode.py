@@ -29,20 +29,30 @@ def pack(records):
     return core, data, off
 
 
-def encode(entry_ctx, text, records, rps, minor):
+def sq_names(text):
+    return [[f[3:] for f in line.split(b"\t") if f.startswith(b"SN:")][0] for line in text.split(b"\n") if line.startswith(b"@SQ\t")]
+
+
+def encode(entry_ctx, text, records, rps, minor, fasta_path=None):
     core, data, off = pack(records)
     out, ln = C.c_void_p(), C.c_uint64(0)
+    refs, keep = None, None
+    if fasta_path:
+        keep = H.load_fasta_upper(fasta_path, sq_names(text))
+        refs = H.CramRefs()
+        refs.bases = keep[0].ctypes.data; refs.off = keep[1].ctypes.data; refs.n_ref = len(keep[1]) - 1
+    rp = C.byref(refs) if refs is not None else None
     if entry_ctx is None:
         so = T.hostsim()                                    # builds / refreshes the harness
         l = C.CDLL(os.path.join(T.HERE, "hostsim", "_build", "libcramrec_hostsim.so"))
-        l.hostsim_cram_encode_records.argtypes = [C.c_char_p, C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.c_uint32, C.c_int, C.c_void_p, C.c_void_p]
+        l.hostsim_cram_encode_records.argtypes = [C.c_char_p, C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p, C.c_uint32, C.c_int, C.c_void_p, C.c_void_p]
         l.hostsim_enc_last_error.restype = C.c_char_p
-        rc = l.hostsim_cram_encode_records(text, len(text), core.ctypes.data, data.ctypes.data, off.ctypes.data, len(records), rps, minor, C.byref(out), C.byref(ln))
+        rc = l.hostsim_cram_encode_records(text, len(text), core.ctypes.data, data.ctypes.data, off.ctypes.data, len(records), rp, rps, minor, C.byref(out), C.byref(ln))
         err = lambda: l.hostsim_enc_last_error().decode()
     else:
         L = H.lib()
-        L.hgpu_cram_encode_records_host.argtypes = [C.c_void_p, C.c_char_p, C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.c_uint32, C.c_int, C.c_void_p, C.c_void_p]
-        rc = L.hgpu_cram_encode_records_host(entry_ctx.h, text, len(text), core.ctypes.data, data.ctypes.data, off.ctypes.data, len(records), rps, minor, C.byref(out), C.byref(ln))
+        L.hgpu_cram_encode_records_host.argtypes = [C.c_void_p, C.c_char_p, C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p, C.c_uint32, C.c_int, C.c_void_p, C.c_void_p]
+        rc = L.hgpu_cram_encode_records_host(entry_ctx.h, text, len(text), core.ctypes.data, data.ctypes.data, off.ctypes.data, len(records), rp, rps, minor, C.byref(out), C.byref(ln))
         err = H.last_error
     if rc != 0:
         return rc, err()
@@ -67,14 +77,15 @@ def expected(c, d):
     return tuple(c[f] for f in NAMES), bytes(d)
 
 
-def roundtrip(tmp_path, entry_ctx, sam, rps, minor):
+def roundtrip(tmp_path, entry_ctx, sam, rps, minor, with_ref=False):
     text, recs = ref_read_sam_records(os.path.join(HT, "sam", sam + ".sam"))
-    rc, img = encode(entry_ctx, text, recs, rps, minor)
+    fa = os.path.join(HT, sam.split("#")[0] + ".fa") if with_ref else None
+    rc, img = encode(entry_ctx, text, recs, rps, minor, fa)
     if rc != 0:
         return rc, img
-    out = str(tmp_path / ("%s.%d.%d.cram" % (sam.replace("#", "_"), rps, minor)))
+    out = str(tmp_path / ("%s.%d.%d.%d.cram" % (sam.replace("#", "_"), rps, minor, with_ref)))
     open(out, "wb").write(img)
-    back = ref_cram_read_all(out, None, 0)
+    back = ref_cram_read_all(out, fa, 0)
     assert len(back) == len(recs), (sam, len(back), len(recs))
     for i, ((gc, gd), (wc, wd)) in enumerate(zip(back, recs)):
         ec, ed = expected(wc, wd)
@@ -84,13 +95,15 @@ def roundtrip(tmp_path, entry_ctx, sam, rps, minor):
 
 
 @pytest.mark.skipif(ref() is None, reason="oracle/_ref not built")
-@pytest.mark.parametrize("rps,minor", [(0, 0), (3, 1)])
+@pytest.mark.parametrize("rps,minor,with_ref", [(0, 0, False), (3, 1, False), (0, 1, True), (2, 0, True)])
 @pytest.mark.parametrize("sam", SAMS)
-def test_hostsim_reference_reads_back_what_we_wrote(tmp_path, sam, rps, minor):
-    rc, img = roundtrip(tmp_path, None, sam, rps, minor)
+def test_hostsim_reference_reads_back_what_we_wrote(tmp_path, sam, rps, minor, with_ref):
+    rc, img = roundtrip(tmp_path, None, sam, rps, minor, with_ref)
     if rc != 0:
         assert rc == -6, (sam, rc, img)            # HGPU_CRAM_UNSUPPORTED: mapped reads without SEQ etc., by contract
         pytest.skip("left to the host library: " + img)
+    if with_ref:
+        return
     # and our own record decoder (hostsim) reads the file back to the same records
     arr = np.frombuffer(img, dtype=np.uint8).copy()
     blocks, udata, off = T.cpu_blocks(arr)
@@ -109,16 +122,20 @@ def test_hostsim_synthetic_10000_reads(tmp_path):
     n = T._synthetic_sam(sam, n=10000, seed=21)
     text, recs = ref_read_sam_records(sam)
     assert len(recs) == n
-    for rps, minor in ((0, 1), (1500, 0)):
-        rc, img = encode(None, text, recs, rps, minor)
+    sizes = {}
+    for rps, minor, fa in ((0, 1, None), (1500, 0, None), (0, 1, os.path.join(HT, "ce.fa"))):
+        rc, img = encode(None, text, recs, rps, minor, fa)
         assert rc == 0, img
         out = str(tmp_path / "syn.cram")
         open(out, "wb").write(img)
-        back = ref_cram_read_all(out, None, 0)
+        back = ref_cram_read_all(out, fa, 0)
         assert len(back) == n
         for i, ((gc, gd), (wc, wd)) in enumerate(zip(back, recs)):
             ec, ed = expected(wc, wd)
             assert gc == ec and gd == ed, (i, dict(zip(NAMES, gc)), dict(zip(NAMES, ec)))
+        sizes[(rps, fa is not None)] = len(img)
+    # coded against the reference, the bases all but disappear (blocks are RAW here: ~100 bytes of bases per read become a few)
+    assert sizes[(0, True)] < 0.75 * sizes[(0, False)], sizes
 
 
 @pytest.mark.gpu
@@ -128,25 +145,28 @@ def test_gpu_reference_reads_back_what_we_wrote(tmp_path, minor):
     ctx = H.Context(0)
     done = 0
     for sam in SAMS:
-        rc, img = roundtrip(tmp_path, ctx, sam, 3 if minor else 0, minor)
-        assert rc in (0, -6), (sam, rc, img)
-        done += rc == 0
-    assert done >= 28
+        for with_ref in (False, True):
+            rc, img = roundtrip(tmp_path, ctx, sam, 3 if minor else 0, minor, with_ref)
+            assert rc in (0, -6), (sam, rc, img)
+            done += rc == 0
+    assert done >= 60
     # a 10 000-read slice: compressed by the device codecs, smaller than the records, read back by the reference
     sam = str(tmp_path / "syn.sam")
     n = T._synthetic_sam(sam, n=10000, seed=21)
     text, recs = ref_read_sam_records(sam)
-    rc, img = encode(ctx, text, recs, 0, minor)
-    assert rc == 0, img
-    out = str(tmp_path / "syn.cram")
-    open(out, "wb").write(img)
-    back = ref_cram_read_all(out, None, 0)
-    assert len(back) == n
-    for i, ((gc, gd), (wc, wd)) in enumerate(zip(back, recs)):
-        ec, ed = expected(wc, wd)
-        assert gc == ec and gd == ed, i
     raw = sum(len(d) + 32 for _, d in recs)
-    assert len(img) < 0.45 * raw, (len(img), raw)
+    for fa, bound in ((None, 0.45), (os.path.join(HT, "ce.fa"), 0.36)):
+        rc, img = encode(ctx, text, recs, 0, minor, fa)
+        assert rc == 0, img
+        out = str(tmp_path / "syn.cram")
+        open(out, "wb").write(img)
+        back = ref_cram_read_all(out, fa, 0)
+        assert len(back) == n
+        for i, ((gc, gd), (wc, wd)) in enumerate(zip(back, recs)):
+            ec, ed = expected(wc, wd)
+            assert gc == ec and gd == ed, i
+        assert len(img) < bound * raw, (fa, len(img), raw)
+    rc, img = encode(ctx, text, recs, 0, minor, None)
     blocks, _ = H.cram_scan_blocks(np.frombuffer(img, dtype=np.uint8).copy())
     methods = set(int(m) for m in blocks["method"])
     assert (5 in methods and 8 in methods) if minor else (4 in methods), methods

@@ -119,12 +119,12 @@ def run(ctx, reads=100000, tiles=20, cpu=True, decode_md=0):
     try:
         header = b"".join(l for l in open(sam, "rb") if l.startswith(b"@"))
         ne = min(nrec, n * 10)
-        L.hgpu_cram_encode_records_host.argtypes = [C.c_void_p, C.c_char_p, C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.c_uint32, C.c_int, C.c_void_p, C.c_void_p]
+        L.hgpu_cram_encode_records_host.argtypes = [C.c_void_p, C.c_char_p, C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p, C.c_uint32, C.c_int, C.c_void_p, C.c_void_p]
         best_e = None
         for it in range(2):
             eo, el = C.c_void_p(), C.c_uint64(0)
             t0 = time.perf_counter()
-            rc = L.hgpu_cram_encode_records_host(ctx.h, header, len(header), out_s.core, out_s.data, out_s.data_off, ne, 10000, 1, C.byref(eo), C.byref(el))
+            rc = L.hgpu_cram_encode_records_host(ctx.h, header, len(header), out_s.core, out_s.data, out_s.data_off, ne, C.byref(refs), 10000, 1, C.byref(eo), C.byref(el))
             sec = time.perf_counter() - t0
             assert rc == 0, H.last_error()
             img_e = C.string_at(eo.value, el.value)
@@ -133,13 +133,13 @@ def run(ctx, reads=100000, tiles=20, cpu=True, decode_md=0):
                 best_e = sec
         enc_path = os.path.join(tmp, "enc.cram")
         open(enc_path, "wb").write(img_e)
-        back = ref_cram_read_all(enc_path, None, 0)
+        back = ref_cram_read_all(enc_path, os.path.join(HT, "ce.fa"), 0)
         assert len(back) == ne
         for i in (0, 1, ne // 2, ne - 1):
             lqn = int(core[i]["l_qname"])
             assert back[i][0][:3] == tuple(int(core[i][f]) for f in names[:3]) and back[i][1][:lqn] == blob[int(doff[i]):int(doff[i]) + lqn].tobytes(), i
         in_bytes = int(doff[ne]) + 48 * ne
-        res["encode"] = {"workload": "the first %d decoded records back into a CRAM 3.1 file (no-reference shape: bases and qualities explicit), 10 000 records per slice" % ne,
+        res["encode"] = {"workload": "the first %d decoded records back into a CRAM 3.1 file (coded against the reference: substitution features), 10 000 records per slice" % ne,
                          "records": ne, "bam_bytes_in": in_bytes, "cram_bytes_out": len(img_e), "ratio": len(img_e) / in_bytes,
                          "wall_s": best_e, "records_per_s_e2e": ne / best_e,
                          "api": "hgpu_cram_encode_records_host (host buffers; series split + rANS Nx16 trial + tok3 names on the device)",
