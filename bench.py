@@ -527,8 +527,8 @@ def run_ours(args):
                      "peak_source": how,
                      "traffic_note": "dram__bytes_read.sum + dram__bytes_write.sum of one launch from the committed ncu --set full capture of "
                                      "`python bench.py --gb 10` (profiles/r2_inflate_ncu_summary.txt); null when this run's launch is a different size. "
-                                     "3.2x the algorithmic bytes: the 8-byte match records make a DRAM round trip (~14 GB) and the CRC pass re-reads "
-                                     "the output (~9.7 GB) because 16 warps/SM x (64 KiB window + records) exceeds the 126 MB L2 (DESIGN.md 6)",
+                                     "3.6x the algorithmic bytes: the 8-byte match records make a DRAM round trip (~14 GB) and the CRC pass re-reads "
+                                     "the output (~9.7 GB) because 21 warps/SM x (64 KiB window + records) exceeds the 126 MB L2 (DESIGN.md 6)",
                      "traffic_capture": cap},
         "gpu_launches": int(launches),
         "clocks": clocks,
