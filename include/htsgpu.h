@@ -84,8 +84,9 @@ int hgpu_bgzf_inflate_jobs_host(hgpu_ctx *ctx, uint32_t n, const uint8_t *const 
  * (bgzf.c:624-683, :709, :1330) for a batch of payloads (each <= 65280 bytes; htslib uses
  * BGZF_BLOCK_SIZE 0xff00), one warp per payload.  Every out slot is 65536 bytes, 4-byte aligned;
  * out_len[i] receives the BGZF block length.  level 0 = stored block (bgzf.c:573-580), level >= 1 =
- * LZ77 + fixed-Huffman DEFLATE with stored fallback.  Output inflates to the input with any
- * RFC 1951 inflater; bytes differ from zlib's (stated ratio in tests/test_gpu_bgzf_compress.py). */
+ * LZ77 tokens coded by the smallest of a dynamic-Huffman block (code lengths built per block on the device), a
+ * fixed-Huffman block and a stored block.  Output inflates to the input with any RFC 1951 inflater; bytes differ
+ * from zlib's (stated ratio in tests/test_gpu_bgzf_compress.py: 1.21x the zlib level-6 size on sorted BAM). */
 int hgpu_bgzf_compress_batch_dev(hgpu_ctx *ctx,
         const uint8_t *d_in, const uint64_t *d_in_off, const uint32_t *d_in_len, uint32_t n, int level,
         uint8_t *d_out, const uint64_t *d_out_off, uint32_t *d_out_len, int32_t *d_status, void *stream);
@@ -275,10 +276,9 @@ long hgpu_cram_parse_slice_header(const uint8_t *payload, uint32_t len, int majo
  * arithmetic, 7 fqzcomp, 8 tok3; RAW is a host copy.  status[i]: HGPU_OK; HGPU_CRAM_ERR_CRC (block CRC32 failure);
  * HGPU_CRAM_ERR_DECODE (the reference returns -1: codec failure or size mismatch); HGPU_CRAM_ERR_SPACE
  * (a tok3 block longer than its uncomp_size field — the reference adopts the new size, a fixed slot
- * cannot); HGPU_CRAM_UNSUPPORTED for BZIP2 / LZMA blocks and for GZIP blocks that are not one plain gzip member
- * of at most 64 KiB, which stay with the host library (small GZIP blocks — compression headers, tiny data
- * series — are re-framed as BGZF blocks and go through the BGZF inflate kernel).  Method 7 (FQZ) blocks go to
- * the fqzcomp batch decoder.
+ * cannot); HGPU_CRAM_UNSUPPORTED for BZIP2 / LZMA blocks, which stay with the host library.  GZIP blocks (method 1) of
+ * any size go through gzip_inflate_kernel (RFC 1952 header walk, multi-block members; CRC-32 and ISIZE checked), method 7
+ * (FQZ) blocks to the fqzcomp batch decoder.
  * got_len[i]: bytes written. */
 #define HGPU_CRAM_ERR_DECODE  (-1)
 #define HGPU_CRAM_ERR_CRC     (-2)
