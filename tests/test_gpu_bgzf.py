@@ -165,3 +165,28 @@ def test_large_file_roundtrip_property(ctx):
     assert zlib.crc32(out[:text.size].tobytes()) == zlib.crc32(text.tobytes())
     v = out.reshape(reps, text.size)
     assert (v == v[0]).all()
+
+
+@pytest.mark.parametrize("name", ["fail_block_3331.npy", "fail_block_6735.npy"])
+def test_false_end_of_block_in_the_preroll_regression(ctx, name):
+    """Two blocks of the 0.5 GB synthetic corpus that once failed their CRC: a sub-range decoder's 128-bit pre-roll ran into
+    a false end-of-block code whose exit coincided with the true token start, so the chain looked consistent.  The failure
+    depended on where the block sat in memory: every 16-byte phase of the input is tried, through the file path."""
+    import zlib
+    blk = np.load(os.path.join(GOLD, "bgzf_regress", name)).tobytes()
+    want = zlib.decompress(blk[18:-8], -15)
+    rng = random.Random(3)
+    for phase in range(16):
+        # a leading block whose compressed length puts `blk` at the wanted phase
+        for _ in range(400):
+            lead_payload = bytes(rng.randrange(256) for _ in range(rng.randrange(1, 200)))
+            lead = bgzf_block(lead_payload)
+            if len(lead) % 16 == phase:
+                break
+        else:
+            pytest.skip("no leading block of phase %d found" % phase)
+        img = np.frombuffer(lead + blk + BGZF_EOF, dtype=np.uint8).copy()
+        out = np.zeros(len(lead_payload) + len(want) + 64, dtype=np.uint8)
+        rc, n, bad = ctx.bgzf_inflate_file_host(img, out)
+        assert rc == 0 and n == len(lead_payload) + len(want), (phase, rc, n, bad)
+        assert out[:n].tobytes() == lead_payload + want, phase
