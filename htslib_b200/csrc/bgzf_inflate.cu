@@ -1272,6 +1272,12 @@ __device__ uint32_t deflate_block_warp(DeflateSmem &s, const uint32_t (*crc_tab)
                 }
                 if (nm < 32 && base + nm < cend) {
                     uint32_t ml = __shfl_sync(0xffffffffu, mlen, nm), md = __shfl_sync(0xffffffffu, mdist, nm);
+                    // lazy evaluation (deflate.c's deflate_slow, one step): a strictly longer match starting at the next byte
+                    // wins; this byte goes out as a literal
+                    if (level >= 4 && nm < 31 && base + nm + 1 < cend) {
+                        const uint32_t ml1 = __shfl_sync(0xffffffffu, mlen, (nm + 1) & 31);
+                        if (ml1 > ml + 1) { has &= ~(1u << nm); continue; }
+                    }
                     if (lane == 0 && ntok < DEFL_TOK_CAP) toks[ntok] = 0x80000000u | (ml - 3) | ((md - 1) << 8);
                     ntok++;
                     cur = base + nm + ml;

@@ -86,7 +86,8 @@ int hgpu_bgzf_inflate_jobs_host(hgpu_ctx *ctx, uint32_t n, const uint8_t *const 
  * out_len[i] receives the BGZF block length.  level 0 = stored block (bgzf.c:573-580), level >= 1 =
  * LZ77 tokens coded by the smallest of a dynamic-Huffman block (code lengths built per block on the device), a
  * fixed-Huffman block and a stored block.  Output inflates to the input with any RFC 1951 inflater; bytes differ
- * from zlib's (stated ratio in tests/test_gpu_bgzf_compress.py: 1.21x the zlib level-6 size on sorted BAM). */
+ * from zlib's (stated ratio in tests/test_gpu_bgzf_compress.py: 1.12x the zlib level-6 size on sorted BAM at level >= 4,
+ * where one step of lazy match evaluation is on). */
 int hgpu_bgzf_compress_batch_dev(hgpu_ctx *ctx,
         const uint8_t *d_in, const uint64_t *d_in_off, const uint32_t *d_in_len, uint32_t n, int level,
         uint8_t *d_out, const uint64_t *d_out_off, uint32_t *d_out_len, int32_t *d_status, void *stream);

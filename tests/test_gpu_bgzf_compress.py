@@ -42,13 +42,14 @@ def test_roundtrip_every_decoder(ctx, level):
 
 
 def test_size_ratio_on_bam(ctx):
-    """Stated ratio: <= 1.4x the zlib level-6 size on the synthetic sorted-BAM corpus (dynamic Huffman codes per block,
-    single-probe greedy LZ77 vs zlib's chained, lazy search; 1.21x on the bench corpus, 1.39x with fixed codes)."""
+    """Stated ratio: <= 1.3x the zlib level-6 size on the synthetic sorted-BAM corpus (dynamic Huffman codes per block,
+    single-probe LZ77 with one step of lazy evaluation vs zlib's chained search; measured 1.12x here, 1.39x with fixed
+    codes and greedy matching in round 1)."""
     stream, offs = synth.bam_records(11, 6000)
     ps = [stream[i:i + 0xff00] for i in range(0, len(stream), 0xff00)]
     blocks = ctx.bgzf_compress(ps, 6)
     mine = sum(len(b) for b in blocks)
     theirs = sum(len(synth.bgzf_block(p, 6)) for p in ps)
     assert b"".join(zlib.decompress(b[18:-8], -15) for b in blocks) == stream
-    assert mine <= 1.4 * theirs, (mine, theirs, len(stream))
+    assert mine <= 1.3 * theirs, (mine, theirs, len(stream))
     print("deflate ratio: ours %.3f zlib6 %.3f" % (mine / len(stream), theirs / len(stream)))
