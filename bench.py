@@ -390,7 +390,7 @@ def run_ours(args):
 
     # ---- BAM record unpack over the inflated stream, still on the device (configs[3] front half) ----
     bam_extra = None
-    if world == 1:
+    if True:                                                     # every rank: its own shard (times = max over ranks below)
         try:
             torch.cuda.synchronize()
             t0 = time.perf_counter()
@@ -413,7 +413,24 @@ def run_ours(args):
                          "records_per_s": n_rec / ms * 1e3, "value": U / ms / 1e6, "unit": "GB/s (input stream)",
                          "roofline": {"bound": "hbm", "achieved": (U + written) / ms / 1e6, "peak": hbm, "unit": "GB/s",
                                       "frac": (U + written) / ms / 1e6 / hbm, "traffic": None, "peak_source": how}}
-            assert n_rec == corpus["n_reads"] and bad == 0
+            assert bad == 0 and (world > 1 or n_rec == corpus["n_reads"])
+            # ---- BAM -> SAM text (configs[3]): sam_format1 of every record on the device ----
+            try:
+                text, t_off, t_st = ctx.sam_format_dev(r["core"], r["data"], r["data_off"], n_rec, [b"chr1"], stream)
+                torch.cuda.synchronize()
+                del text, t_off
+                ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                ev0.record()
+                text, t_off, t_st = ctx.sam_format_dev(r["core"], r["data"], r["data_off"], n_rec, [b"chr1"], stream)
+                ev1.record()
+                torch.cuda.synchronize()
+                sms = ev0.elapsed_time(ev1)
+                bam_extra["sam_text"] = {"ms": sms, "text_bytes": int(text.numel()), "text_GBps": int(text.numel()) / sms / 1e6,
+                                         "records_per_s": n_rec / sms * 1e3, "flagged_for_host": int((t_st != 0).sum().item()),
+                                         "includes": "layout pass, one D2H of the total, output allocation, write pass (hgpu_sam_format_dev twice)"}
+                del text, t_off, t_st
+            except Exception as ex:
+                bam_extra["sam_text"] = {"error": repr(ex)}
             # ---- write half of the BAM round trip (configs[3]): pack (bam_write1) + BGZF compress ----
             try:
                 packed, pk_off, pk_st = ctx.bam_pack_dev(r["core"], r["data"], r["data_off"], n_rec, stream)
@@ -458,6 +475,31 @@ def run_ours(args):
         except Exception as ex:
             bam_extra = {"error": repr(ex)}
 
+    if world > 1:
+        # every rank reaches this all-reduce whatever happened above: times become the max over ranks, rates the aggregate
+        v = [0.0, 0.0, 0.0, 0.0, 0.0]
+        try:
+            if bam_extra and "ms" in bam_extra:
+                v = [1.0, bam_extra["ms"], bam_extra.get("sam_text", {}).get("ms", 0.0), bam_extra.get("write_half", {}).get("pack_ms", 0.0),
+                     bam_extra.get("write_half", {}).get("deflate_ms", 0.0)]
+        except Exception:
+            pass
+        tt = torch.tensor(v, dtype=torch.float64, device=dev)
+        mn = tt.clone()
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        dist.all_reduce(mn, op=dist.ReduceOp.MIN)
+        if bam_extra and "ms" in bam_extra and float(mn[0].item()) == 1.0:
+            ms_u, ms_s, ms_p, ms_d = (float(x) for x in tt[1:].tolist())
+            bam_extra.update({"n_gpus": world, "ms": ms_u, "records_per_s": world * bam_extra["records"] / ms_u * 1e3, "value": world * U / ms_u / 1e6,
+                              "unit": "GB/s (input stream, all GPUs)", "aggregation": "every rank unpacks its own inflated shard; time = max over ranks"})
+            if ms_s and "ms" in bam_extra.get("sam_text", {}):
+                bam_extra["sam_text"].update({"ms": ms_s, "text_GBps": world * bam_extra["sam_text"]["text_bytes"] / ms_s / 1e6,
+                                              "records_per_s": world * bam_extra["records"] / ms_s * 1e3})
+            if ms_p and "pack_ms" in bam_extra.get("write_half", {}):
+                bam_extra["write_half"].update({"pack_ms": ms_p, "pack_GBps": world * U / ms_p / 1e6, "deflate_ms": ms_d, "deflate_GBps": world * U / ms_d / 1e6})
+        elif bam_extra is not None and "error" not in bam_extra:
+            bam_extra = {"error": "a rank failed this leg"}
+
     d_out_keep = d_out
     # ---- e2e: host buffers through the C-ABI file entry point ----
     e2e = None
@@ -501,6 +543,33 @@ def run_ours(args):
         rans = rans_legs(args, ctx, torch, dev, world, dist)
     except Exception as ex:
         rans = {"error": repr(ex)}
+    # ---- CRAM record decode + encode (configs[4] shape), every rank on its own copy of the reference-written file ----
+    cram = None
+    if args.cram_tiles > 0:
+        try:
+            sys.path.insert(0, os.path.join(ROOT, "tools"))
+            sys.path.insert(0, os.path.join(ROOT, "tests"))
+            import cram_records_bench
+            cram = cram_records_bench.run(ctx, 100000, args.cram_tiles if world == 1 else max(10, args.cram_tiles // 2),
+                                          cpu=(world == 1 and not args.no_cpu_baseline))
+        except Exception as ex:
+            cram = {"error": repr(ex)}
+        if world > 1:
+            v = [0.0, 0.0, 0.0, 0.0]
+            if cram and "records" in cram:
+                v = [1.0, cram["slice_decode_ms"] + cram["bam_fill_ms"], cram["e2e_wall_s"], cram.get("encode", {}).get("wall_s", 0.0)]
+            tt = torch.tensor(v, dtype=torch.float64, device=dev)
+            mn = tt.clone()
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+            dist.all_reduce(mn, op=dist.ReduceOp.MIN)
+            if cram and "records" in cram and float(mn[0].item()) == 1.0:
+                dms, wall, ewall = (float(x) for x in tt[1:].tolist())
+                cram.update({"n_gpus": world, "records_per_s_device": world * cram["records"] / dms * 1e3, "records_per_s_e2e": world * cram["records"] / wall,
+                             "aggregation": "every rank decodes its own copy; times = max over ranks"})
+                if ewall and "records" in cram.get("encode", {}):
+                    cram["encode"].update({"wall_s": ewall, "records_per_s_e2e": world * cram["encode"]["records"] / ewall})
+            elif cram is not None and "error" not in cram:
+                cram = {"error": "a rank failed this leg"}
     if rank != 0:
         return
     hbm, how = peaks()
@@ -554,14 +623,8 @@ def run_ours(args):
                 out.setdefault("extra", {})["tok3_decode"] = tl
         except Exception as ex:
             out.setdefault("extra", {})["tok3_decode"] = {"error": repr(ex)}
-        if args.cram_tiles > 0:
-            try:
-                sys.path.insert(0, os.path.join(ROOT, "tools"))
-                sys.path.insert(0, os.path.join(ROOT, "tests"))
-                import cram_records_bench
-                out.setdefault("extra", {})["cram_records"] = cram_records_bench.run(ctx, 100000, args.cram_tiles, cpu=not args.no_cpu_baseline)
-            except Exception as ex:
-                out.setdefault("extra", {})["cram_records"] = {"error": repr(ex)}
+    if cram is not None:
+        out.setdefault("extra", {})["cram_records"] = cram
     print(json.dumps(out), flush=True)
 
 
